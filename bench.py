@@ -1,0 +1,302 @@
+#!/usr/bin/env python3
+"""bench.py -- Msamples/s of the per-sample render loop (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2]
+
+A "step" is one Tracer::render call over one frame of the workload (default C2: cornell2.json.gz,
+1920x1080 at 256 spp = 64 passes x Subpixel(2), 530.8 Msamples).  At N > 1 (torchrun, one rank per
+GPU) every rank renders a disjoint slice of the global pass range of the same frame size and the
+slices are summed with ONE NCCL reduce inside the step (weak scaling: per-GPU work fixed).
+Rank 0 prints ONE JSON line.  `--impl reference` times the reference algorithm's CPU restatement
+(oracle/, kind "port": the Rust crate cannot be built here) on a bounded sample of the same frame.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (scene, width, height, passes, subsample, lens (x, y, z, r_s) or None)
+    "C1": ("cornell", 512, 512, 4, 2, None),
+    "C2": ("cornell2", 1920, 1080, 64, 2, None),
+    "C3": ("scene", 3840, 2160, 16, 2, (1.362, 1.577, 6.114, 0.2)),
+    "C4-cloud": ("cloud", 1920, 1080, 64, 2, None),
+    "C4-volume": ("volume", 1920, 1080, 64, 2, None),
+}
+METRIC = "Msamples/s"
+SCENE_DIR = os.path.join(ROOT, "tests", "golden", "scenes")
+FLOPS_RECT, FLOPS_SPHERE = 35, 25      # SURVEY 8d per-test algorithmic flops
+PRIMS = {"cornell": (18, 0), "cornell2": (18, 0), "scene": (0, 5), "volume": (0, 4), "cloud": (0, 4)}
+
+
+def describe(name):
+    scene, w, h, passes, sub, lens = WORKLOADS[name]
+    spp = passes * max(sub, 1) ** 2
+    return {"workload": f"{name}: {scene}.json.gz {w}x{h} at {spp} spp ({passes} passes x Subpixel({sub}))"
+                        + (f" + lens r_s={lens[3]}" if lens else ""),
+            "scene": scene, "width": w, "height": h, "spp": spp}
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock + throttle reasons with NVML during the timed region"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.mhz, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.mhz.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.05)
+        except Exception as e:  # NVML missing: report it instead of inventing clocks
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.mhz)) if self.mhz else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def load_oracle_scene(name):
+    import oracle_ffi as O
+    scene, w, h, passes, sub, lens = WORKLOADS[name]
+    osc = O.OracleScene.load(os.path.join(SCENE_DIR, scene + ".json.gz"))
+    cam = osc.find_by_tag("camera")
+    osc.set_camera_aspect(cam, float(np.float32(w) / np.float32(h)))
+    if lens:
+        osc.set_lenses(np.array([lens], np.float32))
+    return O, osc, cam
+
+
+def cpu_sample(name, passes):
+    """the reference algorithm (CPU restatement, all host threads) on `passes` passes of the frame"""
+    O, osc, cam = load_oracle_scene(name)
+    scene, w, h, _, sub, _ = WORKLOADS[name]
+    cores = os.cpu_count() or 1
+    cfg = O.make_config(samples=passes, subsample=sub)
+    t0 = time.perf_counter()
+    _, n, _ = osc.render(cam, cfg, w, h, seed=0, n_threads=cores)
+    dt = time.perf_counter() - t0
+    return w * h * n / dt / 1e6, cores, n, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the box's host cores"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload
+    d = describe(name)
+    passes = 1  # bounded sample: 1 pass x Subpixel(2) = 4 spp of the frame per step
+    for _ in range(args.warmup):
+        cpu_sample(name, passes)
+    vals, t = [], 0.0
+    for _ in range(args.steps):
+        v, cores, n, dt = cpu_sample(name, passes)
+        vals.append(v)
+        t += dt
+    value = d["width"] * d["height"] * n * args.steps / t / 1e6
+    sample = f"{n} spp of the {d['width']}x{d['height']} frame per step (the full step is {d['spp']} spp)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {k: d[k] for k in ("workload",)},
+        "cpu_baseline": {"value": value, "unit": METRIC, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference algorithm restated in C++ (oracle/), all host threads; the Rust crate cannot be built here",
+    }))
+
+
+def stepper_roofline(engine, torch, peak_tflops, n_rays=1 << 22, n_steps=512):
+    """SURVEY 8d stepper micro-benchmark: rays past M point masses, fixed RK4 step count"""
+    out = {}
+    rng = np.random.default_rng(1234)
+    b = rng.uniform(2.6, 40.0, n_rays)
+    phi = rng.uniform(0, 2 * np.pi, n_rays)
+    xv = np.zeros((n_rays, 6), np.float32)
+    xv[:, 0], xv[:, 1], xv[:, 2], xv[:, 5] = b * np.cos(phi), b * np.sin(phi), 20.0, -1.0
+    for m in (1, 4, 16):
+        lenses = np.zeros((m, 4), np.float32)
+        lenses[:, :3] = rng.uniform(-3, 3, (m, 3))
+        lenses[0, :3] = 0
+        lenses[:, 3] = 1.0 / m
+        d_xv = torch.from_numpy(xv).cuda()
+        engine.geodesic_integrate(lenses, d_xv, 16)  # warm-up
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(3):
+            d_xv.copy_(torch.from_numpy(xv))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            engine.geodesic_integrate(lenses, d_xv, n_steps)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        flops = float(n_rays) * n_steps * (136 * m + 78)   # F_step(M), SURVEY 8d
+        tf = flops / (best * 1e-3) / 1e12
+        out[f"M{m}"] = {"tflops": tf, "frac": tf / peak_tflops, "ms": best, "steps_per_s": n_rays * n_steps / (best * 1e-3)}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / stepper roofline / e2e legs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import bendy_tracer_b200 as bt
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    name = args.workload
+    scene_name, w, h, passes, sub, lens = WORKLOADS[name]
+    d = describe(name)
+    scene = bt.Scene.load(os.path.join(SCENE_DIR, scene_name + ".json.gz"))
+    cam = scene.find_by_tag("camera")
+    scene.set_camera_aspect(cam, float(np.float32(w) / np.float32(h)))
+    if lens:
+        scene.set_lenses(np.array([lens], np.float32))
+    engine = bt.Engine.default(local)
+    tracer = bt.Tracer(bt.Config(chunks_x=8, chunks_y=4), engine=engine, seed=0)
+    rc = bt.RenderConfig.with_samples_subsample(passes, bt.Subsample(sub))
+    frame = bt.Buffer(w, h, device=dev)       # this rank's slice of the frame
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(i):
+        frame.clear()
+        # rank r renders global passes [r*passes, (r+1)*passes) of step i's frame
+        tracer.render(scene, cam, rc, frame, sample_base=(i * world + rank) * passes, sync=False)
+        if world > 1:
+            dist.reduce(frame.data, dst=0, op=dist.ReduceOp.SUM)   # ONE framebuffer reduce over NVLink
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = engine.launch_count
+    evs = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)                 # L2 flush between timed steps (outside the event pairs)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(args.warmup + i)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = engine.launch_count - launches0
+    clocks = sampler.summary()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    samples_per_step = w * h * d["spp"] * world
+    value = samples_per_step * args.steps / (ms * 1e-3) / 1e6
+
+    result = {
+        "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": d["workload"] + (f"; each of {world} ranks renders its own {d['spp']}-spp pass slice, "
+                                                 "one NCCL reduce per step" if world > 1 else ""),
+                   "l2": "256 MiB device memset between timed steps (L2 flush)", "seed": 0,
+                   "timing": "CUDA events per step on torch's current stream (the launch stream), summed; max over ranks"},
+        "gpu_launches": launches, "clocks": clocks, "wall_s": t_wall,
+    }
+
+    if rank == 0 and not args.no_extras:
+        # ---- e2e: the same step through the C-ABI with HOST buffers (H2D + render + D2H inside) ----
+        host = torch.zeros((h, w, 4), dtype=torch.float32).pin_memory()
+        hb = bt.Buffer(w, h)
+        hb.data = host.numpy()
+        hb.data[..., 3] = 1.0
+        for i in range(2):
+            tracer.render(scene, cam, rc, hb, sample_base=i * passes)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_e2e = max(2, min(args.steps, 3))
+        for i in range(n_e2e):
+            hb.data[..., :3] = 0.0
+            tracer.render(scene, cam, rc, hb, sample_base=i * passes)   # blocking bt_render, BT_MEM_HOST
+            _ = float(hb.data[0, 0, 0])
+        te = time.perf_counter() - t0
+        result["e2e"] = {"value": w * h * d["spp"] * n_e2e / te / 1e6, "unit": METRIC,
+                         "h2d_bytes_per_step": w * h * 16, "d2h_bytes_per_step": w * h * 16,
+                         "note": "bt_render with a pinned host RGBA32F buffer; 1 GPU (rank 0)"}
+
+        # ---- roofline of the dominant kernel (render_kernel) + the geodesic stepper ----
+        peak = engine.fp32_peak_tflops(8192)
+        nominal = 148 * 128 * 2 * (clocks["sm_max_mhz"] or 1965) * 1e6 / 1e12
+        n_rect, n_sph = PRIMS[scene_name]
+        result["fp32_peak"] = {"measured_fma_tflops": peak, "nominal_tflops_at_max_clock": nominal,
+                               "how": "bt_fp32_peak: 8 independent FFMA chains/thread, 8 CTAs/SM, CUDA events"}
+        result["stepper_roofline"] = stepper_roofline(engine, torch, peak)
+        result["roofline"] = {
+            "bound": "fp32", "kernel": "render_kernel", "unit": "TFLOP/s", "peak": peak,
+            "achieved": None, "frac": None, "traffic": None,
+            "note": "CUDA-core FP32 (no dense contraction on this path: neither hbm- nor tensor-bound); achieved = "
+                    "segments x primitives x SURVEY-8d flops per test / kernel time, needs the segment counter (round 2)",
+            "hbm": {"algorithmic_bytes_per_launch": w * h * 32, "achieved_gbs": w * h * 32 / (ms / args.steps * 1e-3) / 1e9,
+                    "peak_gbs": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+                    if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0},
+        }
+        # ---- CPU baseline: the reference algorithm's restatement on this box's host cores ----
+        v, cores, n, dt = cpu_sample(name, 4)
+        result["cpu_baseline"] = {"value": v, "unit": METRIC, "cores": cores, "kind": "port",
+                                  "sample": f"{n} spp of the {w}x{h} frame ({dt:.1f} s wall on {cores} threads)"}
+    if rank == 0:
+        print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

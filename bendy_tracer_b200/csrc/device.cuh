@@ -1,0 +1,478 @@
+// device.cuh -- device-side math of the render loop: RNG + distributions, vector helpers,
+// primitive intersection over the shared-memory SoA blob, shading, volume shading and the
+// geodesic (RK4) stepper.  Compiled with -fmad=false: a*b+c is never contracted (the Rust
+// reference never contracts either), FMAs appear only where written as fmaf() -- i.e. in the
+// geodesic stepper, whose arithmetic is this project's own definition.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "layout.h"
+
+namespace bt {
+
+#define BT_DEV __device__ __forceinline__
+
+// ------------------------------------------------------------------------------------------
+// vectors (glam operation order: dot = (x*x' + y*y') + z*z')
+// ------------------------------------------------------------------------------------------
+struct V3 {
+    float x, y, z;
+};
+BT_DEV V3 v3(float x, float y, float z) { V3 r = {x, y, z}; return r; }
+BT_DEV V3 v3(float4 q) { V3 r = {q.x, q.y, q.z}; return r; }
+BT_DEV V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+BT_DEV V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+BT_DEV V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+BT_DEV V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+BT_DEV V3 operator*(float s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+BT_DEV V3 operator*(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+BT_DEV V3 operator/(V3 a, float s) { return v3(a.x / s, a.y / s, a.z / s); }
+BT_DEV V3 operator/(V3 a, V3 b) { return v3(a.x / b.x, a.y / b.y, a.z / b.z); }
+BT_DEV float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+BT_DEV V3 cross(V3 a, V3 b) { return v3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
+// Vec3A::normalize: v / sqrt(dot);  Vec3::normalize: v * (1 / sqrt(dot))
+BT_DEV V3 normalize_a(V3 a) { return a / sqrtf(dot(a, a)); }
+BT_DEV V3 normalize_s(V3 a) { return a * (1.0f / sqrtf(dot(a, a))); }
+BT_DEV V3 normalize_or_zero_s(V3 a) {
+    float rcp = 1.0f / sqrtf(dot(a, a));
+    if (isfinite(rcp) && rcp > 0.0f) return a * rcp;
+    return v3(0.0f, 0.0f, 0.0f);
+}
+// Mat3A * Vec3A with columns c0,c1,c2: ((c0*x) + c1*y) + c2*z
+BT_DEV V3 mat_vec(V3 c0, V3 c1, V3 c2, V3 v) { return (c0 * v.x + c1 * v.y) + c2 * v.z; }
+
+// Vec3::any_orthonormal_pair (glam)
+BT_DEV void any_orthonormal_pair(V3 n, V3& a_out, V3& b_out) {
+    float sign = copysignf(1.0f, n.z);
+    float a = -1.0f / (sign + n.z);
+    float b = n.x * n.y * a;
+    a_out = v3(1.0f + sign * n.x * n.x * a, sign * b, -sign * n.x);
+    b_out = v3(b, sign + n.y * n.y * a, -n.y);
+}
+BT_DEV float lerpf(float a, float b, float f) { return a + (b - a) * f; }          // math/mod.rs:5-25
+BT_DEV V3 reflect(V3 d, V3 n) { return d - (2.0f * dot(d, n)) * n; }                // math/mod.rs:39-41
+BT_DEV V3 refract(V3 d, V3 n, float ior) {                                          // math/mod.rs:43-48
+    float cos_theta = fminf(dot(-d, n), 1.0f);
+    V3 perp = (n * cos_theta + d) * ior;
+    V3 parallel = n * -sqrtf(fabsf(1.0f - dot(perp, perp)));
+    return perp + parallel;
+}
+BT_DEV float fresnel(V3 d, V3 n, float ior) {                                       // math/mod.rs:50-55
+    float cos_theta = fminf(dot(-d, n), 1.0f);
+    float r0 = (1.0f - ior) / (1.0f + ior);
+    r0 = r0 * r0;
+    float x = 1.0f - cos_theta;
+    float x2 = x * x;
+    float x4 = x2 * x2;
+    return r0 + (1.0f - r0) * (x * x4);  // powi(5)
+}
+
+// ------------------------------------------------------------------------------------------
+// RNG: xoshiro256++ (rand 0.8.5 SmallRng on 64-bit), keyed per camera path
+// ------------------------------------------------------------------------------------------
+BT_DEV uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+BT_DEV uint64_t splitmix_mix(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+struct Rng {
+    uint64_t s0, s1, s2, s3;
+    BT_DEV uint64_t next_u64() {
+        uint64_t result = rotl64(s0 + s3, 23) + s0;
+        uint64_t t = s1 << 17;
+        s2 ^= s0;
+        s3 ^= s1;
+        s1 ^= s2;
+        s0 ^= s3;
+        s2 ^= t;
+        s3 = rotl64(s3, 45);
+        return result;
+    }
+    BT_DEV uint32_t next_u32() { return (uint32_t)(next_u64() >> 32); }
+    BT_DEV void seed_from_u64(uint64_t state) {  // SplitMix64 x 4
+        state += 0x9e3779b97f4a7c15ULL; s0 = splitmix_mix(state);
+        state += 0x9e3779b97f4a7c15ULL; s1 = splitmix_mix(state);
+        state += 0x9e3779b97f4a7c15ULL; s2 = splitmix_mix(state);
+        state += 0x9e3779b97f4a7c15ULL; s3 = splitmix_mix(state);
+        if ((s0 | s1 | s2 | s3) == 0) {  // from_seed(all zero) -> seed_from_u64(0)
+            s0 = 0xe220a8397b1dcdafULL; s1 = 0x6e789e6aa1b965f4ULL; s2 = 0x06c45d188009454fULL; s3 = 0xf88bb8a8724c81ecULL;
+        }
+    }
+};
+BT_DEV uint64_t path_seed(uint64_t seed, uint64_t pixel, uint64_t path_index) {
+    uint64_t k = splitmix_mix(seed + 0x9e3779b97f4a7c15ULL);
+    k = splitmix_mix(k + 0x9e3779b97f4a7c15ULL * (pixel + 1));
+    k = splitmix_mix(k + 0xd1342543de82ef95ULL * (path_index + 1));
+    return k;
+}
+// Uniform<f32>::sample with a precomputed (low, scale)
+BT_DEV float uniform_f32(Rng& rng, float low, float scale) {
+    float value1_2 = __uint_as_float((rng.next_u32() >> 9) | 0x3f800000u);
+    float value0_1 = value1_2 - 1.0f;
+    return value0_1 * scale + low;
+}
+BT_DEV float standard_f32(Rng& rng) { return (float)(rng.next_u32() >> 8) * (1.0f / 16777216.0f); }
+// Bernoulli::new(p as f64): p_int = (p * 2^64) as u64, exact in integer arithmetic for f32 p in [0, 1)
+BT_DEV bool gen_bool(Rng& rng, float p) {
+    if (p >= 1.0f) return true;  // ALWAYS_TRUE: no draw (p > 1 panics in the reference)
+    uint32_t bits = __float_as_uint(p);
+    int e = (int)((bits >> 23) & 0xff);
+    uint64_t mant = bits & 0x7fffffu;
+    if (e != 0) mant |= 0x800000u; else e = 1;
+    int shift = e - 86;  // value = mant * 2^(e - 150); times 2^64
+    uint64_t p_int = shift >= 0 ? (mant << shift) : (shift > -64 ? (mant >> (-shift)) : 0ULL);
+    return rng.next_u64() < p_int;
+}
+// UniformInt<usize>::new(0, n).sample
+BT_DEV uint32_t uniform_index(Rng& rng, uint32_t n) {
+    uint64_t range = n;
+    uint64_t ints_to_reject = (0xffffffffffffffffULL - range + 1) % range;
+    uint64_t zone = 0xffffffffffffffffULL - ints_to_reject;
+    for (;;) {
+        uint64_t v = rng.next_u64();
+        uint64_t lo = v * range;
+        if (lo <= zone) return (uint32_t)__umul64hi(v, range);
+    }
+}
+
+struct Consts {  // Uniform::new_inclusive(0, TAU) / (0, 1): low = 0
+    float tau_scale, one_scale;
+};
+// math/distr.rs:7-27
+BT_DEV V3 unit_sphere(Rng& rng, const Consts& k) {
+    float r1 = uniform_f32(rng, 0.0f, k.tau_scale);
+    float r2 = uniform_f32(rng, 0.0f, k.one_scale);
+    float s, c;
+    sincosf(r1, &s, &c);
+    float w = sqrtf(r2 * (1.0f - r2));
+    return v3(c * 2.0f * w, s * 2.0f * w, 1.0f - 2.0f * r2);
+}
+// math/distr.rs:29-65 (z = 1 - r2: not unit length, as in the reference)
+BT_DEV V3 unit_hemisphere(Rng& rng, const Consts& k, V3 normal) {
+    V3 zx = normalize_s(normal), xa, ya;
+    any_orthonormal_pair(zx, xa, ya);
+    float r1 = uniform_f32(rng, 0.0f, k.tau_scale);
+    float r2 = uniform_f32(rng, 0.0f, k.one_scale);
+    float s, c;
+    sincosf(r1, &s, &c);
+    float w = sqrtf(r2 * (1.0f - r2));
+    return (xa * (c * 2.0f * w) + ya * (s * 2.0f * w)) + zx * (1.0f - r2);
+}
+// math/distr.rs:67-103
+BT_DEV V3 cosine_dir(Rng& rng, const Consts& k, V3 normal) {
+    V3 zx = normalize_s(normal), xa, ya;
+    any_orthonormal_pair(zx, xa, ya);
+    float r1 = uniform_f32(rng, 0.0f, k.tau_scale);
+    float r2 = uniform_f32(rng, 0.0f, k.one_scale);
+    float s, c;
+    sincosf(r1, &s, &c);
+    float w = sqrtf(r2);
+    return (xa * (c * w) + ya * (s * w)) + zx * sqrtf(1.0f - r2);
+}
+
+// ------------------------------------------------------------------------------------------
+// intersection over the shared-memory blob
+// ------------------------------------------------------------------------------------------
+struct Hit {
+    float t;       // clip.max while scanning; the hit distance afterwards
+    int prim;      // -1: miss
+    int face;      // BT_FACE_*-compatible (0 front, 1 back, 2 volume, 3 volume front, 4 volume back)
+};
+
+// Sphere::hit roots (sphere.rs:121-148).  Returns true and the accepted root.
+BT_DEV bool sphere_roots(float4 q0, float r2, V3 o, V3 d, float tmin, float tmax, float& t_out) {
+    V3 oc = o - v3(q0);
+    float half_b = dot(oc, d);
+    float c = dot(oc, oc) - r2;
+    float disc = half_b * half_b - c;
+    if (signbit(disc)) return false;
+    float sqrtd = sqrtf(disc);
+    float t = -half_b - sqrtd;
+    if (t < tmin || t > tmax) {
+        t = -half_b + sqrtd;
+        if (t < tmin || t > tmax) return false;
+    }
+    t_out = t;
+    return true;
+}
+// Rect::hit (rect.rs:110-155) on a pre-transformed record.  strict: Cuboid::hit's `t < best`.
+BT_DEV bool rect_test(const float4* q, V3 o, V3 d, float tmin, float tmax, bool strict, float& t_out, bool& front) {
+    float4 q0 = q[0], q1 = q[1];
+    V3 n = v3(q0);
+    float qq = dot(d, n);
+    if (fabsf(qq) <= 1e-5f) return false;
+    float p = dot(v3(q1) - o, n);
+    float t = p / qq;
+    if (t < tmin || t > tmax) return false;
+    if (strict && !(t < tmax)) return false;
+    V3 pos = o + t * d;
+    float4 q2 = q[2], q3 = q[3];
+    float lx = dot(pos, v3(q2)) + q2.w;
+    float ly = dot(pos, v3(q3)) + q3.w;
+    if (!(lx * lx <= q0.w && ly * ly <= q1.w)) return false;
+    t_out = t;
+    front = p < 0.0f;
+    return true;
+}
+
+// ChunkState::try_hit / try_hit_volume (mod.rs:389-427): linear scan in canonical object order
+// with a shrinking clip.max.  volume_obj >= 0 selects hit_volumetric for that object's sphere.
+BT_DEV Hit scan_prims(const float4* prims, int n_prims, V3 o, V3 d, float tmin, float tmax, int volume_obj) {
+    Hit h;
+    h.t = tmax;
+    h.prim = -1;
+    h.face = 0;
+    for (int i = 0; i < n_prims; ++i) {
+        const float4* q = prims + i * PRIM_STRIDE;
+        float4 meta = q[4];
+        int type = __float_as_int(meta.x);
+        if (type == PRIM_SPHERE) {
+            float4 q0 = q[0];
+            float r2 = q[1].x;
+            if (volume_obj >= 0 && __float_as_int(meta.w) == volume_obj) {
+                // Sphere::hit_volumetric, sphere.rs:150-166
+                V3 e = (o + h.t * d) - v3(q0);
+                if (dot(e, e) <= r2) {
+                    h.prim = i;
+                    h.face = 2;  // Face::Volume at t = clip.max
+                    continue;
+                }
+            }
+            float t;
+            if (sphere_roots(q0, r2, o, d, tmin, h.t, t)) {
+                h.t = t;
+                h.prim = i;
+                h.face = 8;  // resolved after the scan (needs the normal)
+            }
+        } else {
+            float t;
+            bool front;
+            if (rect_test(q, o, d, tmin, h.t, type == PRIM_CUBOID_FACE, t, front)) {
+                h.t = t;
+                h.prim = i;
+                h.face = front ? 0 : 1;
+            }
+        }
+    }
+    return h;
+}
+
+struct Surface {  // Manifold (ray.rs:36-47) reduced to what shading reads
+    V3 position, normal;
+    int face, mat, vol, obj;
+    V3 center;   // sphere centre and radius (volume bbox = centre -/+ radius)
+    float radius;
+};
+BT_DEV Surface resolve_hit(const float4* prims, const Hit& h, V3 o, V3 d) {
+    Surface s;
+    const float4* q = prims + h.prim * PRIM_STRIDE;
+    float4 meta = q[4];
+    s.mat = __float_as_int(meta.y);
+    s.obj = __float_as_int(meta.w);
+    s.vol = -1;
+    s.position = o + h.t * d;
+    s.center = v3(0.0f, 0.0f, 0.0f);
+    s.radius = 0.0f;
+    if (__float_as_int(meta.x) == PRIM_SPHERE) {
+        float4 q0 = q[0];
+        s.vol = __float_as_int(meta.z);
+        s.center = v3(q0);
+        s.radius = q0.w;
+        if (h.face == 2) {  // generate_volume_manifold, sphere.rs:63-83
+            s.normal = v3(0.0f, 0.0f, 0.0f);
+            s.face = 2;
+        } else {            // generate_surface_manifold, sphere.rs:85-119
+            V3 normal = (s.position - s.center) / q0.w;
+            bool front = dot(d, normal) < 0.0f;
+            s.normal = front ? normal : -normal;
+            s.face = (s.vol >= 0 ? 3 : 0) + (front ? 0 : 1);
+        }
+    } else {
+        V3 n = v3(q[0]);
+        s.normal = h.face == 0 ? n : -n;
+        s.face = h.face;
+    }
+    return s;
+}
+
+// Object::pdf for the light's primitives (sphere.rs:44-61, rect.rs:92-108); 0 when missed.
+BT_DEV float light_pdf(const float4* prims, const float4* light, V3 o, V3 d, float tmin, float tmax) {
+    int type = __float_as_int(light[0].x);
+    if (type == LIGHT_POINT) return 0.0f;
+    const float4* q = prims + __float_as_int(light[0].y) * PRIM_STRIDE;
+    if (type == LIGHT_SPHERE) {
+        float t;
+        if (!sphere_roots(q[0], q[1].x, o, d, tmin, tmax, t)) return 0.0f;
+        return (t * t) / q[1].y;
+    }
+    float t;
+    bool front;
+    if (!rect_test(q, o, d, tmin, tmax, false, t, front)) return 0.0f;
+    V3 n = v3(q[0]);
+    float shadow = q[4].z * fabsf(dot(d, front ? n : -n));
+    return (t * t) / shadow;
+}
+// Object::random_point (object/mod.rs:145-152)
+BT_DEV V3 light_point(Rng& rng, const Consts& k, const float4* light) {
+    int type = __float_as_int(light[0].x);
+    float4 l1 = light[1];
+    if (type == LIGHT_SPHERE) return v3(l1) + unit_sphere(rng, k) * l1.w;  // sphere.rs:40-42
+    if (type == LIGHT_POINT) return v3(l1);
+    float4 l2 = light[2], l3 = light[3], l4 = light[4];
+    float x = uniform_f32(rng, l1.w, l3.w);  // rect.rs:82-86
+    float y = uniform_f32(rng, l2.w, l4.w);
+    V3 local = v3(l1) * x + v3(l2) * y;
+    return mat_vec(v3(l3), v3(l4), v3(light[5]), local) + v3(light[6]);
+}
+
+// DensityMap::sample(Trilinear), volume.rs:140-167
+BT_DEV float density_at(const float* g, int w, int h, float x, float y, float z) {
+    return __ldg(g + ((int)z * h + (int)y) * w + (int)x);
+}
+BT_DEV float density_trilinear(const float4* vol, const float* grids, V3 coord) {
+    float4 v0 = vol[0], v1 = vol[1];
+    int w = __float_as_int(v0.x), h = __float_as_int(v0.y), dd = __float_as_int(v0.z);
+    if (w == 0 || h == 0 || dd == 0) return 0.0f;
+    const float* g = grids + __float_as_int(v0.w);
+    float cx = fminf(fmaxf(coord.x, 0.0f), 1.0f) * v1.x;
+    float cy = fminf(fmaxf(coord.y, 0.0f), 1.0f) * v1.y;
+    float cz = fminf(fmaxf(coord.z, 0.0f), 1.0f) * v1.z;
+    float fx = floorf(cx), ux = ceilf(cx), fy = floorf(cy), uy = ceilf(cy), fz = floorf(cz), uz = ceilf(cz);
+    float tx = cx - truncf(cx), ty = cy - truncf(cy), tz = cz - truncf(cz);
+    float x0 = density_at(g, w, h, fx, fy, fz), x1 = density_at(g, w, h, ux, fy, fz);
+    float y0 = lerpf(x0, x1, tx);
+    x0 = density_at(g, w, h, fx, uy, fz); x1 = density_at(g, w, h, ux, uy, fz);
+    float y1 = lerpf(x0, x1, tx);
+    float z0 = lerpf(y0, y1, ty);
+    x0 = density_at(g, w, h, fx, fy, uz); x1 = density_at(g, w, h, ux, fy, uz);
+    y0 = lerpf(x0, x1, tx);
+    x0 = density_at(g, w, h, fx, uy, uz); x1 = density_at(g, w, h, ux, uy, uz);
+    y1 = lerpf(x0, x1, tx);
+    float z1 = lerpf(y0, y1, ty);
+    return lerpf(z0, z1, tz);
+}
+
+// ------------------------------------------------------------------------------------------
+// camera (mod.rs:272-302, ray.rs:103-137)
+// ------------------------------------------------------------------------------------------
+BT_DEV V3 with_frustum_dir(float yfov, float xfov, float u, float v) {
+    float yrot = xfov * 0.5f * -u;
+    float xrot = yfov * 0.5f * -v;
+    float sy, cy, sx, cx;
+    sincosf(yrot * 0.5f, &sy, &cy);
+    sincosf(xrot * 0.5f, &sx, &cx);
+    float qx = cy * sx, qy = sy * cx, qz = -(sy * sx), qw = cy * cx;
+    V3 b = v3(qx, qy, qz);
+    V3 vv = v3(0.0f, 0.0f, -1.0f);
+    float b2 = dot(b, b);
+    float s1 = qw * qw - b2;
+    float s2 = dot(vv, b) * 2.0f;
+    float s3 = qw * 2.0f;
+    return (vv * s1 + b * s2) + cross(b, vv) * s3;
+}
+BT_DEV void camera_ray(const CameraBlock& cam, const Consts& k, Rng& rng, uint32_t x, uint32_t y, uint32_t sub_index,
+                       V3& origin, V3& direction) {
+    float v = (float)y * cam.pixel_height - 1.0f;
+    float u = (float)x * cam.pixel_width - 1.0f;
+    float u_sub = 0.0f, v_sub = 0.0f;
+    if (cam.sub_width != 0.0f) {
+        uint32_t i = sub_index % cam.sub_n, j = sub_index / cam.sub_n;
+        u_sub = (float)i * cam.sub_width;
+        v_sub = (float)j * cam.sub_width;
+    }
+    float u_offset = u_sub * cam.pixel_width + uniform_f32(rng, cam.su_low, cam.su_scale);
+    float v_offset = v_sub * cam.pixel_height + uniform_f32(rng, cam.sv_low, cam.sv_scale);
+    u = u + u_offset;
+    v = v + v_offset;
+    V3 dir_cam = with_frustum_dir(cam.yfov, cam.xfov, u, v);
+    V3 c0 = v3(cam.m[0], cam.m[1], cam.m[2]), c1 = v3(cam.m[3], cam.m[4], cam.m[5]), c2 = v3(cam.m[6], cam.m[7], cam.m[8]);
+    V3 t = v3(cam.t[0], cam.t[1], cam.t[2]);
+    V3 o = t + v3(0.0f, 0.0f, 0.0f);
+    V3 d = normalize_a(normalize_or_zero_s(mat_vec(c0, c1, c2, dir_cam)));
+    if (cam.has_focus) {
+        float angle = uniform_f32(rng, 0.0f, k.tau_scale);  // UnitDisk, distr.rs:105-138
+        float r = uniform_f32(rng, 0.0f, k.one_scale);
+        float s, c;
+        sincosf(angle, &s, &c);
+        V3 dx = v3(cam.disk_x[0], cam.disk_x[1], cam.disk_x[2]), dy = v3(cam.disk_y[0], cam.disk_y[1], cam.disk_y[2]);
+        V3 defocus = (dx * c + dy * s) * r;
+        V3 defocus_offset = mat_vec(c0, c1, c2, defocus * cam.aperture);
+        float frac_f_z = cam.focus / fabsf(dir_cam.z);
+        o = o + defocus_offset;
+        d = normalize_a(d * frac_f_z - defocus_offset);
+    }
+    origin = o;
+    direction = d;
+}
+
+// ------------------------------------------------------------------------------------------
+// geodesic stepper (extension; DESIGN.md "Geodesic model").  FMAs are explicit.
+// ------------------------------------------------------------------------------------------
+// a = sum_m -(3/2) r_s |d x v|^2 d / |d|^5.  INFO 1 also returns min |d|; INFO 2 adds the capture /
+// far-field flags.
+template <int INFO, bool EXACT>
+BT_DEV V3 lens_accel(const float4* lens, int n_lens, V3 x, V3 v, float& rmin, bool& captured, bool& far) {
+    float ax = 0.0f, ay = 0.0f, az = 0.0f;
+    if (INFO >= 1) rmin = __int_as_float(0x7f800000);
+    if (INFO >= 2) {
+        captured = false;
+        far = true;
+    }
+#pragma unroll 1
+    for (int m = 0; m < n_lens; ++m) {
+        float4 e0 = lens[m * LENS_STRIDE];
+        float4 e1 = lens[m * LENS_STRIDE + 1];
+        float dx = x.x - e0.x, dy = x.y - e0.y, dz = x.z - e0.z;
+        float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        float lx = fmaf(dy, v.z, -(dz * v.y));
+        float ly = fmaf(dz, v.x, -(dx * v.z));
+        float lz = fmaf(dx, v.y, -(dy * v.x));
+        float h2 = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
+        // fast: MUFU.RSQ (<= 2 ulp); exact: correctly rounded, bit-identical to the CPU oracle
+        float inv = EXACT ? __frsqrt_rn(r2) : rsqrtf(r2);
+        float inv2 = inv * inv;
+        float inv5 = (inv2 * inv2) * inv;
+        float s = (e1.x * h2) * inv5;
+        ax = fmaf(s, dx, ax);
+        ay = fmaf(s, dy, ay);
+        az = fmaf(s, dz, az);
+        if (INFO >= 1) {
+            float r = r2 * inv;
+            rmin = fminf(rmin, r);
+            if (INFO >= 2) {
+                if (r < e0.w) captured = true;
+                float dv = fmaf(dz, v.z, fmaf(dy, v.y, dx * v.x));
+                if (!(r > e1.y && dv > 0.0f)) far = false;
+            }
+        }
+    }
+    return v3(ax, ay, az);
+}
+BT_DEV V3 axpy(float a, V3 x, V3 y) { return v3(fmaf(a, x.x, y.x), fmaf(a, x.y, y.y), fmaf(a, x.z, y.z)); }
+template <bool EXACT>
+BT_DEV void rk4_from_k1(const float4* lens, int n_lens, V3& x, V3& v, V3 k1, float h) {
+    float hh = 0.5f * h, h6 = h * (float)(1.0 / 6.0);
+    float ru;
+    bool bu;
+    V3 x2 = axpy(hh, v, x), v2 = axpy(hh, k1, v);
+    V3 k2 = lens_accel<0, EXACT>(lens, n_lens, x2, v2, ru, bu, bu);
+    V3 x3 = axpy(hh, v2, x), v3_ = axpy(hh, k2, v);
+    V3 k3 = lens_accel<0, EXACT>(lens, n_lens, x3, v3_, ru, bu, bu);
+    V3 x4 = axpy(h, v3_, x), v4 = axpy(h, k3, v);
+    V3 k4 = lens_accel<0, EXACT>(lens, n_lens, x4, v4, ru, bu, bu);
+    V3 sv = axpy(2.0f, v2 + v3_, v + v4);
+    V3 sk = axpy(2.0f, k2 + k3, k1 + k4);
+    x = axpy(h6, sv, x);
+    v = axpy(h6, sk, v);
+}
+BT_DEV float step_size(float kappa, float h_min, float h_max, float rmin) { return fminf(fmaxf(kappa * rmin, h_min), h_max); }
+BT_DEV V3 normalize_fma(V3 a, float* len_out) {
+    float l2 = fmaf(a.z, a.z, fmaf(a.y, a.y, a.x * a.x));
+    float inv = 1.0f / sqrtf(l2);
+    if (len_out) *len_out = l2 * inv;
+    return a * inv;
+}
+
+}  // namespace bt

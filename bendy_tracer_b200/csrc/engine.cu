@@ -1,0 +1,578 @@
+// engine.cu -- implementation of the C ABI in include/bendy_b200.h.
+//
+// Host side of the drop-in boundary: owns the CUDA device/stream, the parsed Scene and its
+// flattened device buffers, merges Config/RenderConfig exactly like ChunkConfig::with_configs
+// (reference src/tracer/mod.rs:218-229) and launches the kernels.  No CPU fallback.
+#include "../../include/bendy_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "scene.hpp"
+
+using namespace bt;
+
+namespace {
+thread_local std::string g_error;
+int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(BT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                          \
+    do {                                                  \
+        cudaError_t e_ = (call);                          \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+}  // namespace
+
+struct bt_engine {
+    int device;
+    cudaStream_t stream;
+    uint64_t launches;
+    // scratch for host-memory calls
+    void* d_scratch;
+    size_t scratch_bytes;
+    int sm_count;
+    int clock_khz;
+};
+
+struct bt_scene {
+    bt_engine* engine;
+    Scene scene;
+    FlatScene flat;
+    bool flat_dirty;    // host flattening out of date
+    bool device_dirty;  // device copy out of date
+    float4* d_blob;
+    size_t blob_cap;
+    float* d_grids;
+    size_t grids_cap;
+};
+
+namespace {
+
+int ensure_scratch(bt_engine* e, size_t bytes) {
+    if (bytes <= e->scratch_bytes) return BT_OK;
+    if (e->d_scratch) cudaFree(e->d_scratch);
+    e->d_scratch = 0;
+    e->scratch_bytes = 0;
+    CK(cudaMalloc(&e->d_scratch, bytes));
+    e->scratch_bytes = bytes;
+    return BT_OK;
+}
+
+int refresh_scene(bt_scene* s, cudaStream_t stream) {
+    if (s->flat_dirty) {
+        s->flat = flatten(s->scene);
+        s->flat_dirty = false;
+        s->device_dirty = true;
+    }
+    if (s->device_dirty) {
+        size_t bb = s->flat.blob.size() * sizeof(float4), gb = s->flat.grids.size() * sizeof(float);
+        if (bb > s->blob_cap) {
+            if (s->d_blob) cudaFree(s->d_blob);
+            s->d_blob = 0;
+            s->blob_cap = 0;
+            CK(cudaMalloc((void**)&s->d_blob, bb));
+            s->blob_cap = bb;
+        }
+        if (gb > s->grids_cap) {
+            if (s->d_grids) cudaFree(s->d_grids);
+            s->d_grids = 0;
+            s->grids_cap = 0;
+            CK(cudaMalloc((void**)&s->d_grids, gb));
+            s->grids_cap = gb;
+        }
+        CK(cudaMemcpyAsync(s->d_blob, s->flat.blob.data(), bb, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(s->d_grids, s->flat.grids.data(), gb, cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));  // the host vectors may change after we return
+        s->device_dirty = false;
+    }
+    return BT_OK;
+}
+
+// ChunkConfig::with_configs, reference src/tracer/mod.rs:218-229
+struct Merged {
+    int32_t output;
+    uint32_t subsample;
+    uint64_t samples, max_bounces, max_volume_bounces;
+    float clip_min, clip_max, volume_step;
+};
+Merged merge(const bt_config& c, const bt_render_config& r) {
+    Merged m;
+    m.output = r.has_output ? r.output : c.output;
+    m.subsample = r.subsample;
+    m.samples = r.samples;
+    m.max_bounces = r.has_max_bounces ? r.max_bounces : c.max_bounces;
+    // mod.rs:224: max_volume_bounces takes render.max_BOUNCES (reference quirk, preserved)
+    m.max_volume_bounces = r.has_max_bounces ? r.max_bounces : c.max_volume_bounces;
+    m.clip_min = c.clip_min;
+    m.clip_max = c.clip_max;
+    m.volume_step = r.has_volume_step ? r.volume_step : c.volume_step;
+    return m;
+}
+
+uint32_t clamp_u32(uint64_t v) { return v > 0xfffffffeULL ? 0xfffffffeu : (uint32_t)v; }
+
+int build_params(bt_scene* s, uint64_t camera_ref, bool need_camera, const bt_config* config, const bt_render_config* rc,
+                 uint64_t seed, uint64_t sample_base, uint32_t width, uint32_t height, RenderParams* out) {
+    Merged m = merge(*config, *rc);
+    RenderParams p;
+    std::memset(&p, 0, sizeof p);
+    p.scene = s->flat.header;
+    uint32_t sub_n = m.subsample == 0 ? 1u : m.subsample;
+    if ((uint64_t)sub_n * sub_n > 0xffffffffULL) return fail(BT_ERR_INVALID_ARG, "subsample too large");
+    p.sub_count = sub_n * sub_n;
+    if (need_camera) p.cam = make_camera_block(s->scene, camera_ref, width, height, m.subsample);
+    p.cam.sub_n = sub_n;
+    p.blob = s->d_blob;
+    p.grids = s->d_grids;
+    p.width = width;
+    p.height = height;
+    if (m.samples * p.sub_count > 0xffffffffULL) return fail(BT_ERR_INVALID_ARG, "samples * subpixel_count exceeds 2^32 per call");
+    p.paths_per_pixel = (uint32_t)(m.samples * p.sub_count);
+    p.seed = seed;
+    p.path_base = sample_base * p.sub_count;
+    p.output = m.output;
+    p.max_bounces = clamp_u32(m.max_bounces);
+    p.max_volume_bounces = clamp_u32(m.max_volume_bounces);
+    p.clip_min = m.clip_min;
+    p.clip_max = m.clip_max;
+    p.volume_step = m.volume_step;
+    p.tau_scale = uniform_scale_inclusive(0.0f, 6.28318530717958647692f);
+    p.one_scale = uniform_scale_inclusive(0.0f, 1.0f);
+    *out = p;
+    return BT_OK;
+}
+
+int check_renderable(const bt_scene* s) {
+    if (s->flat.diffuse_without_light)
+        return fail(BT_ERR_SCENE, "Uniform::new called with `low >= high` (a Diffuse surface needs at least one LIGHT object)");
+    if (s->flat.unsupported_light) return fail(BT_ERR_UNSUPPORTED, "a Cuboid with ObjectFlags::LIGHT is not supported by the device path yet");
+    if (render_smem_bytes(RenderParams{s->flat.header}) > 200 * 1024)
+        return fail(BT_ERR_UNSUPPORTED, "scene does not fit the shared-memory staging buffer");
+    return BT_OK;
+}
+
+}  // namespace
+
+#define GUARD_BEGIN try {
+#define GUARD_END                                                  \
+    }                                                              \
+    catch (const ParseError& e) { return fail(BT_ERR_PARSE, e.what()); }  \
+    catch (const SceneError& e) { return fail(BT_ERR_SCENE, e.what()); }  \
+    catch (const std::exception& e) { return fail(BT_ERR_INVALID_ARG, e.what()); }
+
+extern "C" {
+
+const char* bt_last_error(void) { return g_error.c_str(); }
+
+int bt_engine_create(int device, bt_engine** out) {
+    if (!out) return fail(BT_ERR_INVALID_ARG, "out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(BT_ERR_CUDA, std::string("no CUDA device available (the engine has no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(BT_ERR_INVALID_ARG, "device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(BT_ERR_CUDA, std::string("device is not sm_100 class: ") + prop.name);
+    bt_engine* en = new bt_engine();
+    en->device = device;
+    en->launches = 0;
+    en->d_scratch = 0;
+    en->scratch_bytes = 0;
+    en->sm_count = prop.multiProcessorCount;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    en->clock_khz = khz;
+    e = cudaStreamCreateWithFlags(&en->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete en;
+        return cuda_fail(e, "cudaStreamCreate");
+    }
+    *out = en;
+    return BT_OK;
+}
+
+void bt_engine_destroy(bt_engine* engine) {
+    if (!engine) return;
+    cudaSetDevice(engine->device);
+    if (engine->d_scratch) cudaFree(engine->d_scratch);
+    cudaStreamDestroy(engine->stream);
+    delete engine;
+}
+
+uint64_t bt_engine_launch_count(const bt_engine* engine) { return engine ? engine->launches : 0; }
+
+int bt_scene_create_json(bt_engine* engine, const void* bytes, size_t n, bt_scene** out) {
+    if (!bytes || !out) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    GUARD_BEGIN
+    bt_scene* s = new bt_scene();
+    s->engine = engine;
+    s->d_blob = 0;
+    s->d_grids = 0;
+    s->blob_cap = s->grids_cap = 0;
+    try {
+        s->scene = Scene::from_json(bytes, n);
+        s->flat = flatten(s->scene);
+    } catch (...) {
+        delete s;
+        throw;
+    }
+    s->flat_dirty = false;
+    s->device_dirty = true;
+    *out = s;
+    return BT_OK;
+    GUARD_END
+}
+
+int bt_scene_to_json(const bt_scene* scene, char** out, size_t* n) {
+    if (!scene || !out || !n) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    GUARD_BEGIN
+    std::string s = scene->scene.to_json();
+    char* buf = (char*)std::malloc(s.size() + 1);
+    if (!buf) return fail(BT_ERR_INVALID_ARG, "out of memory");
+    std::memcpy(buf, s.data(), s.size());
+    buf[s.size()] = 0;
+    *out = buf;
+    *n = s.size();
+    return BT_OK;
+    GUARD_END
+}
+
+void bt_free(void* p) { std::free(p); }
+
+void bt_scene_destroy(bt_scene* scene) {
+    if (!scene) return;
+    if (scene->engine) cudaSetDevice(scene->engine->device);
+    if (scene->d_blob) cudaFree(scene->d_blob);
+    if (scene->d_grids) cudaFree(scene->d_grids);
+    delete scene;
+}
+
+int bt_scene_find_by_tag(const bt_scene* scene, const char* tag, uint64_t* object_ref) {
+    if (!scene || !tag || !object_ref) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    if (!scene->scene.find_by_tag(tag, object_ref)) return fail(BT_ERR_SCENE, std::string("no object tagged `") + tag + "`");
+    return BT_OK;
+}
+
+int bt_scene_set_camera_aspect(bt_scene* scene, uint64_t camera_ref, float aspect_ratio) {
+    if (!scene) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    GUARD_BEGIN
+    Object& o = scene->scene.get_object(camera_ref);
+    if (o.kind != OBJ_CAMERA) return fail(BT_ERR_SCENE, "called `Option::unwrap()` on a `None` value (object is not a camera)");
+    o.camera.aspect_ratio = aspect_ratio;  // read per call by make_camera_block; no re-flatten needed
+    return BT_OK;
+    GUARD_END
+}
+
+int bt_scene_apply_transform(bt_scene* scene, uint64_t object_ref, const float affine[12]) {
+    if (!scene || !affine) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    GUARD_BEGIN
+    Affine a;
+    std::memcpy(a.f, affine, sizeof a.f);
+    scene->scene.apply_transform(object_ref, a);
+    scene->flat_dirty = true;
+    return BT_OK;
+    GUARD_END
+}
+
+void bt_lens_config_default(bt_lens_config* cfg) {
+    if (!cfg) return;
+    cfg->kappa = 0.05f;
+    cfg->h_min = 0.02f;
+    cfg->h_max = 5.0f;
+    cfg->r_far = 500.0f;
+    cfg->max_steps = 4096;
+    cfg->flags = 0;
+}
+
+int bt_scene_set_lenses(bt_scene* scene, const float* xyzr, uint32_t n, const bt_lens_config* cfg) {
+    if (!scene || (n && !xyzr)) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    bt_lens_config c;
+    if (cfg) c = *cfg; else bt_lens_config_default(&c);
+    if (!(c.kappa > 0.0f) || !(c.h_min > 0.0f) || !(c.h_max >= c.h_min) || c.max_steps == 0)
+        return fail(BT_ERR_INVALID_ARG, "lens config: need kappa > 0, 0 < h_min <= h_max, max_steps > 0");
+    scene->scene.lenses.clear();
+    for (uint32_t i = 0; i < n; ++i) {
+        Lens l = {{xyzr[4 * i], xyzr[4 * i + 1], xyzr[4 * i + 2]}, xyzr[4 * i + 3]};
+        scene->scene.lenses.push_back(l);
+    }
+    scene->scene.lens_config.kappa = c.kappa;
+    scene->scene.lens_config.h_min = c.h_min;
+    scene->scene.lens_config.h_max = c.h_max;
+    scene->scene.lens_config.r_far = c.r_far;
+    scene->scene.lens_config.max_steps = c.max_steps;
+    scene->scene.lens_config.flags = c.flags;
+    scene->flat_dirty = true;
+    return BT_OK;
+}
+
+int bt_scene_get_info(const bt_scene* scene, bt_scene_info* info) {
+    if (!scene || !info) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    GUARD_BEGIN
+    FlatScene tmp;
+    const FlatScene* f = &scene->flat;
+    if (scene->flat_dirty) {
+        tmp = flatten(scene->scene);
+        f = &tmp;
+    }
+    info->n_objects = (uint32_t)scene->scene.objects.size();
+    info->n_data = (uint32_t)scene->scene.data.size();
+    info->n_primitives = f->header.n_prims;
+    info->n_lights = f->header.n_lights;
+    info->n_volumes = f->header.n_vols;
+    info->n_lenses = f->header.n_lens;
+    info->n_bvh_nodes = 0;
+    info->root_material = scene->scene.root_material;
+    return BT_OK;
+    GUARD_END
+}
+
+void bt_config_default(bt_config* c) {
+    if (!c) return;
+    c->max_bounces = 8;
+    c->max_volume_bounces = 32;
+    c->clip_min = 0.01f;
+    c->clip_max = 1000.0f;
+    c->volume_step = 0.1f;
+    c->chunks_x = 4;
+    c->chunks_y = 2;
+    c->output = BT_OUTPUT_FULL;
+}
+
+void bt_render_config_default(bt_render_config* c) {
+    if (!c) return;
+    std::memset(c, 0, sizeof *c);
+    c->subsample = 0;
+    c->samples = 64;
+}
+
+int bt_render_async(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_config* config,
+                    const bt_render_config* rc, uint64_t seed, uint64_t sample_base, float* rgba32f_device,
+                    uint32_t width, uint32_t height, uint64_t* samples_inout, int32_t* status, void* cuda_stream) {
+    if (!engine || !scene || !config || !rc || !status) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    if (!scene->engine) scene->engine = engine;  // a scene created without an engine binds on first use
+    if (scene->engine != engine) return fail(BT_ERR_INVALID_ARG, "scene belongs to another engine");
+    GUARD_BEGIN
+    if (rc->samples == 0) {  // mod.rs:186-188
+        *status = BT_STATUS_DONE;
+        return BT_OK;
+    }
+    if (!rgba32f_device || width == 0 || height == 0) return fail(BT_ERR_INVALID_ARG, "empty buffer");
+    if (config->output < 0 || config->output > 3 || (rc->has_output && (rc->output < 0 || rc->output > 3)))
+        return fail(BT_ERR_INVALID_ARG, "invalid Output");
+    CK(cudaSetDevice(engine->device));
+    cudaStream_t stream = (cudaStream_t)cuda_stream;  // NULL is the CUDA default stream, taken literally
+    int rcode = refresh_scene(scene, stream);
+    if (rcode != BT_OK) return rcode;
+    if ((rcode = check_renderable(scene)) != BT_OK) return rcode;
+    RenderParams p;
+    if ((rcode = build_params(scene, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return rcode;
+    p.fb = (float4*)rgba32f_device;
+    CK(launch_render(p, stream, &engine->launches));
+    if (samples_inout) *samples_inout += rc->samples * p.sub_count;  // mod.rs:199
+    *status = BT_STATUS_IN_PROGRESS;
+    return BT_OK;
+    GUARD_END
+}
+
+int bt_render(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_config* config,
+              const bt_render_config* rc, uint64_t seed, uint64_t sample_base, float* rgba32f, int mem,
+              uint32_t width, uint32_t height, uint64_t* samples_inout, int32_t* status) {
+    if (!engine || !rc || !status) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    if (rc->samples == 0) {
+        *status = BT_STATUS_DONE;
+        return BT_OK;
+    }
+    if (!rgba32f) return fail(BT_ERR_INVALID_ARG, "empty buffer");
+    CK(cudaSetDevice(engine->device));
+    if (mem == BT_MEM_DEVICE) {
+        int r = bt_render_async(engine, scene, camera_ref, config, rc, seed, sample_base, rgba32f, width, height,
+                                samples_inout, status, engine->stream);
+        if (r != BT_OK) return r;
+        CK(cudaStreamSynchronize(engine->stream));
+        return BT_OK;
+    }
+    size_t bytes = (size_t)width * height * 4 * sizeof(float);
+    int r = ensure_scratch(engine, bytes);
+    if (r != BT_OK) return r;
+    CK(cudaMemcpyAsync(engine->d_scratch, rgba32f, bytes, cudaMemcpyHostToDevice, engine->stream));
+    r = bt_render_async(engine, scene, camera_ref, config, rc, seed, sample_base, (float*)engine->d_scratch, width,
+                        height, samples_inout, status, engine->stream);
+    if (r != BT_OK) {
+        cudaStreamSynchronize(engine->stream);
+        return r;
+    }
+    CK(cudaMemcpyAsync(rgba32f, engine->d_scratch, bytes, cudaMemcpyDeviceToHost, engine->stream));
+    CK(cudaStreamSynchronize(engine->stream));
+    return BT_OK;
+}
+
+int bt_resolve_u8(bt_engine* engine, const float* rgba32f, int mem, uint32_t width, uint32_t height,
+                  uint64_t samples, int color_space, uint8_t* rgba8) {
+    if (!engine || !rgba32f || !rgba8) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    if (color_space < 0 || color_space > 3) return fail(BT_ERR_INVALID_ARG, "invalid ColorSpace");
+    CK(cudaSetDevice(engine->device));
+    uint32_t n = width * height;
+    if (mem == BT_MEM_DEVICE) {
+        CK(launch_resolve((const float4*)rgba32f, n, samples, color_space, (uchar4*)rgba8, engine->stream, &engine->launches));
+        CK(cudaStreamSynchronize(engine->stream));
+        return BT_OK;
+    }
+    size_t fb_bytes = (size_t)n * 16, out_bytes = (size_t)n * 4;
+    int r = ensure_scratch(engine, fb_bytes + out_bytes);
+    if (r != BT_OK) return r;
+    char* base = (char*)engine->d_scratch;
+    CK(cudaMemcpyAsync(base, rgba32f, fb_bytes, cudaMemcpyHostToDevice, engine->stream));
+    CK(launch_resolve((const float4*)base, n, samples, color_space, (uchar4*)(base + fb_bytes), engine->stream, &engine->launches));
+    CK(cudaMemcpyAsync(rgba8, base + fb_bytes, out_bytes, cudaMemcpyDeviceToHost, engine->stream));
+    CK(cudaStreamSynchronize(engine->stream));
+    return BT_OK;
+}
+
+int bt_trace_segments(bt_engine* engine, bt_scene* scene, const bt_config* config, uint32_t n,
+                      const float* origins, const float* dirs, bt_segment* out) {
+    if (!engine || !scene || !config || (n && (!origins || !dirs || !out))) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    GUARD_BEGIN
+    if (!scene->engine) scene->engine = engine;
+    if (scene->engine != engine) return fail(BT_ERR_INVALID_ARG, "scene belongs to another engine");
+    CK(cudaSetDevice(engine->device));
+    int r = refresh_scene(scene, engine->stream);
+    if (r != BT_OK) return r;
+    if ((r = check_renderable(scene)) != BT_OK && r != BT_ERR_SCENE) return r;
+    bt_render_config rc;
+    bt_render_config_default(&rc);
+    rc.samples = 1;
+    RenderParams p;
+    if ((r = build_params(scene, 0, false, config, &rc, 0, 0, 1, 1, &p)) != BT_OK) return r;
+    size_t in_bytes = (size_t)n * 3 * sizeof(float), out_bytes = (size_t)n * sizeof(DeviceSegment);
+    size_t off_d = (in_bytes + 255) & ~(size_t)255, off_o = 2 * off_d;
+    if ((r = ensure_scratch(engine, off_o + out_bytes + 256)) != BT_OK) return r;
+    char* base = (char*)engine->d_scratch;
+    CK(cudaMemcpyAsync(base, origins, in_bytes, cudaMemcpyHostToDevice, engine->stream));
+    CK(cudaMemcpyAsync(base + off_d, dirs, in_bytes, cudaMemcpyHostToDevice, engine->stream));
+    CK(launch_trace(p, n, (const float*)base, (const float*)(base + off_d), (DeviceSegment*)(base + off_o), engine->stream, &engine->launches));
+    std::vector<DeviceSegment> host(n);
+    CK(cudaMemcpyAsync(host.data(), base + off_o, out_bytes, cudaMemcpyDeviceToHost, engine->stream));
+    CK(cudaStreamSynchronize(engine->stream));
+    for (uint32_t i = 0; i < n; ++i) {
+        const DeviceSegment& d = host[i];
+        bt_segment& o = out[i];
+        o.face = d.face;
+        o.steps = d.steps;
+        o.object_ref = d.obj >= 0 ? scene->flat.object_refs[d.obj] : 0;
+        o.t = d.t;
+        std::memcpy(o.position, d.position, sizeof o.position);
+        std::memcpy(o.normal, d.normal, sizeof o.normal);
+        std::memcpy(o.direction, d.direction, sizeof o.direction);
+    }
+    return BT_OK;
+    GUARD_END
+}
+
+int bt_camera_rays(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_config* config,
+                   const bt_render_config* rc, uint64_t seed, uint64_t sample_base, uint32_t width, uint32_t height,
+                   uint32_t n, const uint32_t* xs, const uint32_t* ys, const uint64_t* path_index, float* out) {
+    if (!engine || !scene || !config || !rc || (n && (!xs || !ys || !path_index || !out))) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    GUARD_BEGIN
+    if (!scene->engine) scene->engine = engine;
+    if (scene->engine != engine) return fail(BT_ERR_INVALID_ARG, "scene belongs to another engine");
+    CK(cudaSetDevice(engine->device));
+    int r = refresh_scene(scene, engine->stream);
+    if (r != BT_OK) return r;
+    RenderParams p;
+    if ((r = build_params(scene, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return r;
+    size_t b32 = ((size_t)n * 4 + 255) & ~(size_t)255, b64 = ((size_t)n * 8 + 255) & ~(size_t)255, bo = (size_t)n * 24;
+    if ((r = ensure_scratch(engine, 2 * b32 + b64 + bo + 256)) != BT_OK) return r;
+    char* base = (char*)engine->d_scratch;
+    CK(cudaMemcpyAsync(base, xs, (size_t)n * 4, cudaMemcpyHostToDevice, engine->stream));
+    CK(cudaMemcpyAsync(base + b32, ys, (size_t)n * 4, cudaMemcpyHostToDevice, engine->stream));
+    CK(cudaMemcpyAsync(base + 2 * b32, path_index, (size_t)n * 8, cudaMemcpyHostToDevice, engine->stream));
+    CK(launch_camera_rays(p, n, (const uint32_t*)base, (const uint32_t*)(base + b32), (const uint64_t*)(base + 2 * b32),
+                          (float*)(base + 2 * b32 + b64), engine->stream, &engine->launches));
+    CK(cudaMemcpyAsync(out, base + 2 * b32 + b64, bo, cudaMemcpyDeviceToHost, engine->stream));
+    CK(cudaStreamSynchronize(engine->stream));
+    return BT_OK;
+    GUARD_END
+}
+
+int bt_geodesic_integrate(bt_engine* engine, const float* xyzr, uint32_t n_lenses, const bt_lens_config* cfg,
+                          uint32_t n, float* xv, int mem, uint32_t n_steps, void* cuda_stream) {
+    if (!engine || (n_lenses && !xyzr) || (n && !xv)) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    bt_lens_config c;
+    if (cfg) c = *cfg; else bt_lens_config_default(&c);
+    CK(cudaSetDevice(engine->device));
+    cudaStream_t stream = mem == BT_MEM_HOST ? engine->stream : (cudaStream_t)cuda_stream;
+    std::vector<float4> lens;
+    for (uint32_t i = 0; i < n_lenses; ++i) {
+        float rs = xyzr[4 * i + 3];
+        if (!(rs > 0.0f)) continue;
+        float4 e0 = {xyzr[4 * i], xyzr[4 * i + 1], xyzr[4 * i + 2], rs};
+        float4 e1 = {-1.5f * rs, c.r_far * rs, 0.0f, 0.0f};
+        lens.push_back(e0);
+        lens.push_back(e1);
+    }
+    size_t lens_bytes = (lens.size() * sizeof(float4) + 255) & ~(size_t)255;
+    size_t xv_bytes = (size_t)n * 6 * sizeof(float);
+    int r = ensure_scratch(engine, lens_bytes + 256 + (mem == BT_MEM_HOST ? xv_bytes : 0));
+    if (r != BT_OK) return r;
+    char* base = (char*)engine->d_scratch;
+    if (!lens.empty()) CK(cudaMemcpyAsync(base, lens.data(), lens.size() * sizeof(float4), cudaMemcpyHostToDevice, stream));
+    IntegrateParams p;
+    p.lens = (const float4*)base;
+    p.n_lens = (uint32_t)(lens.size() / LENS_STRIDE);
+    p.kappa = c.kappa;
+    p.h_min = c.h_min;
+    p.h_max = c.h_max;
+    p.n = n;
+    p.n_steps = n_steps;
+    p.exact = c.flags & BT_LENS_EXACT_RSQRT;
+    if (mem == BT_MEM_HOST) {
+        float* d_xv = (float*)(base + lens_bytes + 256);
+        CK(cudaMemcpyAsync(d_xv, xv, xv_bytes, cudaMemcpyHostToDevice, stream));
+        p.xv = d_xv;
+        CK(launch_integrate(p, stream, &engine->launches));
+        CK(cudaMemcpyAsync(xv, d_xv, xv_bytes, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    } else {
+        p.xv = xv;
+        CK(cudaStreamSynchronize(stream));  // the lens table upload reads a stack vector
+        CK(launch_integrate(p, stream, &engine->launches));
+    }
+    return BT_OK;
+}
+
+int bt_fp32_peak(bt_engine* engine, uint32_t iters, double* tflops) {
+    if (!engine || !tflops || iters == 0) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    CK(cudaSetDevice(engine->device));
+    int blocks = engine->sm_count * 8;
+    int r = ensure_scratch(engine, (size_t)blocks * FP32_PEAK_THREADS * sizeof(float));
+    if (r != BT_OK) return r;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(launch_fp32_peak((float*)engine->d_scratch, iters / 4 + 1, blocks, engine->stream, &engine->launches));  // warm-up
+    CK(cudaEventRecord(e0, engine->stream));
+    CK(launch_fp32_peak((float*)engine->d_scratch, iters, blocks, engine->stream, &engine->launches));
+    CK(cudaEventRecord(e1, engine->stream));
+    CK(cudaStreamSynchronize(engine->stream));
+    float ms = 0.0f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    double flops = 2.0 * (double)blocks * FP32_PEAK_THREADS * FP32_PEAK_CHAINS * FP32_PEAK_UNROLL * (double)iters;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    return BT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,41 @@
+// kernels.h -- host-callable launchers of the CUDA kernels in kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "layout.h"
+
+namespace bt {
+
+struct DeviceSegment {  // mirrors bt_segment (include/bendy_b200.h) with the object INDEX
+    int32_t face;
+    uint32_t steps;
+    int32_t obj;
+    float t;
+    float position[3], normal[3], direction[3];
+};
+
+struct IntegrateParams {
+    const float4* lens;   // LENS_STRIDE records, device memory
+    uint32_t n_lens;
+    float kappa, h_min, h_max;
+    float* xv;            // n * 6
+    uint32_t n, n_steps;
+    uint32_t exact;       // correctly rounded rsqrt (bit-identical to the CPU oracle)
+};
+
+// each returns the cudaError_t of the launch; `launches` is incremented per kernel launched
+cudaError_t launch_render(const RenderParams& p, cudaStream_t stream, uint64_t* launches);
+cudaError_t launch_trace(const RenderParams& p, uint32_t n, const float* origins, const float* dirs,
+                         DeviceSegment* out, cudaStream_t stream, uint64_t* launches);
+cudaError_t launch_camera_rays(const RenderParams& p, uint32_t n, const uint32_t* xs, const uint32_t* ys,
+                               const uint64_t* path_index, float* out, cudaStream_t stream, uint64_t* launches);
+cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t stream, uint64_t* launches);
+cudaError_t launch_resolve(const float4* fb, uint32_t n_pixels, uint64_t samples, int color_space, uchar4* out,
+                           cudaStream_t stream, uint64_t* launches);
+cudaError_t launch_fp32_peak(float* out, uint32_t iters, int blocks, cudaStream_t stream, uint64_t* launches);
+
+size_t render_smem_bytes(const RenderParams& p);
+enum { FP32_PEAK_THREADS = 256, FP32_PEAK_CHAINS = 8, FP32_PEAK_UNROLL = 16 };
+
+}  // namespace bt

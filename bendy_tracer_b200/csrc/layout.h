@@ -1,0 +1,88 @@
+// layout.h -- the flattened, vectorised SoA scene layout shared by the host flattener (scene.cpp)
+// and the device kernels (device.cuh).  Everything is float4 records in ONE contiguous blob that
+// each CTA stages into shared memory once (shipped scenes: <= 2.5 KB), so the per-segment linear
+// scan of reference ChunkState::try_hit (src/tracer/mod.rs:389-402) reads broadcast LDS.128.
+#pragma once
+#include <stdint.h>
+
+namespace bt {
+
+// ---- primitive record: PRIM_STRIDE float4 -------------------------------------------------
+//   q4 = (type, material index, volume index | rect area, object index)   [int bits except area]
+// SPHERE (reference src/scene/object/sphere.rs:11-16; translation only, :121-148)
+//   q0 = (cx, cy, cz, r)   q1 = (r*r, PI*r*r, -, -)
+// RECT / CUBOID_FACE (reference rect.rs:110-155 with everything ray-independent hoisted:
+//   n = M*z, the full affine inverse and the local axes folded into two plane equations)
+//   q0 = (n.xyz, hw^2/|x|^2)  q1 = (T.xyz, hh^2/|y|^2)
+//   q2 = (ax.xyz, cx)  q3 = (ay.xyz, cy)   with local.x = dot(pos, ax) + cx
+enum { PRIM_SPHERE = 0, PRIM_RECT = 1, PRIM_CUBOID_FACE = 2 };
+enum { PRIM_STRIDE = 5 };
+
+// ---- material record: MAT_STRIDE float4 (reference src/scene/data/material.rs:22-44) -------
+//   m0 = (albedo.rgb, kind)   m1 = (roughness, ior, intensity, -)
+enum { MAT_FLAT = 0, MAT_DIFFUSE = 1, MAT_METALLIC = 2, MAT_GLASS = 3, MAT_EMISSIVE = 4 };
+enum { MAT_STRIDE = 2 };
+
+// ---- light record: LIGHT_STRIDE float4 (objects with ObjectFlags::LIGHT, object/mod.rs:23-28)
+//   l0 = (type, first primitive, primitive count, object index)
+//   SPHERE: l1 = (c.xyz, r)
+//   RECT:   l1 = (x.xyz, -hw) l2 = (y.xyz, -hh) l3 = (Mx.xyz, scale_x) l4 = (My.xyz, scale_y)
+//           l5 = (Mz.xyz, -) l6 = (T.xyz, -)       (rect.rs:82-86: Uniform::new_inclusive(-h, h))
+//   POINT:  l1 = (T.xyz, -)                        (object/mod.rs:150)
+enum { LIGHT_SPHERE = 0, LIGHT_RECT = 1, LIGHT_POINT = 2 };
+enum { LIGHT_STRIDE = 7 };
+
+// ---- volume record: VOL_STRIDE float4 (reference src/scene/data/volume.rs:75-82) -----------
+//   v0 = (width, height, depth, grid offset in floats) [ints]   v1 = (size.xyz, -)
+enum { VOL_STRIDE = 2 };
+
+// ---- lens record: LENS_STRIDE float4 (extension) -------------------------------------------
+//   e0 = (c.xyz, r_s)   e1 = (-1.5 r_s, r_far * r_s, -, -)
+enum { LENS_STRIDE = 2 };
+
+struct SceneHeader {
+    uint32_t n_prims, prim_off;      // offsets in float4 units into the blob
+    uint32_t n_mats, mat_off;
+    uint32_t n_lights, light_off;
+    uint32_t n_vols, vol_off;
+    uint32_t n_lens, lens_off;
+    uint32_t blob_f4;                // total float4 count
+    uint32_t has_volume_prims;       // any sphere with volume != None
+    // root material folded to what sample_root returns (src/tracer/mod.rs:429-452)
+    float root_color[3], root_albedo[3];
+    uint32_t root_keeps_normal;      // 1: normal = -dir, depth = clip_max; 0: normal = 0, depth = inf
+    // lens stepping
+    float kappa, h_min, h_max;
+    uint32_t max_steps;
+    uint32_t lens_exact;             // BT_LENS_EXACT_RSQRT
+};
+
+struct CameraBlock {                 // reference src/tracer/mod.rs:244-267 hoisted per render call
+    float m[9];                      // transform_world matrix3 columns
+    float t[3];
+    float yfov, xfov, pixel_width, pixel_height;
+    float su_low, su_scale, sv_low, sv_scale;   // Uniform::from(min..max) for the jitter
+    float sub_width;                 // 1/n, 0 for Subsample::None
+    uint32_t sub_n;                  // n (1 for None)
+    uint32_t has_focus;
+    float focus, aperture;
+    float disk_x[3], disk_y[3];      // UnitDisk::new(NEG_Z) basis
+};
+
+struct RenderParams {
+    SceneHeader scene;
+    CameraBlock cam;
+    const float4* blob;
+    const float* grids;
+    float4* fb;
+    uint32_t width, height;
+    uint32_t paths_per_pixel;        // samples * subpixel_count of this call
+    uint32_t sub_count;
+    uint64_t seed, path_base;        // path index of the first path of this call
+    int32_t output;
+    uint32_t max_bounces, max_volume_bounces;
+    float clip_min, clip_max, volume_step;
+    float tau_scale, one_scale;      // Uniform::new_inclusive(0, TAU).scale, (0, 1).scale
+};
+
+}  // namespace bt

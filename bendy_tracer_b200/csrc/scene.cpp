@@ -1,0 +1,984 @@
+// scene.cpp -- Scene wire format (serde_json-compatible), scene-graph update, and the flattener.
+//
+// Wire format: reference src/scene/mod.rs:16-20,84-90 (Scene, Collection), src/scene/object/mod.rs
+// :23-41,247-256 (Object, ObjectFlags, ObjectKind), src/scene/object/transform.rs:10-15,
+// src/scene/object/{sphere.rs:11-16,rect.rs:11-19,cuboid.rs:12-15,camera.rs:3-10},
+// src/scene/data/mod.rs:9-15,46-51, src/scene/data/material.rs:22-44, volume.rs:21-24,75-82.
+// serde's externally-tagged enums: unit variants are strings ("Empty"), others {"Variant": {...}};
+// newtype structs (ObjectRef, DataRef) are bare integers; HashMap<u64-newtype, V> keys are strings.
+#include "scene.hpp"
+
+#include <zlib.h>
+
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <memory>
+
+namespace bt {
+
+// ------------------------------------------------------------------------------------------
+// minimal JSON
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct JValue;
+typedef std::shared_ptr<JValue> JPtr;
+struct JValue {
+    enum Type { Null, Bool, Number, String, Array, Object } type;
+    bool b;
+    std::string text;  // number token or string contents
+    std::vector<JPtr> arr;
+    std::vector<std::pair<std::string, JPtr> > obj;
+    JValue() : type(Null), b(false) {}
+    const JValue* get(const char* key) const {
+        for (size_t i = 0; i < obj.size(); ++i)
+            if (obj[i].first == key) return obj[i].second.get();
+        return 0;
+    }
+};
+
+struct Parser {
+    const char* p;
+    const char* end;
+    [[noreturn]] void fail(const char* what) const {
+        char buf[160];
+        std::snprintf(buf, sizeof buf, "%s at byte %ld", what, (long)(p - start));
+        throw ParseError(buf);
+    }
+    const char* start;
+    void ws() {
+        while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p;
+    }
+    JPtr value() {
+        ws();
+        if (p >= end) fail("EOF while parsing a value");
+        JPtr v(new JValue());
+        char c = *p;
+        if (c == '{') {
+            v->type = JValue::Object;
+            ++p;
+            ws();
+            if (p < end && *p == '}') {
+                ++p;
+                return v;
+            }
+            for (;;) {
+                ws();
+                if (p >= end || *p != '"') fail("key must be a string");
+                std::string k = string();
+                ws();
+                if (p >= end || *p != ':') fail("expected `:`");
+                ++p;
+                v->obj.push_back(std::make_pair(k, value()));
+                ws();
+                if (p < end && *p == ',') {
+                    ++p;
+                    continue;
+                }
+                if (p < end && *p == '}') {
+                    ++p;
+                    return v;
+                }
+                fail("expected `,` or `}`");
+            }
+        }
+        if (c == '[') {
+            v->type = JValue::Array;
+            ++p;
+            ws();
+            if (p < end && *p == ']') {
+                ++p;
+                return v;
+            }
+            for (;;) {
+                v->arr.push_back(value());
+                ws();
+                if (p < end && *p == ',') {
+                    ++p;
+                    continue;
+                }
+                if (p < end && *p == ']') {
+                    ++p;
+                    return v;
+                }
+                fail("expected `,` or `]`");
+            }
+        }
+        if (c == '"') {
+            v->type = JValue::String;
+            v->text = string();
+            return v;
+        }
+        if (c == 't' && end - p >= 4 && !std::memcmp(p, "true", 4)) {
+            v->type = JValue::Bool;
+            v->b = true;
+            p += 4;
+            return v;
+        }
+        if (c == 'f' && end - p >= 5 && !std::memcmp(p, "false", 5)) {
+            v->type = JValue::Bool;
+            p += 5;
+            return v;
+        }
+        if (c == 'n' && end - p >= 4 && !std::memcmp(p, "null", 4)) {
+            p += 4;
+            return v;
+        }
+        if (c == '-' || (c >= '0' && c <= '9')) {
+            const char* s = p;
+            if (*p == '-') ++p;
+            while (p < end && ((*p >= '0' && *p <= '9') || *p == '.' || *p == 'e' || *p == 'E' || *p == '+' || *p == '-')) ++p;
+            v->type = JValue::Number;
+            v->text.assign(s, p);
+            return v;
+        }
+        fail("expected value");
+    }
+    std::string string() {
+        ++p;  // opening quote
+        std::string out;
+        while (p < end && *p != '"') {
+            if (*p == '\\') {
+                ++p;
+                if (p >= end) fail("EOF while parsing a string");
+                switch (*p) {
+                    case 'n': out += '\n'; break;
+                    case 't': out += '\t'; break;
+                    case 'r': out += '\r'; break;
+                    case 'b': out += '\b'; break;
+                    case 'f': out += '\f'; break;
+                    case 'u': {
+                        if (end - p < 5) fail("invalid escape");
+                        unsigned cp = (unsigned)std::strtoul(std::string(p + 1, p + 5).c_str(), 0, 16);
+                        p += 4;
+                        if (cp < 0x80) out += (char)cp;
+                        else if (cp < 0x800) { out += (char)(0xC0 | (cp >> 6)); out += (char)(0x80 | (cp & 0x3F)); }
+                        else { out += (char)(0xE0 | (cp >> 12)); out += (char)(0x80 | ((cp >> 6) & 0x3F)); out += (char)(0x80 | (cp & 0x3F)); }
+                        break;
+                    }
+                    default: out += *p; break;
+                }
+                ++p;
+            } else {
+                out += *p++;
+            }
+        }
+        if (p >= end) fail("EOF while parsing a string");
+        ++p;
+        return out;
+    }
+};
+
+const JValue& need(const JValue& v, const char* key) {
+    if (v.type != JValue::Object) throw ParseError(std::string("expected a map with field `") + key + "`");
+    const JValue* r = v.get(key);
+    if (!r) throw ParseError(std::string("missing field `") + key + "`");
+    return *r;
+}
+float as_f32(const JValue& v) {  // serde_json: parsed as f64, cast to f32
+    if (v.type != JValue::Number) throw ParseError("invalid type: expected f32");
+    return (float)std::strtod(v.text.c_str(), 0);
+}
+uint64_t as_u64(const JValue& v) {
+    if (v.type != JValue::Number || v.text.empty() || v.text[0] == '-' || v.text.find_first_of(".eE") != std::string::npos)
+        throw ParseError("invalid type: expected u64");
+    return std::strtoull(v.text.c_str(), 0, 10);
+}
+void as_vec3(const JValue& v, float out[3]) {
+    if (v.type != JValue::Array || v.arr.size() != 3) throw ParseError("invalid length, expected 3 floats");
+    for (int i = 0; i < 3; ++i) out[i] = as_f32(*v.arr[i]);
+}
+Affine as_affine(const JValue& v) {
+    if (v.type != JValue::Array || v.arr.size() != 12) throw ParseError("invalid length, expected 12 floats");
+    Affine a;
+    for (int i = 0; i < 12; ++i) a.f[i] = as_f32(*v.arr[i]);
+    return a;
+}
+Rect as_rect(const JValue& v) {
+    Rect r;
+    r.material = as_u64(need(v, "material"));
+    r.half_width = as_f32(need(v, "half_width"));
+    r.half_height = as_f32(need(v, "half_height"));
+    as_vec3(need(v, "x"), r.x);
+    as_vec3(need(v, "y"), r.y);
+    as_vec3(need(v, "z"), r.z);
+    return r;
+}
+const JValue* opt(const JValue& v, const char* key) {
+    const JValue* r = v.type == JValue::Object ? v.get(key) : 0;
+    return (r && r->type != JValue::Null) ? r : 0;
+}
+
+Object parse_object(const JValue& v) {
+    Object o = Object();
+    if (const JValue* r = opt(v, "object_ref")) {
+        o.has_object_ref = true;
+        o.object_ref = as_u64(*r);
+    }
+    if (const JValue* t = opt(v, "tag")) {
+        if (t->type != JValue::String) throw ParseError("invalid type: tag must be a string");
+        o.has_tag = true;
+        o.tag = t->text;
+    }
+    o.flags = (uint32_t)as_u64(need(need(v, "flags"), "bits"));
+    const JValue& tf = need(v, "transform");
+    o.transform_world = as_affine(need(tf, "transform_world"));
+    o.transform_local = as_affine(need(tf, "transform_local"));
+    if (const JValue* p = opt(tf, "transform_parent")) {
+        o.has_parent = true;
+        o.transform_parent = as_affine(*p);
+    }
+    if (const JValue* c = opt(v, "children")) {
+        o.has_children = true;
+        for (size_t i = 0; i < c->arr.size(); ++i) o.children.push_back(as_u64(*c->arr[i]));
+    }
+    const JValue& inner = need(v, "inner");
+    if (inner.type == JValue::String) {
+        if (inner.text != "Empty") throw ParseError("unknown variant `" + inner.text + "`");
+        o.kind = OBJ_EMPTY;
+    } else if (inner.type == JValue::Object && inner.obj.size() == 1) {
+        const std::string& k = inner.obj[0].first;
+        const JValue& b = *inner.obj[0].second;
+        if (k == "Empty") {
+            o.kind = OBJ_EMPTY;
+        } else if (k == "Camera") {
+            o.kind = OBJ_CAMERA;
+            o.camera.sensor_size = as_f32(need(b, "sensor_size"));
+            o.camera.focal_length = as_f32(need(b, "focal_length"));
+            o.camera.aspect_ratio = as_f32(need(b, "aspect_ratio"));
+            o.camera.fstop = as_f32(need(b, "fstop"));
+            if (const JValue* f = opt(b, "focus")) {
+                o.camera.has_focus = true;
+                o.camera.focus = as_f32(*f);
+            }
+        } else if (k == "Sphere") {
+            o.kind = OBJ_SPHERE;
+            o.material = as_u64(need(b, "material"));
+            if (const JValue* vol = opt(b, "volume")) {
+                o.has_volume = true;
+                o.volume = as_u64(*vol);
+            }
+            o.radius = as_f32(need(b, "radius"));
+        } else if (k == "Rect") {
+            o.kind = OBJ_RECT;
+            o.rect = as_rect(b);
+        } else if (k == "Cuboid") {
+            o.kind = OBJ_CUBOID;
+            const JValue& faces = need(b, "faces");
+            if (faces.type != JValue::Array || faces.arr.size() != 6) throw ParseError("invalid length, expected an array of length 6");
+            for (int i = 0; i < 6; ++i) {
+                const JValue& pair = *faces.arr[i];
+                if (pair.type != JValue::Array || pair.arr.size() != 2) throw ParseError("invalid length, expected a tuple of size 2");
+                as_vec3(*pair.arr[0], o.face_offset[i]);
+                o.faces[i] = as_rect(*pair.arr[1]);
+            }
+        } else {
+            throw ParseError("unknown variant `" + k + "`, expected one of `Empty`, `Camera`, `Sphere`, `Rect`, `Cuboid`");
+        }
+    } else {
+        throw ParseError("invalid type for ObjectKind");
+    }
+    return o;
+}
+
+Data parse_data(const JValue& v) {
+    Data d = Data();
+    const JValue& inner = need(v, "inner");
+    if (inner.type != JValue::Object || inner.obj.size() != 1) throw ParseError("invalid type for DataKind");
+    const std::string& k = inner.obj[0].first;
+    const JValue& b = *inner.obj[0].second;
+    if (k == "Material") {
+        d.kind = DATA_MATERIAL;
+        if (b.type != JValue::Object || b.obj.size() != 1) throw ParseError("invalid type for Material");
+        const std::string& mk = b.obj[0].first;
+        const JValue& m = *b.obj[0].second;
+        static const char* names[5] = {"Flat", "Diffuse", "Metallic", "Glass", "Emissive"};
+        d.mat_kind = -1;
+        for (int i = 0; i < 5; ++i)
+            if (mk == names[i]) d.mat_kind = i;
+        if (d.mat_kind < 0) throw ParseError("unknown variant `" + mk + "`");
+        const JValue& a = need(m, "albedo");
+        d.albedo[0] = as_f32(need(a, "r"));
+        d.albedo[1] = as_f32(need(a, "g"));
+        d.albedo[2] = as_f32(need(a, "b"));
+        if (d.mat_kind == MAT_DIFFUSE || d.mat_kind == MAT_METALLIC || d.mat_kind == MAT_GLASS) d.roughness = as_f32(need(m, "roughness"));
+        if (d.mat_kind == MAT_GLASS) d.ior = as_f32(need(m, "ior"));
+        if (d.mat_kind == MAT_EMISSIVE) d.intensity = as_f32(need(m, "intensity"));
+    } else if (k == "Volume") {
+        d.kind = DATA_VOLUME;
+        if (b.type != JValue::Object || b.obj.size() != 1 || b.obj[0].first != "DensityMap") throw ParseError("unknown Volume variant");
+        const JValue& m = *b.obj[0].second;
+        d.width = as_u64(need(m, "width"));
+        d.height = as_u64(need(m, "height"));
+        d.depth = as_u64(need(m, "depth"));
+        as_vec3(need(m, "size"), d.size);
+        const JValue& buf = need(m, "buffer");
+        if (buf.type != JValue::Array) throw ParseError("invalid type: buffer must be a sequence");
+        d.buffer.reserve(buf.arr.size());
+        for (size_t i = 0; i < buf.arr.size(); ++i) d.buffer.push_back(as_f32(*buf.arr[i]));
+    } else {
+        throw ParseError("unknown variant `" + k + "`, expected `Material` or `Volume`");
+    }
+    return d;
+}
+
+std::string gunzip(const void* bytes, size_t n) {
+    z_stream zs;
+    std::memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, 16 + MAX_WBITS) != Z_OK) throw ParseError("zlib init failed");
+    zs.next_in = (Bytef*)bytes;
+    zs.avail_in = (uInt)n;
+    std::string out;
+    char buf[1 << 15];
+    int rc;
+    do {
+        zs.next_out = (Bytef*)buf;
+        zs.avail_out = sizeof buf;
+        rc = inflate(&zs, Z_NO_FLUSH);
+        if (rc != Z_OK && rc != Z_STREAM_END) {
+            inflateEnd(&zs);
+            throw ParseError("corrupt deflate stream");
+        }
+        out.append(buf, sizeof buf - zs.avail_out);
+    } while (rc != Z_STREAM_END);
+    inflateEnd(&zs);
+    return out;
+}
+
+// ---- writer ----
+void put_f32(std::string& s, float v) {
+    if (!std::isfinite(v)) {  // serde_json writes non-finite floats as null
+        s += "null";
+        return;
+    }
+    char buf[48];
+    std::to_chars_result r = std::to_chars(buf, buf + sizeof buf, v);
+    std::string t(buf, r.ptr);
+    if (t.find_first_of(".eEn") == std::string::npos) t += ".0";
+    s += t;
+}
+void put_u64(std::string& s, uint64_t v) { s += std::to_string(v); }
+void put_vec3(std::string& s, const float v[3]) {
+    s += '[';
+    for (int i = 0; i < 3; ++i) {
+        if (i) s += ',';
+        put_f32(s, v[i]);
+    }
+    s += ']';
+}
+void put_affine(std::string& s, const Affine& a) {
+    s += '[';
+    for (int i = 0; i < 12; ++i) {
+        if (i) s += ',';
+        put_f32(s, a.f[i]);
+    }
+    s += ']';
+}
+void put_string(std::string& s, const std::string& v) {
+    s += '"';
+    for (size_t i = 0; i < v.size(); ++i) {
+        unsigned char c = (unsigned char)v[i];
+        if (c == '"' || c == '\\') { s += '\\'; s += (char)c; }
+        else if (c == '\n') s += "\\n";
+        else if (c == '\t') s += "\\t";
+        else if (c == '\r') s += "\\r";
+        else if (c < 0x20) { char b[8]; std::snprintf(b, sizeof b, "\\u%04x", c); s += b; }
+        else s += (char)c;
+    }
+    s += '"';
+}
+void put_rect(std::string& s, const Rect& r) {
+    s += "{\"material\":";
+    put_u64(s, r.material);
+    s += ",\"half_width\":";
+    put_f32(s, r.half_width);
+    s += ",\"half_height\":";
+    put_f32(s, r.half_height);
+    s += ",\"x\":";
+    put_vec3(s, r.x);
+    s += ",\"y\":";
+    put_vec3(s, r.y);
+    s += ",\"z\":";
+    put_vec3(s, r.z);
+    s += '}';
+}
+
+// ---- f32 helpers in glam's operation order (host code is built with -ffp-contract=off) ----
+inline void mat_vec(const Affine& a, const float v[3], float out[3]) {  // Mat3A * Vec3A
+    for (int i = 0; i < 3; ++i) {
+        float r = a.f[i] * v[0];
+        r = r + a.f[3 + i] * v[1];
+        r = r + a.f[6 + i] * v[2];
+        out[i] = r;
+    }
+}
+inline float f32_dec(float x) {
+    uint32_t b;
+    std::memcpy(&b, &x, 4);
+    b -= 1;
+    std::memcpy(&x, &b, 4);
+    return x;
+}
+inline float4 f4(float x, float y, float z, float w) {
+    float4 r;
+    r.x = x; r.y = y; r.z = z; r.w = w;
+    return r;
+}
+inline float as_f(uint32_t u) {
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+
+}  // namespace
+
+float uniform_scale(float low, float high) {  // rand 0.8.5 UniformFloat::new
+    const float max_rand = 1.0f - 1.1920929e-07f;
+    float scale = high - low;
+    while (scale * max_rand + low >= high) scale = f32_dec(scale);
+    return scale;
+}
+float uniform_scale_inclusive(float low, float high) {  // UniformFloat::new_inclusive
+    const float max_rand = 1.0f - 1.1920929e-07f;
+    float scale = (high - low) / max_rand;
+    while (scale * max_rand + low > high) scale = f32_dec(scale);
+    return scale;
+}
+
+Affine affine_mul(const Affine& a, const Affine& b) {  // glam Affine3A * Affine3A
+    Affine r;
+    mat_vec(a, &b.f[0], &r.f[0]);
+    mat_vec(a, &b.f[3], &r.f[3]);
+    mat_vec(a, &b.f[6], &r.f[6]);
+    float t[3];
+    mat_vec(a, &b.f[9], t);
+    for (int i = 0; i < 3; ++i) r.f[9 + i] = t[i] + a.f[9 + i];
+    return r;
+}
+Affine affine_inverse(const Affine& a) {  // glam Mat3A::inverse (cross / det, transposed)
+    const float* x = &a.f[0];
+    const float* y = &a.f[3];
+    const float* z = &a.f[6];
+    float t0[3] = {y[1] * z[2] - z[1] * y[2], y[2] * z[0] - z[2] * y[0], y[0] * z[1] - z[0] * y[1]};
+    float t1[3] = {z[1] * x[2] - x[1] * z[2], z[2] * x[0] - x[2] * z[0], z[0] * x[1] - x[0] * z[1]};
+    float t2[3] = {x[1] * y[2] - y[1] * x[2], x[2] * y[0] - y[2] * x[0], x[0] * y[1] - y[0] * x[1]};
+    float det = (z[0] * t2[0] + z[1] * t2[1]) + z[2] * t2[2];
+    float inv_det = 1.0f / det;
+    Affine r;
+    for (int i = 0; i < 3; ++i) {
+        r.f[0 + i] = (i == 0 ? t0[0] : i == 1 ? t1[0] : t2[0]) * inv_det;
+        r.f[3 + i] = (i == 0 ? t0[1] : i == 1 ? t1[1] : t2[1]) * inv_det;
+        r.f[6 + i] = (i == 0 ? t0[2] : i == 1 ? t1[2] : t2[2]) * inv_det;
+    }
+    float t[3];
+    mat_vec(r, &a.f[9], t);
+    for (int i = 0; i < 3; ++i) r.f[9 + i] = -t[i];
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Scene
+// ------------------------------------------------------------------------------------------
+Scene Scene::from_json(const void* bytes, size_t n) {
+    std::string text;
+    const unsigned char* b = (const unsigned char*)bytes;
+    if (n >= 2 && b[0] == 0x1f && b[1] == 0x8b)
+        text = gunzip(bytes, n);
+    else
+        text.assign((const char*)bytes, n);
+    Parser ps;
+    ps.p = ps.start = text.data();
+    ps.end = text.data() + text.size();
+    JPtr root = ps.value();
+    ps.ws();
+    if (ps.p != ps.end) ps.fail("trailing characters");
+
+    Scene s = Scene();
+    const JValue& r = *root;
+    if (const JValue* roots = opt(r, "roots"))
+        for (size_t i = 0; i < roots->arr.size(); ++i) s.roots.push_back(as_u64(*roots->arr[i]));
+    s.root_material = as_u64(need(r, "root_material"));
+    const JValue& objs = need(r, "objects");
+    const JValue& ocoll = need(objs, "collection");
+    if (ocoll.type != JValue::Object) throw ParseError("invalid type: objects.collection must be a map");
+    for (size_t i = 0; i < ocoll.obj.size(); ++i) {
+        char* endp = 0;
+        uint64_t key = std::strtoull(ocoll.obj[i].first.c_str(), &endp, 10);
+        if (ocoll.obj[i].first.empty() || *endp) throw ParseError("invalid ObjectRef key `" + ocoll.obj[i].first + "`");
+        s.objects[key] = parse_object(*ocoll.obj[i].second);
+    }
+    s.objects_next_key = as_u64(need(objs, "next_key"));
+    const JValue& datas = need(r, "data");
+    const JValue& dcoll = need(datas, "collection");
+    if (dcoll.type != JValue::Object) throw ParseError("invalid type: data.collection must be a map");
+    for (size_t i = 0; i < dcoll.obj.size(); ++i) {
+        char* endp = 0;
+        uint64_t key = std::strtoull(dcoll.obj[i].first.c_str(), &endp, 10);
+        if (dcoll.obj[i].first.empty() || *endp) throw ParseError("invalid DataRef key `" + dcoll.obj[i].first + "`");
+        s.data[key] = parse_data(*dcoll.obj[i].second);
+    }
+    s.data_next_key = as_u64(need(datas, "next_key"));
+    s.lens_config.kappa = 0.05f;
+    s.lens_config.h_min = 0.02f;
+    s.lens_config.h_max = 5.0f;
+    s.lens_config.r_far = 500.0f;
+    s.lens_config.max_steps = 4096;
+    s.lens_config.flags = 0;
+    if (const JValue* lenses = opt(r, "lenses")) {  // extension; serde ignores unknown keys
+        if (lenses->type != JValue::Array) throw ParseError("invalid type: lenses must be a sequence");
+        for (size_t i = 0; i < lenses->arr.size(); ++i) {
+            const JValue& l = *lenses->arr[i];
+            if (l.type != JValue::Array || l.arr.size() != 4) throw ParseError("invalid length, expected [x, y, z, r_s]");
+            Lens ln;
+            for (int k = 0; k < 3; ++k) ln.c[k] = as_f32(*l.arr[k]);
+            ln.rs = as_f32(*l.arr[3]);
+            s.lenses.push_back(ln);
+        }
+    }
+    return s;
+}
+
+std::string Scene::to_json() const {
+    std::string s;
+    s += "{\"roots\":[";
+    for (size_t i = 0; i < roots.size(); ++i) {
+        if (i) s += ',';
+        put_u64(s, roots[i]);
+    }
+    s += "],\"root_material\":";
+    put_u64(s, root_material);
+    s += ",\"objects\":{\"collection\":{";
+    bool first = true;
+    for (std::map<uint64_t, Object>::const_iterator it = objects.begin(); it != objects.end(); ++it) {
+        const Object& o = it->second;
+        if (!first) s += ',';
+        first = false;
+        s += '"';
+        put_u64(s, it->first);
+        s += "\":{\"object_ref\":";
+        if (o.has_object_ref) put_u64(s, o.object_ref); else s += "null";
+        s += ",\"tag\":";
+        if (o.has_tag) put_string(s, o.tag); else s += "null";
+        s += ",\"flags\":{\"bits\":";
+        put_u64(s, o.flags);
+        s += "},\"transform\":{\"transform_world\":";
+        put_affine(s, o.transform_world);
+        s += ",\"transform_local\":";
+        put_affine(s, o.transform_local);
+        s += ",\"transform_parent\":";
+        if (o.has_parent) put_affine(s, o.transform_parent); else s += "null";
+        s += "},\"inner\":";
+        switch (o.kind) {
+            case OBJ_EMPTY: s += "\"Empty\""; break;
+            case OBJ_CAMERA:
+                s += "{\"Camera\":{\"sensor_size\":";
+                put_f32(s, o.camera.sensor_size);
+                s += ",\"focal_length\":";
+                put_f32(s, o.camera.focal_length);
+                s += ",\"aspect_ratio\":";
+                put_f32(s, o.camera.aspect_ratio);
+                s += ",\"fstop\":";
+                put_f32(s, o.camera.fstop);
+                s += ",\"focus\":";
+                if (o.camera.has_focus) put_f32(s, o.camera.focus); else s += "null";
+                s += "}}";
+                break;
+            case OBJ_SPHERE:
+                s += "{\"Sphere\":{\"material\":";
+                put_u64(s, o.material);
+                s += ",\"volume\":";
+                if (o.has_volume) put_u64(s, o.volume); else s += "null";
+                s += ",\"radius\":";
+                put_f32(s, o.radius);
+                s += "}}";
+                break;
+            case OBJ_RECT:
+                s += "{\"Rect\":";
+                put_rect(s, o.rect);
+                s += '}';
+                break;
+            case OBJ_CUBOID:
+                s += "{\"Cuboid\":{\"faces\":[";
+                for (int i = 0; i < 6; ++i) {
+                    if (i) s += ',';
+                    s += '[';
+                    put_vec3(s, o.face_offset[i]);
+                    s += ',';
+                    put_rect(s, o.faces[i]);
+                    s += ']';
+                }
+                s += "]}}";
+                break;
+        }
+        s += ",\"children\":";
+        if (o.has_children) {
+            s += '[';
+            for (size_t i = 0; i < o.children.size(); ++i) {
+                if (i) s += ',';
+                put_u64(s, o.children[i]);
+            }
+            s += ']';
+        } else {
+            s += "null";
+        }
+        s += '}';
+    }
+    s += "},\"next_key\":";
+    put_u64(s, objects_next_key);
+    s += "},\"data\":{\"collection\":{";
+    first = true;
+    for (std::map<uint64_t, Data>::const_iterator it = data.begin(); it != data.end(); ++it) {
+        const Data& d = it->second;
+        if (!first) s += ',';
+        first = false;
+        s += '"';
+        put_u64(s, it->first);
+        s += "\":{\"inner\":";
+        if (d.kind == DATA_MATERIAL) {
+            static const char* names[5] = {"Flat", "Diffuse", "Metallic", "Glass", "Emissive"};
+            s += "{\"Material\":{\"";
+            s += names[d.mat_kind];
+            s += "\":{\"albedo\":{\"r\":";
+            put_f32(s, d.albedo[0]);
+            s += ",\"g\":";
+            put_f32(s, d.albedo[1]);
+            s += ",\"b\":";
+            put_f32(s, d.albedo[2]);
+            s += '}';
+            if (d.mat_kind == MAT_DIFFUSE || d.mat_kind == MAT_METALLIC || d.mat_kind == MAT_GLASS) {
+                s += ",\"roughness\":";
+                put_f32(s, d.roughness);
+            }
+            if (d.mat_kind == MAT_GLASS) {
+                s += ",\"ior\":";
+                put_f32(s, d.ior);
+            }
+            if (d.mat_kind == MAT_EMISSIVE) {
+                s += ",\"intensity\":";
+                put_f32(s, d.intensity);
+            }
+            s += "}}}";
+        } else {
+            s += "{\"Volume\":{\"DensityMap\":{\"width\":";
+            put_u64(s, d.width);
+            s += ",\"height\":";
+            put_u64(s, d.height);
+            s += ",\"depth\":";
+            put_u64(s, d.depth);
+            s += ",\"size\":";
+            put_vec3(s, d.size);
+            s += ",\"buffer\":[";
+            for (size_t i = 0; i < d.buffer.size(); ++i) {
+                if (i) s += ',';
+                put_f32(s, d.buffer[i]);
+            }
+            s += "]}}}";
+        }
+        s += '}';
+    }
+    s += "},\"next_key\":";
+    put_u64(s, data_next_key);
+    s += '}';
+    if (!lenses.empty()) {
+        s += ",\"lenses\":[";
+        for (size_t i = 0; i < lenses.size(); ++i) {
+            if (i) s += ',';
+            s += '[';
+            for (int k = 0; k < 3; ++k) {
+                put_f32(s, lenses[i].c[k]);
+                s += ',';
+            }
+            put_f32(s, lenses[i].rs);
+            s += ']';
+        }
+        s += ']';
+    }
+    s += '}';
+    return s;
+}
+
+bool Scene::find_by_tag(const char* tag, uint64_t* out) const {
+    for (std::map<uint64_t, Object>::const_iterator it = objects.begin(); it != objects.end(); ++it)
+        if (it->second.has_tag && it->second.tag == tag) {
+            *out = it->first;
+            return true;
+        }
+    return false;
+}
+Object& Scene::get_object(uint64_t r) {
+    std::map<uint64_t, Object>::iterator it = objects.find(r);
+    if (it == objects.end()) throw SceneError("invalid object ref");
+    return it->second;
+}
+const Object& Scene::get_object(uint64_t r) const {
+    std::map<uint64_t, Object>::const_iterator it = objects.find(r);
+    if (it == objects.end()) throw SceneError("invalid object ref");
+    return it->second;
+}
+const Data& Scene::get_data(uint64_t r) const {
+    std::map<uint64_t, Data>::const_iterator it = data.find(r);
+    if (it == data.end()) throw SceneError("invalid data ref");
+    return it->second;
+}
+
+namespace {
+// Object::apply_parent_transform, object/mod.rs:200-210 (the queue is replaced by recursion: the
+// reference's breadth-first UpdateQueue::commit reaches the same fixed point)
+void apply_parent(Scene& s, uint64_t ref, const Affine& parent, int depth) {
+    if (depth > 256) throw SceneError("scene graph cycle");
+    Object& o = s.get_object(ref);
+    o.has_parent = true;
+    o.transform_parent = parent;
+    o.transform_world = affine_mul(parent, o.transform_local);  // transform.rs:45-48
+    Affine world = o.transform_world;
+    std::vector<uint64_t> children = o.children;
+    for (size_t i = 0; i < children.size(); ++i) apply_parent(s, children[i], world, depth + 1);
+}
+}  // namespace
+
+void Scene::apply_transform(uint64_t object_ref, const Affine& affine) {  // object/mod.rs:212-223
+    Object& o = get_object(object_ref);
+    o.transform_local = affine_mul(o.transform_local, affine);  // transform.rs:34-42
+    o.transform_world = o.has_parent ? affine_mul(o.transform_parent, o.transform_local) : o.transform_local;
+    Affine world = o.transform_world;
+    std::vector<uint64_t> children = o.children;
+    for (size_t i = 0; i < children.size(); ++i) apply_parent(*this, children[i], world, 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// flattening
+// ------------------------------------------------------------------------------------------
+namespace {
+
+void push_rect(std::vector<float4>& blob, const Rect& r, const Affine& tf, int type, uint32_t mat, uint32_t obj) {
+    float n[3];
+    mat_vec(tf, r.z, n);  // rect.rs:119: transform.transform_vector3a(self.z)
+    // local = M^-1 (pos - T);  local.x = dot(pos, ax) + cx with ax = M^-T x, cx = -dot(ax, T)
+    double m[9], inv[9];
+    for (int i = 0; i < 9; ++i) m[i] = tf.f[i];
+    // column-major: element (row r, col c) = m[3*c + r]
+    double det = m[0] * (m[4] * m[8] - m[7] * m[5]) - m[3] * (m[1] * m[8] - m[7] * m[2]) + m[6] * (m[1] * m[5] - m[4] * m[2]);
+    double id = 1.0 / det;
+    // inverse, row-major rows R0,R1,R2 (so that local = R * (pos - T))
+    inv[0] = (m[4] * m[8] - m[7] * m[5]) * id;
+    inv[1] = (m[6] * m[5] - m[3] * m[8]) * id;
+    inv[2] = (m[3] * m[7] - m[6] * m[4]) * id;
+    inv[3] = (m[7] * m[2] - m[1] * m[8]) * id;
+    inv[4] = (m[0] * m[8] - m[6] * m[2]) * id;
+    inv[5] = (m[6] * m[1] - m[0] * m[7]) * id;
+    inv[6] = (m[1] * m[5] - m[4] * m[2]) * id;
+    inv[7] = (m[3] * m[2] - m[0] * m[5]) * id;
+    inv[8] = (m[0] * m[4] - m[3] * m[1]) * id;
+    double ax[3], ay[3];
+    for (int k = 0; k < 3; ++k) {
+        ax[k] = r.x[0] * inv[0 + k] + r.x[1] * inv[3 + k] + r.x[2] * inv[6 + k];
+        ay[k] = r.y[0] * inv[0 + k] + r.y[1] * inv[3 + k] + r.y[2] * inv[6 + k];
+    }
+    double cx = -(ax[0] * tf.f[9] + ax[1] * tf.f[10] + ax[2] * tf.f[11]);
+    double cy = -(ay[0] * tf.f[9] + ay[1] * tf.f[10] + ay[2] * tf.f[11]);
+    double x2 = (double)r.x[0] * r.x[0] + (double)r.x[1] * r.x[1] + (double)r.x[2] * r.x[2];
+    double y2 = (double)r.y[0] * r.y[0] + (double)r.y[1] * r.y[1] + (double)r.y[2] * r.y[2];
+    float hw2 = (float)((double)(r.half_width * r.half_width) / x2);
+    float hh2 = (float)((double)(r.half_height * r.half_height) / y2);
+    float area = 4.0f * r.half_width * r.half_height;  // rect.rs:88-90
+    blob.push_back(f4(n[0], n[1], n[2], hw2));
+    blob.push_back(f4(tf.f[9], tf.f[10], tf.f[11], hh2));
+    blob.push_back(f4((float)ax[0], (float)ax[1], (float)ax[2], (float)cx));
+    blob.push_back(f4((float)ay[0], (float)ay[1], (float)ay[2], (float)cy));
+    blob.push_back(f4(as_f((uint32_t)type), as_f(mat), area, as_f(obj)));
+}
+
+}  // namespace
+
+FlatScene flatten(const Scene& scene) {
+    FlatScene fs;
+    std::memset(&fs.header, 0, sizeof fs.header);
+    fs.diffuse_without_light = false;
+    fs.unsupported_light = false;
+
+    // data tables
+    std::map<uint64_t, uint32_t> mat_index, vol_index;
+    std::vector<float4> mats, vols;
+    for (std::map<uint64_t, Data>::const_iterator it = scene.data.begin(); it != scene.data.end(); ++it) {
+        const Data& d = it->second;
+        if (d.kind == DATA_MATERIAL) {
+            mat_index[it->first] = (uint32_t)(mats.size() / MAT_STRIDE);
+            mats.push_back(f4(d.albedo[0], d.albedo[1], d.albedo[2], as_f((uint32_t)d.mat_kind)));
+            mats.push_back(f4(d.roughness, d.ior, d.intensity, 0.0f));
+        } else {
+            if (d.buffer.size() != d.width * d.height * d.depth && d.width && d.height && d.depth)
+                throw SceneError("index out of bounds: density buffer length does not match width*height*depth");
+            for (int k = 0; k < 3; ++k) {
+                uint64_t dim = k == 0 ? d.width : k == 1 ? d.height : d.depth;
+                if (dim && !(d.size[k] >= 0.0f && std::ceil(d.size[k]) <= (float)(dim - 1))) throw SceneError("volume index out of bounds");
+            }
+            for (size_t i = 0; i < d.buffer.size(); ++i)
+                if (!(d.buffer[i] >= 0.0f)) throw SceneError("p is outside range [0.0, 1.0] (negative or NaN density)");
+            vol_index[it->first] = (uint32_t)(vols.size() / VOL_STRIDE);
+            vols.push_back(f4(as_f((uint32_t)d.width), as_f((uint32_t)d.height), as_f((uint32_t)d.depth), as_f((uint32_t)fs.grids.size())));
+            vols.push_back(f4(d.size[0], d.size[1], d.size[2], 0.0f));
+            fs.grids.insert(fs.grids.end(), d.buffer.begin(), d.buffer.end());
+        }
+    }
+    struct Resolve {
+        const Scene& s;
+        std::map<uint64_t, uint32_t>& mi;
+        uint32_t material(uint64_t r) const {
+            const Data& d = s.get_data(r);
+            if (d.kind != DATA_MATERIAL) throw SceneError("expected material data");
+            return mi[r];
+        }
+    } resolve = {scene, mat_index};
+
+    // root material folded to the ColorData sample_root returns (src/tracer/mod.rs:429-452)
+    {
+        const Data& d = scene.get_data(scene.root_material);
+        if (d.kind != DATA_MATERIAL) throw SceneError("expected root material to be a material");
+        SceneHeader& h = fs.header;
+        for (int k = 0; k < 3; ++k) {
+            switch (d.mat_kind) {
+                case MAT_FLAT: h.root_color[k] = 0.0f + d.albedo[k]; h.root_albedo[k] = 0.0f; break;
+                case MAT_EMISSIVE: h.root_color[k] = 0.0f + d.albedo[k] * d.intensity; h.root_albedo[k] = 0.0f; break;
+                default: h.root_color[k] = d.albedo[k] + 0.0f; h.root_albedo[k] = d.albedo[k]; break;
+            }
+        }
+        h.root_keeps_normal = d.mat_kind == MAT_EMISSIVE ? 0u : 1u;
+    }
+
+    std::vector<float4> prims, lights;
+    bool any_diffuse = false;
+    for (std::map<uint64_t, Object>::const_iterator it = scene.objects.begin(); it != scene.objects.end(); ++it) {
+        const Object& o = it->second;
+        uint32_t obj = (uint32_t)fs.object_refs.size();
+        fs.object_refs.push_back(it->first);
+        uint32_t first_prim = (uint32_t)(prims.size() / PRIM_STRIDE);
+        uint32_t n_prims = 0;
+        const Affine& tf = o.transform_world;
+        if (o.kind == OBJ_SPHERE) {
+            uint32_t mat = resolve.material(o.material);
+            uint32_t vol = 0xffffffffu;
+            if (o.has_volume) {
+                const Data& d = scene.get_data(o.volume);
+                if (d.kind != DATA_VOLUME) throw SceneError("expected volume data");
+                vol = vol_index[o.volume];
+                fs.header.has_volume_prims = 1;
+            }
+            float r = o.radius;
+            prims.push_back(f4(tf.f[9], tf.f[10], tf.f[11], r));
+            prims.push_back(f4(r * r, 3.14159265358979323846f * r * r, 0.0f, 0.0f));
+            prims.push_back(f4(0, 0, 0, 0));
+            prims.push_back(f4(0, 0, 0, 0));
+            prims.push_back(f4(as_f(PRIM_SPHERE), as_f(mat), as_f(vol), as_f(obj)));
+            n_prims = 1;
+            any_diffuse |= scene.get_data(o.material).mat_kind == MAT_DIFFUSE;
+        } else if (o.kind == OBJ_RECT) {
+            push_rect(prims, o.rect, tf, PRIM_RECT, resolve.material(o.rect.material), obj);
+            n_prims = 1;
+            any_diffuse |= scene.get_data(o.rect.material).mat_kind == MAT_DIFFUSE;
+        } else if (o.kind == OBJ_CUBOID) {
+            for (int i = 0; i < 6; ++i) {
+                // transform * Affine3A::from_translation(offset), cuboid.rs:95
+                Affine ftf = tf;
+                float t[3];
+                mat_vec(tf, o.face_offset[i], t);
+                for (int k = 0; k < 3; ++k) ftf.f[9 + k] = t[k] + tf.f[9 + k];
+                push_rect(prims, o.faces[i], ftf, PRIM_CUBOID_FACE, resolve.material(o.faces[i].material), obj);
+                any_diffuse |= scene.get_data(o.faces[i].material).mat_kind == MAT_DIFFUSE;
+            }
+            n_prims = 6;
+        }
+        if (o.flags & 1u) {  // ObjectFlags::LIGHT
+            if (o.kind == OBJ_CUBOID) {
+                fs.unsupported_light = true;
+                continue;
+            }
+            size_t base = lights.size();
+            lights.resize(base + LIGHT_STRIDE, f4(0, 0, 0, 0));
+            if (o.kind == OBJ_SPHERE) {
+                lights[base] = f4(as_f(LIGHT_SPHERE), as_f(first_prim), as_f(n_prims), as_f(obj));
+                lights[base + 1] = f4(tf.f[9], tf.f[10], tf.f[11], o.radius);
+            } else if (o.kind == OBJ_RECT) {
+                const Rect& r = o.rect;
+                lights[base] = f4(as_f(LIGHT_RECT), as_f(first_prim), as_f(n_prims), as_f(obj));
+                lights[base + 1] = f4(r.x[0], r.x[1], r.x[2], -r.half_width);
+                lights[base + 2] = f4(r.y[0], r.y[1], r.y[2], -r.half_height);
+                lights[base + 3] = f4(tf.f[0], tf.f[1], tf.f[2], uniform_scale_inclusive(-r.half_width, r.half_width));
+                lights[base + 4] = f4(tf.f[3], tf.f[4], tf.f[5], uniform_scale_inclusive(-r.half_height, r.half_height));
+                lights[base + 5] = f4(tf.f[6], tf.f[7], tf.f[8], 0.0f);
+                lights[base + 6] = f4(tf.f[9], tf.f[10], tf.f[11], 0.0f);
+            } else {
+                lights[base] = f4(as_f(LIGHT_POINT), as_f(0), as_f(0), as_f(obj));
+                lights[base + 1] = f4(tf.f[9], tf.f[10], tf.f[11], 0.0f);
+            }
+        }
+    }
+
+    std::vector<float4> lens;
+    for (size_t i = 0; i < scene.lenses.size(); ++i) {
+        const Lens& l = scene.lenses[i];
+        if (!(l.rs > 0.0f)) continue;  // r_s <= 0: no mass -> exact flat limit
+        lens.push_back(f4(l.c[0], l.c[1], l.c[2], l.rs));
+        lens.push_back(f4(-1.5f * l.rs, scene.lens_config.r_far * l.rs, 0.0f, 0.0f));
+    }
+
+    SceneHeader& h = fs.header;
+    h.n_prims = (uint32_t)(prims.size() / PRIM_STRIDE);
+    h.n_mats = (uint32_t)(mats.size() / MAT_STRIDE);
+    h.n_lights = (uint32_t)(lights.size() / LIGHT_STRIDE);
+    h.n_vols = (uint32_t)(vols.size() / VOL_STRIDE);
+    h.n_lens = (uint32_t)(lens.size() / LENS_STRIDE);
+    h.prim_off = 0;
+    fs.blob = prims;
+    h.mat_off = (uint32_t)fs.blob.size();
+    fs.blob.insert(fs.blob.end(), mats.begin(), mats.end());
+    h.light_off = (uint32_t)fs.blob.size();
+    fs.blob.insert(fs.blob.end(), lights.begin(), lights.end());
+    h.vol_off = (uint32_t)fs.blob.size();
+    fs.blob.insert(fs.blob.end(), vols.begin(), vols.end());
+    h.lens_off = (uint32_t)fs.blob.size();
+    fs.blob.insert(fs.blob.end(), lens.begin(), lens.end());
+    h.blob_f4 = (uint32_t)fs.blob.size();
+    h.kappa = scene.lens_config.kappa;
+    h.h_min = scene.lens_config.h_min;
+    h.h_max = scene.lens_config.h_max;
+    h.max_steps = scene.lens_config.max_steps;
+    h.lens_exact = scene.lens_config.flags & 1u;
+    fs.diffuse_without_light = any_diffuse && h.n_lights == 0;
+    if (fs.blob.empty()) fs.blob.push_back(f4(0, 0, 0, 0));
+    if (fs.grids.empty()) fs.grids.push_back(0.0f);
+    return fs;
+}
+
+CameraBlock make_camera_block(const Scene& scene, uint64_t camera_ref, uint32_t width, uint32_t height, uint32_t subsample) {
+    const Object& o = scene.get_object(camera_ref);
+    if (o.kind != OBJ_CAMERA) throw SceneError("expected a camera object");
+    CameraBlock c;
+    std::memset(&c, 0, sizeof c);
+    for (int i = 0; i < 9; ++i) c.m[i] = o.transform_world.f[i];
+    for (int i = 0; i < 3; ++i) c.t[i] = o.transform_world.f[9 + i];
+    const Camera& cam = o.camera;
+    c.yfov = 2.0f * std::atan2(cam.sensor_size, 2.0f * cam.focal_length);  // mod.rs:248
+    c.xfov = c.yfov * cam.aspect_ratio;                                     // mod.rs:249
+    c.pixel_width = 2.0f * (1.0f / (float)width);                           // buffer.rs:68-76
+    c.pixel_height = 2.0f * (1.0f / (float)height);
+    float subpixel_scale = subsample == 0 ? 1.0f : 1.0f / (float)subsample;  // mod.rs:55-60
+    c.su_low = -0.5f * c.pixel_width * subpixel_scale;                      // mod.rs:255-265
+    c.su_scale = uniform_scale(c.su_low, 0.5f * c.pixel_width * subpixel_scale);
+    c.sv_low = -0.5f * c.pixel_height * subpixel_scale;
+    c.sv_scale = uniform_scale(c.sv_low, 0.5f * c.pixel_height * subpixel_scale);
+    c.sub_width = subsample == 0 ? 0.0f : 1.0f / (float)subsample;
+    c.sub_n = subsample == 0 ? 1u : subsample;
+    c.has_focus = cam.has_focus ? 1u : 0u;
+    c.focus = cam.focus;
+    c.aperture = 0.5f * cam.focal_length / cam.fstop;  // mod.rs:289
+    // UnitDisk::new(Vec3::NEG_Z): any_orthonormal_pair((0,0,-1)) = ((1,-0,0),(0,-1,-0))
+    c.disk_x[0] = 1.0f; c.disk_x[1] = -0.0f; c.disk_x[2] = 0.0f;
+    c.disk_y[0] = 0.0f; c.disk_y[1] = -1.0f; c.disk_y[2] = -0.0f;
+    return c;
+}
+
+}  // namespace bt

@@ -666,6 +666,11 @@ float density_trilinear(const Data& v, V3f coord) {  // volume.rs:140-167
 // lens field + geodesic segments (NOT in the reference; DESIGN.md "Geodesic model")
 // ------------------------------------------------------------------------------------------
 template <class T> inline T fma_t(T a, T b, T c) { return std::fma(a, b, c); }
+// the stepper's 1/sqrt: correctly rounded (f32: via f64, exact up to 2^-29-probability double
+// rounding).  The device's BT_LENS_EXACT_RSQRT mode (__frsqrt_rn) computes the same value; its
+// default mode uses MUFU.RSQ (<= 2 ulp).
+inline float rsqrt_t(float x) { return (float)(1.0 / std::sqrt((double)x)); }
+inline double rsqrt_t(double x) { return 1.0 / std::sqrt(x); }
 
 template <class T>
 struct LensT {
@@ -716,7 +721,7 @@ inline V3<T> accel(const Field<T>& f, V3<T> x, V3<T> v, T* rmin_out, AccelInfo* 
         T ly = fma_t(dz, v.x, -(dx * v.z));
         T lz = fma_t(dx, v.y, -(dy * v.x));
         T h2 = fma_t(lz, lz, fma_t(ly, ly, lx * lx));
-        T inv = T(1) / std::sqrt(r2);
+        T inv = rsqrt_t(r2);
         T inv2 = inv * inv;
         T inv5 = (inv2 * inv2) * inv;
         T s = (l.k * h2) * inv5;
