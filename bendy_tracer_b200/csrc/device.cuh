@@ -410,31 +410,89 @@ BT_DEV void camera_ray(const CameraBlock& cam, const Consts& k, Rng& rng, uint32
 // ------------------------------------------------------------------------------------------
 // geodesic stepper (extension; DESIGN.md "Geodesic model").  FMAs are explicit.
 // ------------------------------------------------------------------------------------------
-// a = sum_m -(3/2) r_s |d x v|^2 d / |d|^5.  INFO 1 also returns min |d|; INFO 2 adds the capture /
-// far-field flags.
-template <int INFO, bool EXACT>
-BT_DEV V3 lens_accel(const float4* lens, int n_lens, V3 x, V3 v, float& rmin, bool& captured, bool& far) {
+// The lens table is read through a provider: LensShared walks the shared-memory records,
+// LensRegs<N> holds N masses in registers with the loop fully unrolled (no LDS, no loop
+// overhead in the stepper's inner loop).
+struct LensShared {
+    const float4* p;
+    int count;
+    enum { UNROLL = 4 };
+    BT_DEV int n() const { return count; }
+    BT_DEV float4 e0(int m) const { return p[m * LENS_STRIDE]; }
+    BT_DEV float4 e1(int m) const { return p[m * LENS_STRIDE + 1]; }
+};
+template <int N>
+struct LensRegs {
+    float4 a[N], b[N];
+    enum { UNROLL = N };
+    BT_DEV explicit LensRegs(const float4* p) {
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+            a[m] = p[m * LENS_STRIDE];
+            b[m] = p[m * LENS_STRIDE + 1];
+        }
+    }
+    BT_DEV int n() const { return N; }
+    BT_DEV float4 e0(int m) const { return a[m]; }
+    BT_DEV float4 e1(int m) const { return b[m]; }
+};
+// MUFU.RSQ without the denormal-input fix-up of rsqrtf() (|d|^2 is never denormal here)
+BT_DEV float rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// Per-step cache of d0_m = x - c_m, filled by the k1 evaluation and reused by the three stage
+// evaluations (register-resident tables only; the shared-memory walk recomputes it).
+template <class L>
+struct D0Cache {
+    enum { CACHED = 0 };
+    BT_DEV V3 get(int, V3 x, float4 e0) const { return v3(x.x - e0.x, x.y - e0.y, x.z - e0.z); }
+    BT_DEV void put(int, V3) {}
+};
+template <int N>
+struct D0Cache<LensRegs<N> > {
+    enum { CACHED = 1 };
+    V3 d[N];
+    BT_DEV V3 get(int m, V3, float4) const { return d[m]; }
+    BT_DEV void put(int m, V3 v) { d[m] = v; }
+};
+// a = sum_m -(3/2) r_s |d x v|^2 d / |d|^5 evaluated at x + a*w, written as d = fma(a, w, x - c)
+// (STAGE 0: a = 0, d = x - c).  INFO 1 also returns min |d|; INFO 2 adds the capture / far flags.
+template <int INFO, bool EXACT, int STAGE, class L>
+BT_DEV V3 lens_accel(const L& lens, D0Cache<L>& cache, V3 x, float a, V3 w, V3 v, float& rmin, bool& captured, bool& far) {
     float ax = 0.0f, ay = 0.0f, az = 0.0f;
     if (INFO >= 1) rmin = __int_as_float(0x7f800000);
     if (INFO >= 2) {
         captured = false;
         far = true;
     }
-#pragma unroll 1
+    const int n_lens = lens.n();
+#pragma unroll(L::UNROLL)
     for (int m = 0; m < n_lens; ++m) {
-        float4 e0 = lens[m * LENS_STRIDE];
-        float4 e1 = lens[m * LENS_STRIDE + 1];
-        float dx = x.x - e0.x, dy = x.y - e0.y, dz = x.z - e0.z;
+        const float4 e0 = lens.e0(m);  // (c.xyz, -1.5 r_s)
+        float dx, dy, dz;
+        if (STAGE == 0) {
+            dx = x.x - e0.x;
+            dy = x.y - e0.y;
+            dz = x.z - e0.z;
+            cache.put(m, v3(dx, dy, dz));
+        } else {
+            const V3 d0 = cache.get(m, x, e0);
+            dx = fmaf(a, w.x, d0.x);
+            dy = fmaf(a, w.y, d0.y);
+            dz = fmaf(a, w.z, d0.z);
+        }
         float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
         float lx = fmaf(dy, v.z, -(dz * v.y));
         float ly = fmaf(dz, v.x, -(dx * v.z));
         float lz = fmaf(dx, v.y, -(dy * v.x));
         float h2 = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
         // fast: MUFU.RSQ (<= 2 ulp); exact: correctly rounded, bit-identical to the CPU oracle
-        float inv = EXACT ? __frsqrt_rn(r2) : rsqrtf(r2);
+        float inv = EXACT ? __frsqrt_rn(r2) : rsqrt_approx(r2);
         float inv2 = inv * inv;
         float inv5 = (inv2 * inv2) * inv;
-        float s = (e1.x * h2) * inv5;
+        float s = (e0.w * h2) * inv5;
         ax = fmaf(s, dx, ax);
         ay = fmaf(s, dy, ay);
         az = fmaf(s, dz, az);
@@ -442,7 +500,8 @@ BT_DEV V3 lens_accel(const float4* lens, int n_lens, V3 x, V3 v, float& rmin, bo
             float r = r2 * inv;
             rmin = fminf(rmin, r);
             if (INFO >= 2) {
-                if (r < e0.w) captured = true;
+                const float4 e1 = lens.e1(m);  // (r_s, r_far * r_s, -, -)
+                if (r < e1.x) captured = true;
                 float dv = fmaf(dz, v.z, fmaf(dy, v.y, dx * v.x));
                 if (!(r > e1.y && dv > 0.0f)) far = false;
             }
@@ -451,17 +510,18 @@ BT_DEV V3 lens_accel(const float4* lens, int n_lens, V3 x, V3 v, float& rmin, bo
     return v3(ax, ay, az);
 }
 BT_DEV V3 axpy(float a, V3 x, V3 y) { return v3(fmaf(a, x.x, y.x), fmaf(a, x.y, y.y), fmaf(a, x.z, y.z)); }
-template <bool EXACT>
-BT_DEV void rk4_from_k1(const float4* lens, int n_lens, V3& x, V3& v, V3 k1, float h) {
+// classic RK4 given k1 = accel(x, v) (whose evaluation filled `cache`)
+template <bool EXACT, class L>
+BT_DEV void rk4_from_k1(const L& lens, D0Cache<L>& cache, V3& x, V3& v, V3 k1, float h) {
     float hh = 0.5f * h, h6 = h * (float)(1.0 / 6.0);
     float ru;
     bool bu;
-    V3 x2 = axpy(hh, v, x), v2 = axpy(hh, k1, v);
-    V3 k2 = lens_accel<0, EXACT>(lens, n_lens, x2, v2, ru, bu, bu);
-    V3 x3 = axpy(hh, v2, x), v3_ = axpy(hh, k2, v);
-    V3 k3 = lens_accel<0, EXACT>(lens, n_lens, x3, v3_, ru, bu, bu);
-    V3 x4 = axpy(h, v3_, x), v4 = axpy(h, k3, v);
-    V3 k4 = lens_accel<0, EXACT>(lens, n_lens, x4, v4, ru, bu, bu);
+    V3 v2 = axpy(hh, k1, v);
+    V3 k2 = lens_accel<0, EXACT, 1>(lens, cache, x, hh, v, v2, ru, bu, bu);
+    V3 v3_ = axpy(hh, k2, v);
+    V3 k3 = lens_accel<0, EXACT, 1>(lens, cache, x, hh, v2, v3_, ru, bu, bu);
+    V3 v4 = axpy(h, k3, v);
+    V3 k4 = lens_accel<0, EXACT, 1>(lens, cache, x, h, v3_, v4, ru, bu, bu);
     V3 sv = axpy(2.0f, v2 + v3_, v + v4);
     V3 sk = axpy(2.0f, k2 + k3, k1 + k4);
     x = axpy(h6, sv, x);

@@ -517,8 +517,8 @@ int bt_geodesic_integrate(bt_engine* engine, const float* xyzr, uint32_t n_lense
     for (uint32_t i = 0; i < n_lenses; ++i) {
         float rs = xyzr[4 * i + 3];
         if (!(rs > 0.0f)) continue;
-        float4 e0 = {xyzr[4 * i], xyzr[4 * i + 1], xyzr[4 * i + 2], rs};
-        float4 e1 = {-1.5f * rs, c.r_far * rs, 0.0f, 0.0f};
+        float4 e0 = {xyzr[4 * i], xyzr[4 * i + 1], xyzr[4 * i + 2], -1.5f * rs};
+        float4 e1 = {rs, c.r_far * rs, 0.0f, 0.0f};
         lens.push_back(e0);
         lens.push_back(e1);
     }

@@ -45,8 +45,8 @@ struct Traced {
 
 // One "ray" of the render loop.  Flat field (or inside a volume march): exactly try_hit /
 // try_hit_volume.  Lens field: RK4 chords, each intersected with the same scan.
-template <bool LENS, bool EXACT>
-BT_DEV Traced trace_ray(const RenderParams& p, const SceneView& sc, V3 o, V3 d, float tmin, float tmax, int vol_obj) {
+template <bool LENS, bool EXACT, class L>
+BT_DEV Traced trace_ray(const RenderParams& p, const SceneView& sc, const L& lens, V3 o, V3 d, float tmin, float tmax, int vol_obj) {
     Traced r;
     r.steps = 0;
     r.captured = false;
@@ -58,13 +58,13 @@ BT_DEV Traced trace_ray(const RenderParams& p, const SceneView& sc, V3 o, V3 d, 
         r.t_total = r.h.t;
         return r;
     }
-    const int n_lens = (int)p.scene.n_lens;
     V3 x = o, v = d;
     float travelled = 0.0f;
     for (;;) {
         float rmin;
         bool captured, far;
-        V3 k1 = lens_accel<2, EXACT>(sc.lens, n_lens, x, v, rmin, captured, far);
+        D0Cache<L> cache;
+        V3 k1 = lens_accel<2, EXACT, 0>(lens, cache, x, 0.0f, v, v, rmin, captured, far);
         if (captured) {
             r.captured = true;
             r.h.prim = -1;
@@ -87,7 +87,7 @@ BT_DEV Traced trace_ray(const RenderParams& p, const SceneView& sc, V3 o, V3 d, 
         }
         float h = step_size(p.scene.kappa, p.scene.h_min, p.scene.h_max, rmin);
         V3 x1 = x, v1 = v;
-        rk4_from_k1<EXACT>(sc.lens, n_lens, x1, v1, k1, h);
+        rk4_from_k1<EXACT>(lens, cache, x1, v1, k1, h);
         float len;
         V3 dir = normalize_fma(x1 - x, &len);
         r.h = scan_prims(sc.prims, n_prims, x, dir, cmin, fminf(len, remaining), -1);
@@ -110,10 +110,28 @@ BT_DEV Traced trace_ray(const RenderParams& p, const SceneView& sc, V3 o, V3 d, 
     }
 }
 
-template <bool LENS, bool EXACT>
+// NL: 0 = lens table walked in shared memory, N > 0 = exactly N masses held in registers
+template <int NL>
+struct LensSel {
+    typedef LensRegs<NL> type;
+    static BT_DEV type make(const float4* p, int) { return type(p); }
+};
+template <>
+struct LensSel<0> {
+    typedef LensShared type;
+    static BT_DEV type make(const float4* p, int n) {
+        LensShared l;
+        l.p = p;
+        l.count = n;
+        return l;
+    }
+};
+
+template <bool LENS, bool EXACT, int NL>
 __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ RenderParams p) {
     extern __shared__ float4 smem[];
     const SceneView sc = stage_scene(p, smem);
+    const typename LensSel<NL>::type lens = LensSel<NL>::make(sc.lens, (int)p.scene.n_lens);
     Consts k;
     k.tau_scale = p.tau_scale;
     k.one_scale = p.one_scale;
@@ -164,7 +182,7 @@ __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ Ren
 
         // ---- trace one segment ------------------------------------------------------------
         const bool in_volume = vol_obj >= 0;
-        Traced tr = trace_ray<LENS, EXACT>(p, sc, o, d, in_volume ? 0.0f : p.clip_min, in_volume ? p.volume_step : p.clip_max, vol_obj);
+        Traced tr = trace_ray<LENS, EXACT>(p, sc, lens, o, d, in_volume ? 0.0f : p.clip_min, in_volume ? p.volume_step : p.clip_max, vol_obj);
 
         // terminal outcome of this event (if any): colour and the AOVs it would latch
         bool finish = false;
@@ -307,16 +325,17 @@ __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ Ren
     }
 }
 
-template <bool LENS, bool EXACT>
+template <bool LENS, bool EXACT, int NL>
 __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ RenderParams p, uint32_t n, const float* __restrict__ origins,
                                                     const float* __restrict__ dirs, DeviceSegment* __restrict__ out) {
     extern __shared__ float4 smem[];
     const SceneView sc = stage_scene(p, smem);
+    const typename LensSel<NL>::type lens = LensSel<NL>::make(sc.lens, (int)p.scene.n_lens);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     V3 o = v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
     V3 d = v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
-    Traced tr = trace_ray<LENS, EXACT>(p, sc, o, d, p.clip_min, p.clip_max, -1);
+    Traced tr = trace_ray<LENS, EXACT>(p, sc, lens, o, d, p.clip_min, p.clip_max, -1);
     DeviceSegment seg;
     seg.steps = tr.steps;
     seg.obj = -1;
@@ -358,7 +377,7 @@ __global__ void camera_rays_kernel(const __grid_constant__ RenderParams p, uint3
 
 // The geodesic stepper in isolation: n_steps RK4 steps per ray, state in registers, the lens
 // table in shared memory.  No memory traffic in the loop: this is the FP32-roofline kernel.
-template <bool EXACT>
+template <bool EXACT, int NL>
 __global__ void __launch_bounds__(256) integrate_kernel(const IntegrateParams p) {
     extern __shared__ float4 slens[];
     for (uint32_t i = threadIdx.x; i < p.n_lens * LENS_STRIDE; i += blockDim.x) slens[i] = p.lens[i];
@@ -367,13 +386,14 @@ __global__ void __launch_bounds__(256) integrate_kernel(const IntegrateParams p)
     if (i >= p.n) return;
     float* s = p.xv + 6 * (size_t)i;
     V3 x = v3(s[0], s[1], s[2]), v = v3(s[3], s[4], s[5]);
-    const int n_lens = (int)p.n_lens;
+    const typename LensSel<NL>::type lens = LensSel<NL>::make(slens, (int)p.n_lens);
 #pragma unroll 1
     for (uint32_t it = 0; it < p.n_steps; ++it) {
         float rmin;
         bool captured, far;
-        V3 k1 = lens_accel<1, EXACT>(slens, n_lens, x, v, rmin, captured, far);
-        rk4_from_k1<EXACT>(slens, n_lens, x, v, k1, step_size(p.kappa, p.h_min, p.h_max, rmin));
+        D0Cache<typename LensSel<NL>::type> cache;
+        V3 k1 = lens_accel<1, EXACT, 0>(lens, cache, x, 0.0f, v, v, rmin, captured, far);
+        rk4_from_k1<EXACT>(lens, cache, x, v, k1, step_size(p.kappa, p.h_min, p.h_max, rmin));
     }
     s[0] = x.x; s[1] = x.y; s[2] = x.z; s[3] = v.x; s[4] = v.y; s[5] = v.z;
 }
@@ -436,20 +456,30 @@ cudaError_t ensure_smem(K kernel, size_t bytes) {
 
 size_t render_smem_bytes(const RenderParams& p) { return (size_t)p.scene.blob_f4 * sizeof(float4); }
 
+// picks <LENS, EXACT, NL> from the scene header
+#define BT_DISPATCH_LENS(KERNEL, GRID, BLOCK, SMEM, STREAM, ...)                                   \
+    do {                                                                                           \
+        cudaError_t e_;                                                                            \
+        const bool exact_ = p.scene.lens_exact != 0;                                               \
+        if (p.scene.n_lens == 0) {                                                                 \
+            if ((e_ = ensure_smem(KERNEL<false, false, 0>, SMEM)) != cudaSuccess) return e_;       \
+            KERNEL<false, false, 0><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);                   \
+        } else if (p.scene.n_lens == 1 && !exact_) {                                               \
+            if ((e_ = ensure_smem(KERNEL<true, false, 1>, SMEM)) != cudaSuccess) return e_;        \
+            KERNEL<true, false, 1><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);                    \
+        } else if (!exact_) {                                                                      \
+            if ((e_ = ensure_smem(KERNEL<true, false, 0>, SMEM)) != cudaSuccess) return e_;        \
+            KERNEL<true, false, 0><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);                    \
+        } else {                                                                                   \
+            if ((e_ = ensure_smem(KERNEL<true, true, 0>, SMEM)) != cudaSuccess) return e_;         \
+            KERNEL<true, true, 0><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);                     \
+        }                                                                                          \
+    } while (0)
+
 cudaError_t launch_render(const RenderParams& p, cudaStream_t stream, uint64_t* launches) {
     dim3 grid((p.width + 15) / 16, (p.height + 15) / 16), block(256);
     size_t smem = render_smem_bytes(p);
-    cudaError_t e;
-    if (p.scene.n_lens > 0 && p.scene.lens_exact) {
-        if ((e = ensure_smem(render_kernel<true, true>, smem)) != cudaSuccess) return e;
-        render_kernel<true, true><<<grid, block, smem, stream>>>(p);
-    } else if (p.scene.n_lens > 0) {
-        if ((e = ensure_smem(render_kernel<true, false>, smem)) != cudaSuccess) return e;
-        render_kernel<true, false><<<grid, block, smem, stream>>>(p);
-    } else {
-        if ((e = ensure_smem(render_kernel<false, false>, smem)) != cudaSuccess) return e;
-        render_kernel<false, false><<<grid, block, smem, stream>>>(p);
-    }
+    BT_DISPATCH_LENS(render_kernel, grid, block, smem, stream, p);
     ++*launches;
     return cudaGetLastError();
 }
@@ -458,17 +488,7 @@ cudaError_t launch_trace(const RenderParams& p, uint32_t n, const float* origins
                          DeviceSegment* out, cudaStream_t stream, uint64_t* launches) {
     if (n == 0) return cudaSuccess;
     size_t smem = render_smem_bytes(p);
-    cudaError_t e;
-    if (p.scene.n_lens > 0 && p.scene.lens_exact) {
-        if ((e = ensure_smem(trace_kernel<true, true>, smem)) != cudaSuccess) return e;
-        trace_kernel<true, true><<<(n + 255) / 256, 256, smem, stream>>>(p, n, origins, dirs, out);
-    } else if (p.scene.n_lens > 0) {
-        if ((e = ensure_smem(trace_kernel<true, false>, smem)) != cudaSuccess) return e;
-        trace_kernel<true, false><<<(n + 255) / 256, 256, smem, stream>>>(p, n, origins, dirs, out);
-    } else {
-        if ((e = ensure_smem(trace_kernel<false, false>, smem)) != cudaSuccess) return e;
-        trace_kernel<false, false><<<(n + 255) / 256, 256, smem, stream>>>(p, n, origins, dirs, out);
-    }
+    BT_DISPATCH_LENS(trace_kernel, (n + 255) / 256, 256, smem, stream, p, n, origins, dirs, out);
     ++*launches;
     return cudaGetLastError();
 }
@@ -485,13 +505,18 @@ cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t stream, uint
     if (p.n == 0) return cudaSuccess;
     size_t smem = (size_t)p.n_lens * LENS_STRIDE * sizeof(float4);
     cudaError_t e;
-    if (p.exact) {
-        if ((e = ensure_smem(integrate_kernel<true>, smem)) != cudaSuccess) return e;
-        integrate_kernel<true><<<(p.n + 255) / 256, 256, smem, stream>>>(p);
-    } else {
-        if ((e = ensure_smem(integrate_kernel<false>, smem)) != cudaSuccess) return e;
-        integrate_kernel<false><<<(p.n + 255) / 256, 256, smem, stream>>>(p);
-    }
+    const unsigned grid = (p.n + 255) / 256;
+#define BT_INTEGRATE(EXACT, NL)                                                                \
+    do {                                                                                       \
+        if ((e = ensure_smem(integrate_kernel<EXACT, NL>, smem)) != cudaSuccess) return e;     \
+        integrate_kernel<EXACT, NL><<<grid, 256, smem, stream>>>(p);                           \
+    } while (0)
+    if (p.exact) BT_INTEGRATE(true, 0);
+    else if (p.n_lens == 1) BT_INTEGRATE(false, 1);
+    else if (p.n_lens == 2) BT_INTEGRATE(false, 2);
+    else if (p.n_lens == 4) BT_INTEGRATE(false, 4);
+    else BT_INTEGRATE(false, 0);
+#undef BT_INTEGRATE
     ++*launches;
     return cudaGetLastError();
 }

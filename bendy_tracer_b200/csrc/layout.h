@@ -37,7 +37,7 @@ enum { LIGHT_STRIDE = 7 };
 enum { VOL_STRIDE = 2 };
 
 // ---- lens record: LENS_STRIDE float4 (extension) -------------------------------------------
-//   e0 = (c.xyz, r_s)   e1 = (-1.5 r_s, r_far * r_s, -, -)
+//   e0 = (c.xyz, -1.5 r_s)   e1 = (r_s, r_far * r_s, -, -)   (stage evaluations read e0 only)
 enum { LENS_STRIDE = 2 };
 
 struct SceneHeader {

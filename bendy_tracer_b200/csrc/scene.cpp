@@ -921,8 +921,8 @@ FlatScene flatten(const Scene& scene) {
     for (size_t i = 0; i < scene.lenses.size(); ++i) {
         const Lens& l = scene.lenses[i];
         if (!(l.rs > 0.0f)) continue;  // r_s <= 0: no mass -> exact flat limit
-        lens.push_back(f4(l.c[0], l.c[1], l.c[2], l.rs));
-        lens.push_back(f4(-1.5f * l.rs, scene.lens_config.r_far * l.rs, 0.0f, 0.0f));
+        lens.push_back(f4(l.c[0], l.c[1], l.c[2], -1.5f * l.rs));
+        lens.push_back(f4(l.rs, scene.lens_config.r_far * l.rs, 0.0f, 0.0f));
     }
 
     SceneHeader& h = fs.header;

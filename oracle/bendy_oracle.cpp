@@ -709,13 +709,19 @@ struct AccelInfo {
 // a = sum_m -(3/2) rs |d x v|^2 d / |d|^5, written with the explicit FMA placement the device
 // stepper uses.  With info != 0 also returns min_m |d| and the capture / far-field flags.
 template <class T>
-inline V3<T> accel(const Field<T>& f, V3<T> x, V3<T> v, T* rmin_out, AccelInfo* info) {
+inline V3<T> accel(const Field<T>& f, V3<T> x, bool staged, T a, V3<T> w, V3<T> v, T* rmin_out, AccelInfo* info) {
     T ax = 0, ay = 0, az = 0;
     T rmin = std::numeric_limits<T>::infinity();
     bool captured = false, far = true;
     for (size_t m = 0; m < f.l.size(); ++m) {
         const LensT<T>& l = f.l[m];
+        // evaluated at x + a*w as d = fma(a, w, x - c): the stage offset is applied after the subtraction
         T dx = x.x - l.cx, dy = x.y - l.cy, dz = x.z - l.cz;
+        if (staged) {
+            dx = fma_t(a, w.x, dx);
+            dy = fma_t(a, w.y, dy);
+            dz = fma_t(a, w.z, dz);
+        }
         T r2 = fma_t(dz, dz, fma_t(dy, dy, dx * dx));
         T lx = fma_t(dy, v.z, -(dz * v.y));
         T ly = fma_t(dz, v.x, -(dx * v.z));
@@ -750,12 +756,12 @@ template <class T> inline V3<T> axpy(T a, V3<T> x, V3<T> y) {
 template <class T>
 inline void rk4_from_k1(const Field<T>& f, V3<T>& x, V3<T>& v, V3<T> k1, T h) {
     T hh = T(0.5) * h, h6 = h * T(1.0 / 6.0);
-    V3<T> x2 = axpy(hh, v, x), v2 = axpy(hh, k1, v);
-    V3<T> k2 = accel<T>(f, x2, v2, 0, 0);
-    V3<T> x3 = axpy(hh, v2, x), v3 = axpy(hh, k2, v);
-    V3<T> k3 = accel<T>(f, x3, v3, 0, 0);
-    V3<T> x4 = axpy(h, v3, x), v4 = axpy(h, k3, v);
-    V3<T> k4 = accel<T>(f, x4, v4, 0, 0);
+    V3<T> v2 = axpy(hh, k1, v);
+    V3<T> k2 = accel<T>(f, x, true, hh, v, v2, 0, 0);
+    V3<T> v3 = axpy(hh, k2, v);
+    V3<T> k3 = accel<T>(f, x, true, hh, v2, v3, 0, 0);
+    V3<T> v4 = axpy(h, k3, v);
+    V3<T> k4 = accel<T>(f, x, true, h, v3, v4, 0, 0);
     V3<T> sv = axpy(T(2), v2 + v3, v + v4);
     V3<T> sk = axpy(T(2), k2 + k3, k1 + k4);
     x = axpy(h6, sv, x);
@@ -814,7 +820,7 @@ Segment<T> trace_segment(const Scene& scene, const Field<T>& f, const Ray<T>& ra
     for (;;) {
         T rmin;
         AccelInfo info;
-        V3<T> k1 = accel<T>(f, x, v, &rmin, &info);
+        V3<T> k1 = accel<T>(f, x, false, T(0), v, v, &rmin, &info);
         if (info.captured) {
             seg.status = SEG_CAPTURED;
             return seg;
@@ -1481,7 +1487,7 @@ static void integrate_one(const Field<T>& f, V3<T>& x, V3<T>& v, uint32_t n_step
     for (uint32_t s = 0; s < n_steps; ++s) {
         T rmin;
         AccelInfo info;
-        V3<T> k1 = accel<T>(f, x, v, &rmin, &info);
+        V3<T> k1 = accel<T>(f, x, false, T(0), v, v, &rmin, &info);
         rk4_from_k1(f, x, v, k1, step_size(f, rmin));
     }
 }
@@ -1625,7 +1631,7 @@ void orc_rk4_step_f32(const float* xyzr, int n_lens, float* x, float* v, float h
     orc_lens_config cfg = {0.05f, 0.0f, 1e30f, 1e30f, 0};
     Field<float> f = make_field<float>(xyzr, n_lens, cfg);
     V3f X = mk<float>(x[0], x[1], x[2]), V = mk<float>(v[0], v[1], v[2]);
-    V3f k1 = accel<float>(f, X, V, 0, 0);
+    V3f k1 = accel<float>(f, X, false, 0.0f, V, V, 0, 0);
     rk4_from_k1(f, X, V, k1, h);
     x[0] = X.x; x[1] = X.y; x[2] = X.z; v[0] = V.x; v[1] = V.y; v[2] = V.z;
 }
@@ -1633,7 +1639,7 @@ void orc_rk4_step_f64(const float* xyzr, int n_lens, double* x, double* v, doubl
     orc_lens_config cfg = {0.05f, 0.0f, 1e30f, 1e30f, 0};
     Field<double> f = make_field<double>(xyzr, n_lens, cfg);
     V3<double> X = mk<double>(x[0], x[1], x[2]), V = mk<double>(v[0], v[1], v[2]);
-    V3<double> k1 = accel<double>(f, X, V, 0, 0);
+    V3<double> k1 = accel<double>(f, X, false, 0.0, V, V, 0, 0);
     rk4_from_k1(f, X, V, k1, h);
     x[0] = X.x; x[1] = X.y; x[2] = X.z; v[0] = V.x; v[1] = V.y; v[2] = V.z;
 }

@@ -1,0 +1,194 @@
+"""CPU-side tests of the host logic and the C-ABI boundary (no compute calls: there is no GPU here)."""
+import ctypes as C
+import gzip
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import bendy_tracer_b200 as bt
+import oracle_ffi as O
+from bendy_tracer_b200 import _ffi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SCENES = ["cornell", "cornell2", "scene", "volume", "cloud"]
+
+
+def test_library_exports_every_header_symbol():
+    header = open(os.path.join(ROOT, "include", "bendy_b200.h")).read()
+    declared = set(re.findall(r"\b(bt_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    lib = C.CDLL(_ffi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/bendy_b200.h but not exported"
+    assert declared == set(_ffi.SIGNATURES), declared ^ set(_ffi.SIGNATURES)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry point fails loudly (BT_ERR_CUDA), nothing renders."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(bt.BendyError) as e:
+        bt.Engine(0)
+    assert e.value.code == _ffi.ERR_CUDA and "no CPU fallback" in e.value.message
+    scene = bt.Scene.load(O.scene_path("cornell"))
+    with pytest.raises(bt.BendyError):
+        bt.Tracer().render(scene, 0, bt.RenderConfig.with_samples(1), bt.Buffer(8, 8))
+
+
+def test_product_never_touches_the_oracle():
+    """the engine sources and the package must not include, link or import anything under oracle/"""
+    pkg = os.path.join(ROOT, "bendy_tracer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "bendy_oracle" not in text and "oracle_ffi" not in text and "oracle/" not in text, f
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_scene_round_trip(name):
+    """serde wire format: load -> to_json -> identical JSON value (src/main.rs:93-102, 299-313)"""
+    path = O.scene_path(name)
+    scene = bt.Scene.load(path)
+    original = json.load(gzip.open(path))
+    assert json.loads(scene.to_json()) == original
+    again = bt.Scene.from_json(scene.to_json())
+    assert again.to_json() == scene.to_json()
+    info = scene.info()
+    n_obj = len(original["objects"]["collection"])
+    assert info["n_objects"] == n_obj and info["n_data"] == len(original["data"]["collection"])
+    expect_prims = {"cornell": 18, "cornell2": 18, "scene": 5, "volume": 4, "cloud": 4}[name]
+    assert info["n_primitives"] == expect_prims and info["n_lights"] == 1
+    assert info["n_volumes"] == (1 if name in ("volume", "cloud") else 0)
+    assert info["root_material"] == original["root_material"]
+    assert scene.find_by_tag("camera") == 0 and scene.find_by_tag("no such tag") is None
+
+
+def test_scene_plain_json_and_gzip(tmp_path):
+    text = gzip.open(O.scene_path("scene")).read()
+    a, b = bt.Scene(text), bt.Scene.load(O.scene_path("scene"))
+    assert a.to_json() == b.to_json()
+    a.save(tmp_path / "s.json.gz")
+    a.save(tmp_path / "s.json")
+    assert bt.Scene.load(tmp_path / "s.json.gz").to_json() == bt.Scene.load(tmp_path / "s.json").to_json() == a.to_json()
+
+
+def test_scene_lens_extension_round_trip():
+    scene = json.load(gzip.open(O.scene_path("scene")))
+    scene["lenses"] = [[1.362, 1.577, 6.114, 0.2], [0.0, 0.0, 0.0, 0.0]]
+    s = bt.Scene.from_json(json.dumps(scene))
+    assert s.info()["n_lenses"] == 1                    # r_s = 0 masses are dropped (exact flat limit)
+    assert json.loads(s.to_json())["lenses"] == [[1.362, 1.577, 6.114, 0.2], [0.0, 0.0, 0.0, 0.0]]
+    s.set_lenses(np.zeros((0, 4), np.float32))
+    assert s.info()["n_lenses"] == 0 and "lenses" not in json.loads(s.to_json())
+
+
+def test_scene_parse_errors():
+    good = json.load(gzip.open(O.scene_path("cornell")))
+    for mutate, code in [
+        (lambda s: s.pop("root_material"), _ffi.ERR_PARSE),                               # missing field
+        (lambda s: s["objects"]["collection"]["1"].__setitem__("inner", {"Torus": {}}), _ffi.ERR_PARSE),
+        (lambda s: s["objects"]["collection"]["1"]["transform"].__setitem__("transform_world", [1.0] * 11), _ffi.ERR_PARSE),
+        (lambda s: s.__setitem__("root_material", 99), _ffi.ERR_SCENE),                    # invalid data ref
+        (lambda s: s["objects"]["collection"]["1"]["inner"]["Rect"].__setitem__("material", 99), _ffi.ERR_SCENE),
+    ]:
+        bad = json.loads(json.dumps(good))
+        mutate(bad)
+        with pytest.raises(bt.BendyError) as e:
+            bt.Scene.from_json(json.dumps(bad))
+        assert e.value.code == code, e.value
+    with pytest.raises(bt.BendyError) as e:
+        bt.Scene(b"{ not json")
+    assert e.value.code == _ffi.ERR_PARSE
+    with pytest.raises(bt.BendyError) as e:
+        bt.Scene(b"\x1f\x8b\x08\x00garbage")
+    assert e.value.code == _ffi.ERR_PARSE
+    vol = json.load(gzip.open(O.scene_path("volume")))
+    vol["data"]["collection"]["5"]["inner"]["Volume"]["DensityMap"]["buffer"][3] = -0.5   # gen_bool(p < 0) panics
+    with pytest.raises(bt.ScenePanic):
+        bt.Scene.from_json(json.dumps(vol))
+    vol = json.load(gzip.open(O.scene_path("volume")))
+    vol["objects"]["collection"]["2"]["inner"]["Sphere"]["volume"] = 4                     # a material, not a volume
+    with pytest.raises(bt.ScenePanic, match="expected volume data"):
+        bt.Scene.from_json(json.dumps(vol))
+
+
+def test_apply_transform_propagates_to_children():
+    """Object::apply_transform + UpdateQueue::commit (object/mod.rs:200-223, scene/mod.rs:204-213)"""
+    scene = json.load(gzip.open(O.scene_path("scene")))
+    objs = scene["objects"]["collection"]
+    objs["4"]["children"] = [5]                                        # glass sphere -> parent of the metal sphere
+    s = bt.Scene.from_json(json.dumps(scene))
+    shift = [1, 0, 0, 0, 1, 0, 0, 0, 1, 0.5, 1.0, -2.0]
+    s.apply_transform(4, shift)
+    out = json.loads(s.to_json())["objects"]["collection"]
+    assert out["4"]["transform"]["transform_world"][9:] == [0.0, 1.0, -2.0]
+    assert out["4"]["transform"]["transform_local"] == out["4"]["transform"]["transform_world"]
+    child = out["5"]["transform"]
+    assert child["transform_parent"] == out["4"]["transform"]["transform_world"]
+    # world = parent * local: the child's local (2.5, 0, -2.5) is now relative to the parent at (0, 1, -2)
+    assert np.allclose(child["transform_world"][9:], [2.5, 1.0, -4.5])
+    assert child["transform_local"] == objs["5"]["transform"]["transform_local"]
+    with pytest.raises(bt.ScenePanic, match="invalid object ref"):
+        s.apply_transform(42, shift)
+
+
+def test_camera_aspect_update():
+    s = bt.Scene.load(O.scene_path("cornell"))
+    s.set_camera_aspect(0, 1.7777778)
+    assert json.loads(s.to_json())["objects"]["collection"]["0"]["inner"]["Camera"]["aspect_ratio"] == 1.7777778
+    with pytest.raises(bt.ScenePanic):
+        s.set_camera_aspect(1, 1.0)                                    # object 1 is a Rect
+    with pytest.raises(bt.ScenePanic):
+        s.set_camera_aspect(99, 1.0)
+
+
+def test_api_mirror_defaults():
+    c = bt.Config()
+    assert (c.max_bounces, c.max_volume_bounces, c.clip_min, c.clip_max, c.volume_step, c.chunks_x, c.chunks_y,
+            c.output) == (8, 32, 0.01, 1000.0, 0.1, 4, 2, bt.Output.Full)                  # Config::DEFAULT, mod.rs:29-38
+    r = bt.RenderConfig()
+    assert r.samples == 64 and r.subsample == bt.Subsample.none() and r.output is None     # RenderConfig::DEFAULT
+    assert bt.RenderConfig.with_samples(3).samples == 3
+    rc = bt.RenderConfig.with_samples_subsample(2, bt.Subsample.subpixel(3))
+    assert rc.subsample.subpixel_count() == 9 and abs(rc.subsample.subpixel_size() - 1 / 3) < 1e-7
+    offs = list(bt.Subsample.subpixel(2))
+    assert offs == [(0.0, 0.0), (0.5, 0.0), (0.0, 0.5), (0.5, 0.5)]                        # i fastest (mod.rs:96-101)
+    assert list(bt.Subsample.none()) == [(0.0, 0.0)] and bt.Subsample.none().subpixel_count() == 1
+    cc, cr = _ffi.BtConfig(), _ffi.BtRenderConfig()
+    _ffi.lib.bt_config_default(C.byref(cc))
+    _ffi.lib.bt_render_config_default(C.byref(cr))
+    assert (cc.max_bounces, cc.max_volume_bounces, cc.chunks_x, cc.chunks_y, cc.output) == (8, 32, 4, 2, 0)
+    assert abs(cc.clip_min - 0.01) < 1e-9 and cc.clip_max == 1000.0 and abs(cc.volume_step - 0.1) < 1e-8
+    assert cr.samples == 64 and cr.subsample == 0 and not (cr.has_output or cr.has_max_bounces or cr.has_volume_step)
+    lc = _ffi.BtLensConfig()
+    _ffi.lib.bt_lens_config_default(C.byref(lc))
+    d = bt.LensConfig()
+    assert (lc.max_steps, lc.flags) == (d.max_steps, 0) and abs(lc.kappa - d.kappa) < 1e-9
+
+
+def test_buffer_mirror():
+    b = bt.Buffer(6, 4, bt.ColorSpace.SRgb)
+    assert b.dimensions() == (6, 4) and b.samples() == 0 and b.width() == 6 and b.height() == 4
+    assert (b.into_buffer()[..., :3] == 0).all() and (b.into_buffer()[..., 3] == 1).all()     # BLACK_ALPHA_ONE
+    assert abs(b.pixel_width() - 2 / 6) < 1e-7 and abs(b.pixel_height() - 0.5) < 1e-7
+    b.data[..., 0] = 5
+    b._samples = 3
+    b.clear()
+    assert (b.data[..., :3] == 0).all() and (b.data[..., 3] == 1).all() and b.samples() == 0
+    b.resize(3, 2)
+    assert b.dimensions() == (3, 2) and b.maybe_preview() is None and b.take_preview() is None
+
+
+def test_shard_passes_partition():
+    for samples in (1, 7, 64, 1024):
+        for world in (1, 2, 3, 4, 8):
+            cuts = [bt.shard_passes(samples, world, r) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == samples
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in cuts]
+            assert max(sizes) - min(sizes) <= 1
