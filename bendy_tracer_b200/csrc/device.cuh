@@ -181,40 +181,58 @@ struct Hit {
     int face;      // BT_FACE_*-compatible (0 front, 1 back, 2 volume, 3 volume front, 4 volume back)
 };
 
+// Two arithmetic flavours of the per-primitive tests:
+//  * BT_EXACT_SCAN: the reference's operation order with every product and sum rounded separately
+//    and an IEEE division -- hit distances are bit-identical to the CPU oracle;
+//  * default: the RECT test with its dot products contracted to FMA chains, t = p * rcp(q)
+//    (MUFU.RCP, <= 2 ulp) and no divergent early-outs.  Rect hit distances differ from the
+//    reference by a few ulp (well inside the 1e-3 image bar, see tests/test_gpu_parity.py); ~35 %
+//    fewer instructions per test.  Sphere tests keep the reference's rounding in both flavours.
+#ifdef BT_EXACT_SCAN
+BT_DEV float sdot(V3 a, V3 b) { return dot(a, b); }
+BT_DEV V3 sat(V3 o, float t, V3 d) { return o + t * d; }
+BT_DEV float sdiv(float p, float q) { return p / q; }
+#else
+BT_DEV float sdot(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+BT_DEV V3 sat(V3 o, float t, V3 d) { return v3(fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z)); }
+BT_DEV float sdiv(float p, float q) { return __fdividef(p, q); }
+#endif
+
 // Sphere::hit roots (sphere.rs:121-148).  Returns true and the accepted root.
 BT_DEV bool sphere_roots(float4 q0, float r2, V3 o, V3 d, float tmin, float tmax, float& t_out) {
+    // always the reference's rounding: |oc|^2 - r^2 cancels catastrophically for large spheres, and
+    // a 1e-5 shift of a volume entry point flips Bernoulli scatter decisions at a visible rate
     V3 oc = o - v3(q0);
     float half_b = dot(oc, d);
     float c = dot(oc, oc) - r2;
     float disc = half_b * half_b - c;
-    if (signbit(disc)) return false;
+    if (signbit(disc)) return false;  // most rays miss most spheres: a (mostly warp-uniform) early-out
     float sqrtd = sqrtf(disc);
-    float t = -half_b - sqrtd;
-    if (t < tmin || t > tmax) {
-        t = -half_b + sqrtd;
-        if (t < tmin || t > tmax) return false;
-    }
-    t_out = t;
-    return true;
+    float t0 = -half_b - sqrtd, t1 = -half_b + sqrtd;
+    bool in0 = !(t0 < tmin || t0 > tmax), in1 = !(t1 < tmin || t1 > tmax);
+    t_out = in0 ? t0 : t1;
+    return in0 || in1;
 }
 // Rect::hit (rect.rs:110-155) on a pre-transformed record.  strict: Cuboid::hit's `t < best`.
 BT_DEV bool rect_test(const float4* q, V3 o, V3 d, float tmin, float tmax, bool strict, float& t_out, bool& front) {
-    float4 q0 = q[0], q1 = q[1];
-    V3 n = v3(q0);
-    float qq = dot(d, n);
-    if (fabsf(qq) <= 1e-5f) return false;
-    float p = dot(v3(q1) - o, n);
-    float t = p / qq;
-    if (t < tmin || t > tmax) return false;
-    if (strict && !(t < tmax)) return false;
-    V3 pos = o + t * d;
-    float4 q2 = q[2], q3 = q[3];
-    float lx = dot(pos, v3(q2)) + q2.w;
-    float ly = dot(pos, v3(q3)) + q3.w;
-    if (!(lx * lx <= q0.w && ly * ly <= q1.w)) return false;
+    const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+    const V3 n = v3(q0);
+    const float qq = sdot(d, n);
+    const float p = sdot(v3(q1) - o, n);
+    const float t = sdiv(p, qq);
+    bool ok = fabsf(qq) > 1e-5f && !(t < tmin || t > tmax) && !(strict && !(t < tmax));
+    const V3 pos = sat(o, t, d);
+#ifdef BT_EXACT_SCAN
+    const float lx = dot(pos, v3(q2)) + q2.w;
+    const float ly = dot(pos, v3(q3)) + q3.w;
+#else
+    const float lx = fmaf(pos.x, q2.x, fmaf(pos.y, q2.y, fmaf(pos.z, q2.z, q2.w)));
+    const float ly = fmaf(pos.x, q3.x, fmaf(pos.y, q3.y, fmaf(pos.z, q3.z, q3.w)));
+#endif
+    ok = ok && (lx * lx <= q0.w) && (ly * ly <= q1.w);
     t_out = t;
     front = p < 0.0f;
-    return true;
+    return ok;
 }
 
 // ChunkState::try_hit / try_hit_volume (mod.rs:389-427): linear scan in canonical object order
