@@ -44,54 +44,51 @@ struct Traced {
 };
 
 // One "ray" of the render loop.  Flat field (or inside a volume march): exactly try_hit /
-// try_hit_volume.  Lens field: RK4 chords, each intersected with the same scan.
+// try_hit_volume.  Lens field: RK4 chords, each intersected with the same scan (ONE scan call
+// site: the kernel must stay inside the instruction cache).
 template <bool LENS, bool EXACT, class L>
 BT_DEV Traced trace_ray(const RenderParams& p, const SceneView& sc, const L& lens, V3 o, V3 d, float tmin, float tmax, int vol_obj) {
     Traced r;
     r.steps = 0;
     r.captured = false;
     const int n_prims = (int)p.scene.n_prims;
-    if (!LENS || vol_obj >= 0) {
-        r.h = scan_prims(sc.prims, n_prims, o, d, tmin, tmax, vol_obj);
-        r.o = o;
-        r.d = d;
-        r.t_total = r.h.t;
-        return r;
-    }
+    const bool bent = LENS && vol_obj < 0;
     V3 x = o, v = d;
     float travelled = 0.0f;
+#pragma unroll 1
     for (;;) {
-        float rmin;
-        bool captured, far;
-        D0Cache<L> cache;
-        V3 k1 = lens_accel<2, EXACT, 0>(lens, cache, x, 0.0f, v, v, rmin, captured, far);
-        if (captured) {
-            r.captured = true;
-            r.h.prim = -1;
-            r.h.t = 0.0f;
-            r.h.face = 0;
-            r.o = x;
-            r.d = v;
-            r.t_total = travelled;
-            return r;
+        V3 dir = d, x1 = x, v1 = v;
+        float cmin = tmin, cmax = tmax, len = 0.0f;
+        bool last = true;
+        if (bent) {
+            float rmin;
+            bool captured, far;
+            D0Cache<L> cache;
+            const V3 k1 = lens_accel<2, EXACT, 0>(lens, cache, x, 0.0f, v, v, rmin, captured, far);
+            if (captured) {
+                r.captured = true;
+                r.h.prim = -1;
+                r.h.t = 0.0f;
+                r.h.face = 0;
+                r.o = x;
+                r.d = v;
+                r.t_total = travelled;
+                return r;
+            }
+            const float remaining = tmax - travelled;
+            cmin = fmaxf(tmin - travelled, 0.0f);
+            if (far) {
+                dir = normalize_fma(v, 0);
+                cmax = remaining;
+            } else {
+                rk4_from_k1<EXACT>(lens, cache, x1, v1, k1, step_size(p.scene.kappa, p.scene.h_min, p.scene.h_max, rmin));
+                dir = normalize_fma(x1 - x, &len);
+                cmax = fminf(len, remaining);
+                last = false;
+            }
         }
-        float remaining = tmax - travelled;
-        float cmin = fmaxf(tmin - travelled, 0.0f);
-        if (far) {
-            V3 dir = normalize_fma(v, 0);
-            r.h = scan_prims(sc.prims, n_prims, x, dir, cmin, remaining, -1);
-            r.o = x;
-            r.d = dir;
-            r.t_total = travelled + r.h.t;
-            return r;
-        }
-        float h = step_size(p.scene.kappa, p.scene.h_min, p.scene.h_max, rmin);
-        V3 x1 = x, v1 = v;
-        rk4_from_k1<EXACT>(lens, cache, x1, v1, k1, h);
-        float len;
-        V3 dir = normalize_fma(x1 - x, &len);
-        r.h = scan_prims(sc.prims, n_prims, x, dir, cmin, fminf(len, remaining), -1);
-        if (r.h.prim >= 0) {
+        r.h = scan_prims(sc.prims, n_prims, x, dir, cmin, cmax, vol_obj);
+        if (r.h.prim >= 0 || last) {
             r.o = x;
             r.d = dir;
             r.t_total = travelled + r.h.t;
@@ -127,8 +124,13 @@ struct LensSel<0> {
     }
 };
 
+// what an event does next
+enum { EV_TERMINAL = 0, EV_DIFFUSE = 1, EV_SPECULAR = 2 /* metallic, glass */, EV_VOLUME = 3 };
+// how its new direction is sampled: every variant consumes the same two u32 draws (r1, r2)
+enum { SK_NONE = 0, SK_COSINE = 1, SK_HEMI = 2, SK_SPHERE = 3, SK_RECT = 4 };
+
 template <bool LENS, bool EXACT, int NL>
-__global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ RenderParams p) {
+__global__ void __launch_bounds__(256, 3) render_kernel(const __grid_constant__ RenderParams p) {
     extern __shared__ float4 smem[];
     const SceneView sc = stage_scene(p, smem);
     const typename LensSel<NL>::type lens = LensSel<NL>::make(sc.lens, (int)p.scene.n_lens);
@@ -143,6 +145,8 @@ __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ Ren
     const bool valid = px < p.width && py < p.height;
     const uint64_t pixel = (uint64_t)py * p.width + px;
     const float inf = __int_as_float(0x7f800000);
+    // path_seed(seed, pixel, index) with its pixel-dependent prefix hoisted out of the path loop
+    const uint64_t pixel_key = splitmix_mix(splitmix_mix(p.seed + 0x9e3779b97f4a7c15ULL) + 0x9e3779b97f4a7c15ULL * (pixel + 1));
 
     V3 acc = v3(0.0f, 0.0f, 0.0f);
     uint32_t path = 0;
@@ -157,11 +161,11 @@ __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ Ren
     V3 aov_albedo, aov_normal;
     float aov_depth = inf;
 
+#pragma unroll 1
     for (;;) {
         if (!alive && !done) {
             if (path < p.paths_per_pixel) {
-                uint64_t path_index = p.path_base + path;
-                rng.seed_from_u64(path_seed(p.seed, pixel, path_index));
+                rng.seed_from_u64(splitmix_mix(pixel_key + 0xd1342543de82ef95ULL * (p.path_base + path + 1)));
                 camera_ray(p.cam, k, rng, px, py, path % p.sub_count, o, d);
                 T = v3(1.0f, 1.0f, 1.0f);
                 bounce = 0;
@@ -178,120 +182,183 @@ __global__ void __launch_bounds__(256) render_kernel(const __grid_constant__ Ren
             }
         }
         if (__all_sync(0xffffffffu, done)) break;
-        if (!alive) continue;
 
-        // ---- trace one segment ------------------------------------------------------------
-        const bool in_volume = vol_obj >= 0;
-        Traced tr = trace_ray<LENS, EXACT>(p, sc, lens, o, d, in_volume ? 0.0f : p.clip_min, in_volume ? p.volume_step : p.clip_max, vol_obj);
-
-        // terminal outcome of this event (if any): colour and the AOVs it would latch
+        // ---- 1. trace one segment and classify the event ---------------------------------------
+        int ev = EV_TERMINAL, sk = SK_NONE;
         bool finish = false;
         V3 fin_color = v3(0.0f, 0.0f, 0.0f), fin_albedo = v3(0.0f, 0.0f, 0.0f), fin_normal = v3(0.0f, 0.0f, 0.0f);
         float fin_depth = inf;
+        V3 pos = o, nrm = d, din = d, A = T, dir0 = d;  // event geometry (defaults are placeholders)
+        float rough = 0.0f, hit_t = 0.0f;
+        int face = 0, hit_obj = -1;
+        const float4* light = sc.lights;
+        bool vol_scatter = false;
+        const bool in_volume = vol_obj >= 0;
 
-        if (tr.h.prim < 0) {
-            finish = true;
-            if (!tr.captured) {  // sample_root, mod.rs:429-452
-                fin_color = v3(p.scene.root_color[0], p.scene.root_color[1], p.scene.root_color[2]);
-                fin_albedo = v3(p.scene.root_albedo[0], p.scene.root_albedo[1], p.scene.root_albedo[2]);
-                if (p.scene.root_keeps_normal) {
-                    fin_normal = -tr.d;
-                    fin_depth = p.clip_max;
-                }
-            }
-        } else {
-            const Surface s = resolve_hit(sc.prims, tr.h, tr.o, tr.d);
-            const V3 din = tr.d;
-            if (s.face <= 1) {
-                // ---- sample_surface, mod.rs:454-486 + Material::shade, material.rs:81-199 ----
-                const float4 m0 = sc.mats[s.mat * MAT_STRIDE], m1 = sc.mats[s.mat * MAT_STRIDE + 1];
-                const int kind = __float_as_int(m0.w);
-                const V3 A = v3(m0);
-                if (kind == MAT_FLAT) {
-                    finish = true;  // ColorData::from_emitted(albedo)
-                    fin_color = A;
-                    fin_albedo = A;
-                } else if (kind == MAT_EMISSIVE) {
-                    finish = true;
-                    fin_color = A * m1.z;
-                    fin_albedo = fin_color;
-                } else {
-                    V3 nd;
-                    float pdf = 1.0f, mpdf = 1.0f;
-                    if (kind == MAT_DIFFUSE) {
-                        const uint32_t li = uniform_index(rng, p.scene.n_lights);
-                        const float4* light = sc.lights + li * LIGHT_STRIDE;
-                        if (gen_bool(rng, 0.5f))  // Pdf::Mix: true selects the light (material.rs:269-275)
-                            nd = normalize_a(light_point(rng, k, light) - s.position);
-                        else
-                            nd = normalize_a(cosine_dir(rng, k, s.normal));
-                        mpdf = dot(s.normal, nd) * 0.318309886183790671538f;
-                        const float pb = light_pdf(sc.prims, light, s.position, nd, p.clip_min, p.clip_max);
-                        pdf = lerpf(mpdf, pb, 0.5f);
-                    } else if (kind == MAT_METALLIC) {
-                        const V3 dir = reflect(din, s.normal);
-                        nd = normalize_a(dir + unit_hemisphere(rng, k, s.normal) * m1.x);
-                    } else {  // MAT_GLASS, material.rs:231-261
-                        float ior = m1.y;
-                        if (s.face == 0) ior = 1.0f / ior;
-                        const float cos_theta = fminf(dot(-din, s.normal), 1.0f);
-                        const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
-                        const float fr = fresnel(din, s.normal, ior);
-                        V3 dir;
-                        if (ior * sin_theta > 1.0f || gen_bool(rng, fr))
-                            dir = reflect(din, s.normal);
-                        else
-                            dir = refract(din, s.normal, ior);
-                        nd = normalize_a(dir + unit_hemisphere(rng, k, s.normal) * m1.x);
-                    }
-                    if (fabsf(pdf) <= 1e-5f) {
-                        finish = true;  // no scatter: from_emitted(BLACK)
-                    } else {
-                        if (!latched) {
-                            latched = true;
-                            aov_albedo = A;
-                            aov_normal = s.normal;
-                            aov_depth = tr.t_total;
-                        }
-                        T = T * ((A * mpdf) * (1.0f / pdf));
-                        o = s.position;
-                        d = nd;
-                        vol_obj = -1;
-                        ++bounce;
-                        if (bounce > p.max_bounces) finish = true;  // sample(): black, AOVs already latched
+        if (alive) {
+            const Traced tr = trace_ray<LENS, EXACT>(p, sc, lens, o, d, in_volume ? 0.0f : p.clip_min,
+                                                     in_volume ? p.volume_step : p.clip_max, vol_obj);
+            din = tr.d;
+            hit_t = tr.t_total;
+            if (tr.h.prim < 0) {
+                finish = true;
+                if (!tr.captured) {  // sample_root, mod.rs:429-452
+                    fin_color = v3(p.scene.root_color[0], p.scene.root_color[1], p.scene.root_color[2]);
+                    fin_albedo = v3(p.scene.root_albedo[0], p.scene.root_albedo[1], p.scene.root_albedo[2]);
+                    if (p.scene.root_keeps_normal) {
+                        fin_normal = -tr.d;
+                        fin_depth = p.clip_max;
                     }
                 }
             } else {
-                // ---- sample_volume, mod.rs:488-523 + Volume::shade, volume.rs:26-60 ----
-                if (!in_volume) vb = 0;  // entered from sample(): volume_bounce = 0
-                const V3 bmin = v3(s.center.x - s.radius, s.center.y - s.radius, s.center.z - s.radius);
-                const V3 bmax = v3(s.center.x + s.radius, s.center.y + s.radius, s.center.z + s.radius);
-                const V3 coord = (s.position - bmin) / (bmax - bmin);
-                const float density = p.volume_step * density_trilinear(sc.vols + s.vol * VOL_STRIDE, sc.grids, coord);
-                if (density >= 1.0f || gen_bool(rng, density)) {
-                    V3 origin = s.position;
-                    if (s.face == 2) origin = origin - din * p.volume_step * standard_f32(rng);
-                    d = normalize_a(unit_sphere(rng, k));
-                    o = origin;
+                const Surface s = resolve_hit(sc.prims, tr.h, tr.o, tr.d);
+                pos = s.position;
+                nrm = s.normal;
+                face = s.face;
+                hit_obj = s.obj;
+                if (s.face <= 1) {
+                    // ---- sample_surface, mod.rs:454-486 + Material::shade, material.rs:81-199 ----
+                    const float4 m0 = sc.mats[s.mat * MAT_STRIDE], m1 = sc.mats[s.mat * MAT_STRIDE + 1];
+                    const int mk = __float_as_int(m0.w);
+                    A = v3(m0);
+                    if (mk == MAT_FLAT) {
+                        finish = true;  // ColorData::from_emitted(albedo)
+                        fin_color = A;
+                        fin_albedo = A;
+                    } else if (mk == MAT_EMISSIVE) {
+                        finish = true;
+                        fin_color = A * m1.z;
+                        fin_albedo = fin_color;
+                    } else if (mk == MAT_DIFFUSE) {
+                        ev = EV_DIFFUSE;
+                        light = sc.lights + uniform_index(rng, p.scene.n_lights) * LIGHT_STRIDE;
+                        if (gen_bool(rng, 0.5f)) {  // Pdf::Mix: true selects the light (material.rs:269-275)
+                            const int lt = __float_as_int(light[0].x);
+                            sk = lt == LIGHT_SPHERE ? SK_SPHERE : (lt == LIGHT_RECT ? SK_RECT : SK_NONE);
+                        } else {
+                            sk = SK_COSINE;
+                        }
+                    } else {
+                        ev = EV_SPECULAR;
+                        sk = SK_HEMI;
+                        rough = m1.x;
+                        if (mk == MAT_METALLIC) {
+                            dir0 = reflect(din, nrm);
+                        } else {  // MAT_GLASS, material.rs:231-261
+                            float ior = m1.y;
+                            if (s.face == 0) ior = 1.0f / ior;
+                            const float cos_theta = fminf(dot(-din, nrm), 1.0f);
+                            const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+                            const float fr = fresnel(din, nrm, ior);
+                            if (ior * sin_theta > 1.0f || gen_bool(rng, fr))
+                                dir0 = reflect(din, nrm);
+                            else
+                                dir0 = refract(din, nrm, ior);
+                        }
+                    }
+                } else {
+                    // ---- sample_volume, mod.rs:488-523 + Volume::shade, volume.rs:26-60 ----
+                    ev = EV_VOLUME;
+                    if (!in_volume) vb = 0;  // entered from sample(): volume_bounce = 0
+                    const V3 bmin = v3(s.center.x - s.radius, s.center.y - s.radius, s.center.z - s.radius);
+                    const V3 bmax = v3(s.center.x + s.radius, s.center.y + s.radius, s.center.z + s.radius);
+                    const V3 coord = (s.position - bmin) / (bmax - bmin);
+                    const float density = p.volume_step * density_trilinear(sc.vols + s.vol * VOL_STRIDE, sc.grids, coord);
+                    if (density >= 1.0f || gen_bool(rng, density)) {
+                        vol_scatter = true;
+                        sk = SK_SPHERE;
+                        if (s.face == 2) pos = pos - din * p.volume_step * standard_f32(rng);
+                    }
+                }
+            }
+        }
+
+        // ---- 2. the shared direction sampler: two u32 draws, one sincos, one basis --------------
+        // UnitSphere / UnitHemisphere / Cosine (math/distr.rs:7-103) and Rect::random_point
+        // (rect.rs:82-86) all draw (r1, r2) in this order; only the combination differs.
+        V3 vec = v3(0.0f, 0.0f, 0.0f);
+        if (sk != SK_NONE) {
+            const float4 l1 = light[1], l2 = light[2];
+            const bool rect = sk == SK_RECT;
+            const float r1 = uniform_f32(rng, rect ? l1.w : 0.0f, rect ? light[3].w : k.tau_scale);
+            const float r2 = uniform_f32(rng, rect ? l2.w : 0.0f, rect ? light[4].w : k.one_scale);
+            float cx = r1, sy = r2, z = 0.0f;
+            V3 X = v3(l1), Y = v3(l2), Z = v3(0.0f, 0.0f, 0.0f);
+            if (!rect) {
+                float s, c;
+                sincosf(r1, &s, &c);
+                const float w = sqrtf(sk == SK_COSINE ? r2 : r2 * (1.0f - r2));
+                const float two = sk == SK_COSINE ? 1.0f : 2.0f;
+                cx = c * two * w;
+                sy = s * two * w;
+                z = sk == SK_COSINE ? sqrtf(1.0f - r2) : (sk == SK_HEMI ? 1.0f - r2 : 1.0f - 2.0f * r2);
+                X = v3(1.0f, 0.0f, 0.0f);
+                Y = v3(0.0f, 1.0f, 0.0f);
+                Z = v3(0.0f, 0.0f, 1.0f);
+                if (sk != SK_SPHERE) {
+                    Z = normalize_s(nrm);
+                    any_orthonormal_pair(Z, X, Y);
+                }
+            }
+            vec = (X * cx + Y * sy) + Z * z;
+        }
+
+        // ---- 3. the scattered ray ------------------------------------------------------------
+        if (ev != EV_TERMINAL) {
+            V3 dirvec = vec;  // Cosine, volume scatter
+            if (ev == EV_DIFFUSE && sk != SK_COSINE) {  // Pdf::Light: random_point(light) - origin
+                V3 point = v3(light[1]);                                        // POINT: the translation
+                if (sk == SK_SPHERE) point = v3(light[1]) + vec * light[1].w;   // sphere.rs:40-42
+                if (sk == SK_RECT) point = mat_vec(v3(light[3]), v3(light[4]), v3(light[5]), vec) + v3(light[6]);
+                dirvec = point - pos;
+            }
+            if (ev == EV_SPECULAR) dirvec = dir0 + vec * rough;
+            if (ev == EV_VOLUME && !vol_scatter) dirvec = din;
+            const V3 nd = normalize_a(dirvec);  // Ray::new
+
+            if (ev == EV_VOLUME) {
+                o = pos;
+                d = nd;
+                if (vol_scatter) {
                     if (!latched) {
                         latched = true;
                         aov_albedo = v3(0.8f, 0.8f, 0.8f);
-                        aov_normal = s.normal;
-                        aov_depth = tr.t_total;
+                        aov_normal = nrm;
+                        aov_depth = hit_t;
                     }
                     T = T * 0.8f;
-                } else {
-                    o = s.position;
-                    d = normalize_a(din);
                 }
-                if (s.face == 4) {  // VolumeBack: leave the medium through sample(ray, bounce + 1)
+                if (face == 4) {  // VolumeBack: leave the medium through sample(ray, bounce + 1)
                     vol_obj = -1;
                     ++bounce;
                     if (bounce > p.max_bounces) finish = true;
-                } else {            // keep marching: sample_volumetric(.., volume_bounce + 1)
-                    vol_obj = s.obj;
+                } else {          // keep marching: sample_volumetric(.., volume_bounce + 1)
+                    vol_obj = hit_obj;
                     ++vb;
                     if (vb > p.max_volume_bounces) finish = true;
+                }
+            } else {
+                float pdf = 1.0f, mpdf = 1.0f;
+                if (ev == EV_DIFFUSE) {
+                    mpdf = dot(nrm, nd) * 0.318309886183790671538f;
+                    const float pb = light_pdf(sc.prims, light, pos, nd, p.clip_min, p.clip_max);
+                    pdf = lerpf(mpdf, pb, 0.5f);
+                }
+                if (fabsf(pdf) <= 1e-5f) {
+                    finish = true;  // no scatter: from_emitted(BLACK)
+                } else {
+                    if (!latched) {
+                        latched = true;
+                        aov_albedo = A;
+                        aov_normal = nrm;
+                        aov_depth = hit_t;
+                    }
+                    T = T * ((A * mpdf) * (1.0f / pdf));
+                    o = pos;
+                    d = nd;
+                    vol_obj = -1;
+                    ++bounce;
+                    if (bounce > p.max_bounces) finish = true;  // sample(): black, AOVs already latched
                 }
             }
         }
