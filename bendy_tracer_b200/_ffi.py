@@ -68,6 +68,8 @@ SIGNATURES = {
     "bt_render_async": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(BtConfig), C.POINTER(BtRenderConfig), C.c_uint64,
                                   C.c_uint64, _P, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64),
                                   C.POINTER(C.c_int32), _P]),
+    "bt_render_stats": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(BtConfig), C.POINTER(BtRenderConfig), C.c_uint64,
+                                  C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
     "bt_resolve_u8": (C.c_int, [_P, _P, C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, _P]),
     "bt_trace_segments": (C.c_int, [_P, _P, C.POINTER(BtConfig), C.c_uint32, _P, _P, C.POINTER(BtSegment)]),
     "bt_camera_rays": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(BtConfig), C.POINTER(BtRenderConfig), C.c_uint64,

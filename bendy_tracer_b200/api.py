@@ -393,6 +393,15 @@ class Tracer:
         buffer._samples = samples.value
         return Status(status.value)
 
+    def render_stats(self, scene: Scene, camera: int, config: RenderConfig, width, height, sample_base=0):
+        """work counters of the render call with these arguments (bt_render_stats): dict"""
+        engine = self.engine or Engine.default(0)
+        cfg, rc = self.config._c(), config._c()
+        out = (C.c_uint64 * 4)()
+        check(lib.bt_render_stats(engine.handle, scene.handle, camera, C.byref(cfg), C.byref(rc), self.seed, sample_base,
+                                  width, height, out))
+        return dict(paths=out[0], scans=out[1], rk4_steps=out[2], events=out[3])
+
     def trace_segments(self, scene: Scene, origins, dirs):
         """ChunkState::try_hit (mod.rs:389-402) / the geodesic segment for each ray; dict of numpy arrays"""
         engine = self.engine or Engine.default(0)

@@ -386,6 +386,35 @@ int bt_render_async(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, con
     GUARD_END
 }
 
+int bt_render_stats(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_config* config,
+                    const bt_render_config* rc, uint64_t seed, uint64_t sample_base, uint32_t width, uint32_t height,
+                    uint64_t stats_out[4]) {
+    if (!engine || !scene || !config || !rc || !stats_out) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    GUARD_BEGIN
+    if (!scene->engine) scene->engine = engine;
+    if (scene->engine != engine) return fail(BT_ERR_INVALID_ARG, "scene belongs to another engine");
+    for (int i = 0; i < 4; ++i) stats_out[i] = 0;
+    if (rc->samples == 0) return BT_OK;
+    CK(cudaSetDevice(engine->device));
+    int rcode = refresh_scene(scene, engine->stream);
+    if (rcode != BT_OK) return rcode;
+    if ((rcode = check_renderable(scene)) != BT_OK) return rcode;
+    RenderParams p;
+    if ((rcode = build_params(scene, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return rcode;
+    size_t fb_bytes = (size_t)width * height * 16;
+    if ((rcode = ensure_scratch(engine, fb_bytes + 64)) != BT_OK) return rcode;
+    CK(cudaMemsetAsync(engine->d_scratch, 0, fb_bytes + 64, engine->stream));
+    p.fb = (float4*)engine->d_scratch;
+    p.stats = (unsigned long long*)((char*)engine->d_scratch + fb_bytes);
+    CK(launch_render(p, engine->stream, &engine->launches));
+    unsigned long long host[4];
+    CK(cudaMemcpyAsync(host, p.stats, sizeof host, cudaMemcpyDeviceToHost, engine->stream));
+    CK(cudaStreamSynchronize(engine->stream));
+    for (int i = 0; i < 4; ++i) stats_out[i] = host[i];
+    return BT_OK;
+    GUARD_END
+}
+
 int bt_render(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_config* config,
               const bt_render_config* rc, uint64_t seed, uint64_t sample_base, float* rgba32f, int mem,
               uint32_t width, uint32_t height, uint64_t* samples_inout, int32_t* status) {

@@ -40,6 +40,7 @@ struct Traced {
     V3 o, d;          // the straight piece the hit lies on (chord under lensing) / escape direction
     float t_total;    // accumulated length up to the hit
     uint32_t steps;
+    uint32_t scans;   // scan_prims calls (= chords intersected)
     bool captured;
 };
 
@@ -50,6 +51,7 @@ template <bool LENS, bool EXACT, class L>
 BT_DEV Traced trace_ray(const RenderParams& p, const SceneView& sc, const L& lens, V3 o, V3 d, float tmin, float tmax, int vol_obj) {
     Traced r;
     r.steps = 0;
+    r.scans = 0;
     r.captured = false;
     const int n_prims = (int)p.scene.n_prims;
     const bool bent = LENS && vol_obj < 0;
@@ -88,6 +90,7 @@ BT_DEV Traced trace_ray(const RenderParams& p, const SceneView& sc, const L& len
             }
         }
         r.h = scan_prims(sc.prims, n_prims, x, dir, cmin, cmax, vol_obj);
+        r.scans++;
         if (r.h.prim >= 0 || last) {
             r.o = x;
             r.d = dir;
@@ -129,8 +132,8 @@ enum { EV_TERMINAL = 0, EV_DIFFUSE = 1, EV_SPECULAR = 2 /* metallic, glass */, E
 // how its new direction is sampled: every variant consumes the same two u32 draws (r1, r2)
 enum { SK_NONE = 0, SK_COSINE = 1, SK_HEMI = 2, SK_SPHERE = 3, SK_RECT = 4 };
 
-template <bool LENS, bool EXACT, int NL>
-__global__ void __launch_bounds__(256, 3) render_kernel(const __grid_constant__ RenderParams p) {
+template <bool STATS, bool LENS, bool EXACT, int NL>
+BT_DEV void render_body(const RenderParams& p) {
     extern __shared__ float4 smem[];
     const SceneView sc = stage_scene(p, smem);
     const typename LensSel<NL>::type lens = LensSel<NL>::make(sc.lens, (int)p.scene.n_lens);
@@ -151,6 +154,7 @@ __global__ void __launch_bounds__(256, 3) render_kernel(const __grid_constant__ 
     V3 acc = v3(0.0f, 0.0f, 0.0f);
     uint32_t path = 0;
     bool alive = false, done = !valid;
+    uint32_t st_scans = 0, st_steps = 0, st_events = 0;  // STATS only
 
     // per-path state
     Rng rng;
@@ -200,6 +204,11 @@ __global__ void __launch_bounds__(256, 3) render_kernel(const __grid_constant__ 
                                                      in_volume ? p.volume_step : p.clip_max, vol_obj);
             din = tr.d;
             hit_t = tr.t_total;
+            if (STATS) {
+                st_scans += tr.scans;
+                st_steps += tr.steps;
+                st_events++;
+            }
             if (tr.h.prim < 0) {
                 finish = true;
                 if (!tr.captured) {  // sample_root, mod.rs:429-452
@@ -390,6 +399,26 @@ __global__ void __launch_bounds__(256, 3) render_kernel(const __grid_constant__ 
         v.z += acc.z;
         p.fb[pixel] = v;
     }
+    if (STATS) {
+        const uint32_t a = __reduce_add_sync(0xffffffffu, valid ? path : 0u), b = __reduce_add_sync(0xffffffffu, st_scans);
+        const uint32_t c = __reduce_add_sync(0xffffffffu, st_steps), e = __reduce_add_sync(0xffffffffu, st_events);
+        if (lane == 0) {
+            atomicAdd(p.stats + 0, (unsigned long long)a);
+            atomicAdd(p.stats + 1, (unsigned long long)b);
+            atomicAdd(p.stats + 2, (unsigned long long)c);
+            atomicAdd(p.stats + 3, (unsigned long long)e);
+        }
+    }
+}
+
+template <bool LENS, bool EXACT, int NL>
+__global__ void __launch_bounds__(256, 3) render_kernel(const __grid_constant__ RenderParams p) {
+    render_body<false, LENS, EXACT, NL>(p);
+}
+// the same kernel + work counters for bench.py's roofline accounting (never timed)
+template <bool LENS, bool EXACT, int NL>
+__global__ void __launch_bounds__(256, 2) render_kernel_stats(const __grid_constant__ RenderParams p) {
+    render_body<true, LENS, EXACT, NL>(p);
 }
 
 template <bool LENS, bool EXACT, int NL>
@@ -546,7 +575,10 @@ size_t render_smem_bytes(const RenderParams& p) { return (size_t)p.scene.blob_f4
 cudaError_t launch_render(const RenderParams& p, cudaStream_t stream, uint64_t* launches) {
     dim3 grid((p.width + 15) / 16, (p.height + 15) / 16), block(256);
     size_t smem = render_smem_bytes(p);
-    BT_DISPATCH_LENS(render_kernel, grid, block, smem, stream, p);
+    if (p.stats)
+        BT_DISPATCH_LENS(render_kernel_stats, grid, block, smem, stream, p);
+    else
+        BT_DISPATCH_LENS(render_kernel, grid, block, smem, stream, p);
     ++*launches;
     return cudaGetLastError();
 }

@@ -158,6 +158,14 @@ int bt_render_async(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, con
                     float* rgba32f_device, uint32_t width, uint32_t height, uint64_t* samples_inout,
                     int32_t* status, void* cuda_stream);
 
+/* Work counters of one bt_render call (same scene, config, seeds => same deterministic paths),
+ * rendered into a scratch buffer by an instrumented copy of the render kernel; never timed.
+ * stats_out = {camera paths, segment-intersection scans (each tests every primitive once), RK4
+ * steps, shading events}.  bench.py turns them into the algorithmic flops of SURVEY 8d. */
+int bt_render_stats(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_config* config,
+                    const bt_render_config* render_config, uint64_t seed, uint64_t sample_base,
+                    uint32_t width, uint32_t height, uint64_t stats_out[4]);
+
 /* Buffer::preview, reference src/tracer/buffer.rs:117-138 (+ ColorSpace::convert_linear :19-30,
  * linear_to_srgb / f32_to_u8 src/color.rs:14-24).  rgba8 lives where rgba32f lives. */
 int bt_resolve_u8(bt_engine* engine, const float* rgba32f, int mem, uint32_t width, uint32_t height,
