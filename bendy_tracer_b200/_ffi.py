@@ -59,6 +59,7 @@ SIGNATURES = {
     "bt_scene_apply_transform": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_float)]),
     "bt_scene_set_lenses": (C.c_int, [_P, _P, C.c_uint32, C.POINTER(BtLensConfig)]),
     "bt_lens_config_default": (None, [C.POINTER(BtLensConfig)]),
+    "bt_scene_set_accel": (C.c_int, [_P, C.c_int]),
     "bt_scene_get_info": (C.c_int, [_P, C.POINTER(BtSceneInfo)]),
     "bt_config_default": (None, [C.POINTER(BtConfig)]),
     "bt_render_config_default": (None, [C.POINTER(BtRenderConfig)]),

@@ -246,6 +246,10 @@ class Scene:
         cfg = (lens_config or LensConfig())._c()
         check(lib.bt_scene_set_lenses(self.handle, xyzr.ctypes.data, len(xyzr), C.byref(cfg)))
 
+    def set_accel(self, accel):
+        """closest-hit structure: "auto" (linear scan up to 64 primitives, BVH beyond), "linear", "bvh" """
+        check(lib.bt_scene_set_accel(self.handle, {"auto": 0, "linear": 1, "bvh": 2}[accel]))
+
     def info(self):
         i = _ffi.BtSceneInfo()
         check(lib.bt_scene_get_info(self.handle, C.byref(i)))

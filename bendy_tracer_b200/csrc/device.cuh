@@ -245,7 +245,7 @@ BT_DEV Hit scan_prims(const float4* prims, int n_prims, V3 o, V3 d, float tmin, 
     for (int i = 0; i < n_prims; ++i) {
         const float4* q = prims + i * PRIM_STRIDE;
         float4 meta = q[4];
-        int type = __float_as_int(meta.x);
+        int type = __float_as_int(meta.x) & 3;
         if (type == PRIM_SPHERE) {
             float4 q0 = q[0];
             float r2 = q[1].x;
@@ -277,6 +277,80 @@ BT_DEV Hit scan_prims(const float4* prims, int n_prims, V3 o, V3 d, float tmin, 
     return h;
 }
 
+// Closest hit through the BVH (extension; scenes above the linear-scan budget).  Records and
+// nodes are read from global memory (L2 / HBM), the traversal stack lives in shared memory
+// (stack[level * blockDim.x + tid]: conflict-free).  Same per-primitive tests as the scan; an
+// exact-distance tie is decided by the canonical primitive index exactly as the reference's
+// scan order would: the later record wins unless it is a cuboid face (strict '<', cuboid.rs:97).
+BT_DEV Hit bvh_closest(const float4* __restrict__ prims, const float4* __restrict__ nodes, uint32_t* stack, V3 o, V3 d,
+                       float tmin, float tmax) {
+    Hit h;
+    h.t = tmax;
+    h.prim = -1;
+    h.face = 0;
+    int best_canon = -1;
+    bool best_strict = false;
+    const V3 inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const uint32_t lanes = blockDim.x, tid = threadIdx.x;
+    uint32_t sp = 0, node = 0;
+    for (;;) {
+        const float4 b0 = __ldg(nodes + node * BVH_STRIDE), b1 = __ldg(nodes + node * BVH_STRIDE + 1);
+        // slab test against [tmin, h.t] (inclusive: equal-distance hits must still be visited)
+        const float tx0 = (b0.x - o.x) * inv.x, tx1 = (b1.x - o.x) * inv.x;
+        const float ty0 = (b0.y - o.y) * inv.y, ty1 = (b1.y - o.y) * inv.y;
+        const float tz0 = (b0.z - o.z) * inv.z, tz1 = (b1.z - o.z) * inv.z;
+        const float tnear = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
+        const float tfar = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), h.t));
+        const uint32_t a = __float_as_uint(b0.w), b = __float_as_uint(b1.w);
+        bool descend = false;
+        if (tnear <= tfar * 1.00001f + 1e-6f) {
+            if (b & BVH_LEAF) {
+                const uint32_t count = b & 0x7fffffffu;
+                for (uint32_t i = a; i < a + count; ++i) {
+                    const float4* q = prims + i * PRIM_STRIDE;
+                    const int meta = __float_as_int(__ldg(q + 4).x);
+                    const int type = meta & 3, canon = meta >> 2;
+                    const bool strict = type == PRIM_CUBOID_FACE;
+                    float t;
+                    bool front = true, ok;
+                    if (type == PRIM_SPHERE) {
+                        ok = sphere_roots(__ldg(q), __ldg(q + 1).x, o, d, tmin, h.t, t);
+                    } else {
+                        ok = rect_test(q, o, d, tmin, h.t, false, t, front);
+                    }
+                    if (ok) {
+                        // t <= h.t here.  Equal distance: the later canonical index wins unless strict.
+                        bool take = t < h.t;
+                        if (!take) take = canon > best_canon ? !strict : best_strict;
+                        if (take) {
+                            h.t = t;
+                            h.prim = (int)i;
+                            h.face = type == PRIM_SPHERE ? 8 : (front ? 0 : 1);
+                            best_canon = canon;
+                            best_strict = strict;
+                        }
+                    }
+                }
+            } else {
+                // near child first: the sign of the direction on the split axis
+                const uint32_t right = b & 0x0fffffffu, axis = b >> 28;
+                const float da = axis == 0 ? d.x : (axis == 1 ? d.y : d.z);
+                const uint32_t first = da >= 0.0f ? a : right, second = da >= 0.0f ? right : a;
+                stack[sp * lanes + tid] = second;
+                ++sp;
+                node = first;
+                descend = true;
+            }
+        }
+        if (!descend) {
+            if (sp == 0) break;
+            --sp;
+            node = stack[sp * lanes + tid];
+        }
+    }
+    return h;
+}
+
 struct Surface {  // Manifold (ray.rs:36-47) reduced to what shading reads
     V3 position, normal;
     int face, mat, vol, obj;
@@ -293,7 +367,7 @@ BT_DEV Surface resolve_hit(const float4* prims, const Hit& h, V3 o, V3 d) {
     s.position = o + h.t * d;
     s.center = v3(0.0f, 0.0f, 0.0f);
     s.radius = 0.0f;
-    if (__float_as_int(meta.x) == PRIM_SPHERE) {
+    if ((__float_as_int(meta.x) & 3) == PRIM_SPHERE) {
         float4 q0 = q[0];
         s.vol = __float_as_int(meta.z);
         s.center = v3(q0);

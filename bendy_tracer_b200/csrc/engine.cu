@@ -48,6 +48,7 @@ struct bt_scene {
     bt_engine* engine;
     Scene scene;
     FlatScene flat;
+    int accel;          // ACCEL_AUTO / ACCEL_LINEAR / ACCEL_BVH
     bool flat_dirty;    // host flattening out of date
     bool device_dirty;  // device copy out of date
     float4* d_blob;
@@ -70,7 +71,7 @@ int ensure_scratch(bt_engine* e, size_t bytes) {
 
 int refresh_scene(bt_scene* s, cudaStream_t stream) {
     if (s->flat_dirty) {
-        s->flat = flatten(s->scene);
+        s->flat = flatten(s->scene, s->accel);
         s->flat_dirty = false;
         s->device_dirty = true;
     }
@@ -157,7 +158,7 @@ int check_renderable(const bt_scene* s) {
         return fail(BT_ERR_SCENE, "Uniform::new called with `low >= high` (a Diffuse surface needs at least one LIGHT object)");
     if (s->flat.unsupported_light) return fail(BT_ERR_UNSUPPORTED, "a Cuboid with ObjectFlags::LIGHT is not supported by the device path yet");
     if (render_smem_bytes(RenderParams{s->flat.header}) > 200 * 1024)
-        return fail(BT_ERR_UNSUPPORTED, "scene does not fit the shared-memory staging buffer");
+        return fail(BT_ERR_UNSUPPORTED, "scene does not fit the shared-memory staging buffer (use BT_ACCEL_BVH / BT_ACCEL_AUTO)");
     return BT_OK;
 }
 
@@ -222,8 +223,9 @@ int bt_scene_create_json(bt_engine* engine, const void* bytes, size_t n, bt_scen
     s->d_grids = 0;
     s->blob_cap = s->grids_cap = 0;
     try {
+        s->accel = ACCEL_AUTO;
         s->scene = Scene::from_json(bytes, n);
-        s->flat = flatten(s->scene);
+        s->flat = flatten(s->scene, s->accel);
     } catch (...) {
         delete s;
         throw;
@@ -317,13 +319,21 @@ int bt_scene_set_lenses(bt_scene* scene, const float* xyzr, uint32_t n, const bt
     return BT_OK;
 }
 
+int bt_scene_set_accel(bt_scene* scene, int accel) {
+    if (!scene) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    if (accel < ACCEL_AUTO || accel > ACCEL_BVH) return fail(BT_ERR_INVALID_ARG, "accel must be BT_ACCEL_AUTO, _LINEAR or _BVH");
+    scene->accel = accel;
+    scene->flat_dirty = true;
+    return BT_OK;
+}
+
 int bt_scene_get_info(const bt_scene* scene, bt_scene_info* info) {
     if (!scene || !info) return fail(BT_ERR_INVALID_ARG, "NULL argument");
     GUARD_BEGIN
     FlatScene tmp;
     const FlatScene* f = &scene->flat;
     if (scene->flat_dirty) {
-        tmp = flatten(scene->scene);
+        tmp = flatten(scene->scene, scene->accel);
         f = &tmp;
     }
     info->n_objects = (uint32_t)scene->scene.objects.size();
@@ -332,7 +342,7 @@ int bt_scene_get_info(const bt_scene* scene, bt_scene_info* info) {
     info->n_lights = f->header.n_lights;
     info->n_volumes = f->header.n_vols;
     info->n_lenses = f->header.n_lens;
-    info->n_bvh_nodes = 0;
+    info->n_bvh_nodes = f->header.n_bvh;
     info->root_material = scene->scene.root_material;
     return BT_OK;
     GUARD_END

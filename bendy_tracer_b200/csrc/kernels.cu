@@ -14,6 +14,8 @@ namespace bt {
 namespace {
 
 struct SceneView {
+    const float4* nodes;   // BVH nodes in global memory (BVH kernels only)
+    uint32_t* stack;       // BVH traversal stack in shared memory
     const float4* prims;
     const float4* mats;
     const float4* lights;
@@ -22,15 +24,19 @@ struct SceneView {
     const float* grids;
 };
 
+template <bool BVH>
 BT_DEV SceneView stage_scene(const RenderParams& p, float4* smem) {
-    for (uint32_t i = threadIdx.x; i < p.scene.blob_f4; i += blockDim.x) smem[i] = p.blob[i];
+    const uint32_t base = p.scene.stage_off;
+    for (uint32_t i = threadIdx.x; i < p.scene.stage_f4; i += blockDim.x) smem[i] = p.blob[base + i];
     __syncthreads();
     SceneView s;
-    s.prims = smem + p.scene.prim_off;
-    s.mats = smem + p.scene.mat_off;
-    s.lights = smem + p.scene.light_off;
-    s.vols = smem + p.scene.vol_off;
-    s.lens = smem + p.scene.lens_off;
+    s.prims = BVH ? p.blob + p.scene.prim_off : smem + (p.scene.prim_off - base);
+    s.nodes = p.blob + p.scene.bvh_off;
+    s.stack = reinterpret_cast<uint32_t*>(smem + p.scene.stage_f4);
+    s.mats = smem + (p.scene.mat_off - base);
+    s.lights = smem + (p.scene.light_off - base);
+    s.vols = smem + (p.scene.vol_off - base);
+    s.lens = smem + (p.scene.lens_off - base);
     s.grids = p.grids;
     return s;
 }
@@ -47,7 +53,7 @@ struct Traced {
 // One "ray" of the render loop.  Flat field (or inside a volume march): exactly try_hit /
 // try_hit_volume.  Lens field: RK4 chords, each intersected with the same scan (ONE scan call
 // site: the kernel must stay inside the instruction cache).
-template <bool LENS, bool EXACT, class L>
+template <bool LENS, bool EXACT, bool BVH, class L>
 BT_DEV Traced trace_ray(const RenderParams& p, const SceneView& sc, const L& lens, V3 o, V3 d, float tmin, float tmax, int vol_obj) {
     Traced r;
     r.steps = 0;
@@ -89,7 +95,10 @@ BT_DEV Traced trace_ray(const RenderParams& p, const SceneView& sc, const L& len
                 last = false;
             }
         }
-        r.h = scan_prims(sc.prims, n_prims, x, dir, cmin, cmax, vol_obj);
+        if (BVH)
+            r.h = bvh_closest(sc.prims, sc.nodes, sc.stack, x, dir, cmin, cmax);
+        else
+            r.h = scan_prims(sc.prims, n_prims, x, dir, cmin, cmax, vol_obj);
         r.scans++;
         if (r.h.prim >= 0 || last) {
             r.o = x;
@@ -132,10 +141,10 @@ enum { EV_TERMINAL = 0, EV_DIFFUSE = 1, EV_SPECULAR = 2 /* metallic, glass */, E
 // how its new direction is sampled: every variant consumes the same two u32 draws (r1, r2)
 enum { SK_NONE = 0, SK_COSINE = 1, SK_HEMI = 2, SK_SPHERE = 3, SK_RECT = 4 };
 
-template <bool STATS, bool LENS, bool EXACT, int NL>
+template <bool STATS, bool LENS, bool EXACT, int NL, bool BVH>
 BT_DEV void render_body(const RenderParams& p) {
     extern __shared__ float4 smem[];
-    const SceneView sc = stage_scene(p, smem);
+    const SceneView sc = stage_scene<BVH>(p, smem);
     const typename LensSel<NL>::type lens = LensSel<NL>::make(sc.lens, (int)p.scene.n_lens);
     Consts k;
     k.tau_scale = p.tau_scale;
@@ -200,7 +209,7 @@ BT_DEV void render_body(const RenderParams& p) {
         const bool in_volume = vol_obj >= 0;
 
         if (alive) {
-            const Traced tr = trace_ray<LENS, EXACT>(p, sc, lens, o, d, in_volume ? 0.0f : p.clip_min,
+            const Traced tr = trace_ray<LENS, EXACT, BVH>(p, sc, lens, o, d, in_volume ? 0.0f : p.clip_min,
                                                      in_volume ? p.volume_step : p.clip_max, vol_obj);
             din = tr.d;
             hit_t = tr.t_total;
@@ -411,27 +420,27 @@ BT_DEV void render_body(const RenderParams& p) {
     }
 }
 
-template <bool LENS, bool EXACT, int NL>
+template <bool LENS, bool EXACT, int NL, bool BVH>
 __global__ void __launch_bounds__(256, 3) render_kernel(const __grid_constant__ RenderParams p) {
-    render_body<false, LENS, EXACT, NL>(p);
+    render_body<false, LENS, EXACT, NL, BVH>(p);
 }
 // the same kernel + work counters for bench.py's roofline accounting (never timed)
-template <bool LENS, bool EXACT, int NL>
+template <bool LENS, bool EXACT, int NL, bool BVH>
 __global__ void __launch_bounds__(256, 2) render_kernel_stats(const __grid_constant__ RenderParams p) {
-    render_body<true, LENS, EXACT, NL>(p);
+    render_body<true, LENS, EXACT, NL, BVH>(p);
 }
 
-template <bool LENS, bool EXACT, int NL>
+template <bool LENS, bool EXACT, int NL, bool BVH>
 __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ RenderParams p, uint32_t n, const float* __restrict__ origins,
                                                     const float* __restrict__ dirs, DeviceSegment* __restrict__ out) {
     extern __shared__ float4 smem[];
-    const SceneView sc = stage_scene(p, smem);
+    const SceneView sc = stage_scene<BVH>(p, smem);
     const typename LensSel<NL>::type lens = LensSel<NL>::make(sc.lens, (int)p.scene.n_lens);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n) return;  // (after the staging barrier)
     V3 o = v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
     V3 d = v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
-    Traced tr = trace_ray<LENS, EXACT>(p, sc, lens, o, d, p.clip_min, p.clip_max, -1);
+    Traced tr = trace_ray<LENS, EXACT, BVH>(p, sc, lens, o, d, p.clip_min, p.clip_max, -1);
     DeviceSegment seg;
     seg.steps = tr.steps;
     seg.obj = -1;
@@ -550,26 +559,26 @@ cudaError_t ensure_smem(K kernel, size_t bytes) {
 
 }  // namespace
 
-size_t render_smem_bytes(const RenderParams& p) { return (size_t)p.scene.blob_f4 * sizeof(float4); }
+size_t render_smem_bytes(const RenderParams& p) {
+    return (size_t)p.scene.stage_f4 * sizeof(float4) + (p.scene.n_bvh ? (size_t)BVH_STACK * 256 * sizeof(uint32_t) : 0);
+}
 
-// picks <LENS, EXACT, NL> from the scene header
-#define BT_DISPATCH_LENS(KERNEL, GRID, BLOCK, SMEM, STREAM, ...)                                   \
-    do {                                                                                           \
-        cudaError_t e_;                                                                            \
-        const bool exact_ = p.scene.lens_exact != 0;                                               \
-        if (p.scene.n_lens == 0) {                                                                 \
-            if ((e_ = ensure_smem(KERNEL<false, false, 0>, SMEM)) != cudaSuccess) return e_;       \
-            KERNEL<false, false, 0><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);                   \
-        } else if (p.scene.n_lens == 1 && !exact_) {                                               \
-            if ((e_ = ensure_smem(KERNEL<true, false, 1>, SMEM)) != cudaSuccess) return e_;        \
-            KERNEL<true, false, 1><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);                    \
-        } else if (!exact_) {                                                                      \
-            if ((e_ = ensure_smem(KERNEL<true, false, 0>, SMEM)) != cudaSuccess) return e_;        \
-            KERNEL<true, false, 0><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);                    \
-        } else {                                                                                   \
-            if ((e_ = ensure_smem(KERNEL<true, true, 0>, SMEM)) != cudaSuccess) return e_;         \
-            KERNEL<true, true, 0><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);                     \
-        }                                                                                          \
+// picks <LENS, EXACT, NL, BVH> from the scene header
+#define BT_LAUNCH_(KERNEL, L, E, N, B, GRID, BLOCK, SMEM, STREAM, ...)                                 \
+    do {                                                                                              \
+        cudaError_t e_ = ensure_smem(KERNEL<L, E, N, B>, SMEM);                                        \
+        if (e_ != cudaSuccess) return e_;                                                              \
+        KERNEL<L, E, N, B><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);                                \
+    } while (0)
+#define BT_DISPATCH_LENS(KERNEL, GRID, BLOCK, SMEM, STREAM, ...)                                       \
+    do {                                                                                              \
+        const bool exact_ = p.scene.lens_exact != 0, bvh_ = p.scene.n_bvh != 0;                        \
+        if (p.scene.n_lens == 0 && !bvh_) BT_LAUNCH_(KERNEL, false, false, 0, false, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);      \
+        else if (p.scene.n_lens == 0) BT_LAUNCH_(KERNEL, false, false, 0, true, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);           \
+        else if (bvh_) BT_LAUNCH_(KERNEL, true, false, 0, true, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);                            \
+        else if (p.scene.n_lens == 1 && !exact_) BT_LAUNCH_(KERNEL, true, false, 1, false, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__); \
+        else if (!exact_) BT_LAUNCH_(KERNEL, true, false, 0, false, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);                        \
+        else BT_LAUNCH_(KERNEL, true, true, 0, false, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);                                      \
     } while (0)
 
 cudaError_t launch_render(const RenderParams& p, cudaStream_t stream, uint64_t* launches) {

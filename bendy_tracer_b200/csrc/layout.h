@@ -17,6 +17,13 @@ namespace bt {
 //   q2 = (ax.xyz, cx)  q3 = (ay.xyz, cy)   with local.x = dot(pos, ax) + cx
 enum { PRIM_SPHERE = 0, PRIM_RECT = 1, PRIM_CUBOID_FACE = 2 };
 enum { PRIM_STRIDE = 5 };
+// q4.x = type | (canonical primitive index << 2): under a BVH the records are stored in tree order
+// and the canonical index decides exact-distance ties the way the reference's scan order does.
+
+// ---- BVH node: BVH_STRIDE float4 (extension: built when a scene exceeds the linear-scan budget)
+//   b0 = (min.xyz, a)  b1 = (max.xyz, b)
+//   inner: a = left child, b = right child | split axis << 28     leaf: a = first record, b = count | 1<<31
+enum { BVH_STRIDE = 2, BVH_LEAF = 0x80000000u, BVH_STACK = 32 };
 
 // ---- material record: MAT_STRIDE float4 (reference src/scene/data/material.rs:22-44) -------
 //   m0 = (albedo.rgb, kind)   m1 = (roughness, ior, intensity, -)
@@ -47,6 +54,8 @@ struct SceneHeader {
     uint32_t n_vols, vol_off;
     uint32_t n_lens, lens_off;
     uint32_t blob_f4;                // total float4 count
+    uint32_t n_bvh, bvh_off;         // BVH nodes (0: linear scan over shared memory)
+    uint32_t stage_off, stage_f4;    // the part of the blob every CTA stages into shared memory
     uint32_t has_volume_prims;       // any sphere with volume != None
     // root material folded to what sample_root returns (src/tracer/mod.rs:429-452)
     float root_color[3], root_albedo[3];

@@ -10,6 +10,7 @@
 
 #include <zlib.h>
 
+#include <algorithm>
 #include <charconv>
 #include <cmath>
 #include <cstdio>
@@ -754,7 +755,25 @@ void Scene::apply_transform(uint64_t object_ref, const Affine& affine) {  // obj
 // ------------------------------------------------------------------------------------------
 namespace {
 
-void push_rect(std::vector<float4>& blob, const Rect& r, const Affine& tf, int type, uint32_t mat, uint32_t obj) {
+struct Bounds {
+    float lo[3], hi[3];
+};
+void push_rect(std::vector<float4>& blob, std::vector<Bounds>& bounds, const Rect& r, const Affine& tf, int type, uint32_t mat, uint32_t obj) {
+    {   // world-space AABB of the four corners (rect.rs:38-56)
+        Bounds b;
+        for (int k = 0; k < 3; ++k) { b.lo[k] = 3.0e38f; b.hi[k] = -3.0e38f; }
+        for (int c = 0; c < 4; ++c) {
+            float sx = (c & 1) ? -r.half_width : r.half_width, sy = (c & 2) ? -r.half_height : r.half_height;
+            float local[3] = {r.x[0] * sx + r.y[0] * sy, r.x[1] * sx + r.y[1] * sy, r.x[2] * sx + r.y[2] * sy}, w[3];
+            mat_vec(tf, local, w);
+            for (int k = 0; k < 3; ++k) {
+                float v = w[k] + tf.f[9 + k];
+                b.lo[k] = std::min(b.lo[k], v);
+                b.hi[k] = std::max(b.hi[k], v);
+            }
+        }
+        bounds.push_back(b);
+    }
     float n[3];
     mat_vec(tf, r.z, n);  // rect.rs:119: transform.transform_vector3a(self.z)
     // local = M^-1 (pos - T);  local.x = dot(pos, ax) + cx with ax = M^-T x, cx = -dot(ax, T)
@@ -789,12 +808,61 @@ void push_rect(std::vector<float4>& blob, const Rect& r, const Affine& tf, int t
     blob.push_back(f4(tf.f[9], tf.f[10], tf.f[11], hh2));
     blob.push_back(f4((float)ax[0], (float)ax[1], (float)ax[2], (float)cx));
     blob.push_back(f4((float)ay[0], (float)ay[1], (float)ay[2], (float)cy));
-    blob.push_back(f4(as_f((uint32_t)type), as_f(mat), area, as_f(obj)));
+    blob.push_back(f4(as_f((uint32_t)type | ((uint32_t)(blob.size() / PRIM_STRIDE) << 2)), as_f(mat), area, as_f(obj)));
 }
+
+// ---- BVH: median split on the widest centroid axis, <= 4 primitives per leaf ----------------
+struct BvhBuild {
+    const std::vector<Bounds>& b;
+    std::vector<uint32_t> order;   // record position -> canonical primitive index
+    std::vector<float4> nodes;
+    explicit BvhBuild(const std::vector<Bounds>& bounds) : b(bounds) {
+        for (uint32_t i = 0; i < b.size(); ++i) order.push_back(i);
+    }
+    uint32_t build(uint32_t first, uint32_t count, int depth) {
+        Bounds box;
+        float clo[3], chi[3];
+        for (int k = 0; k < 3; ++k) { box.lo[k] = clo[k] = 3.0e38f; box.hi[k] = chi[k] = -3.0e38f; }
+        for (uint32_t i = first; i < first + count; ++i) {
+            const Bounds& p = b[order[i]];
+            for (int k = 0; k < 3; ++k) {
+                box.lo[k] = std::min(box.lo[k], p.lo[k]);
+                box.hi[k] = std::max(box.hi[k], p.hi[k]);
+                float c = 0.5f * (p.lo[k] + p.hi[k]);
+                clo[k] = std::min(clo[k], c);
+                chi[k] = std::max(chi[k], c);
+            }
+        }
+        for (int k = 0; k < 3; ++k) {  // conservative padding: the tree must never cull what the scan would hit
+            float pad = 1e-4f * std::max(1.0f, std::max(std::fabs(box.lo[k]), std::fabs(box.hi[k])));
+            box.lo[k] -= pad;
+            box.hi[k] += pad;
+        }
+        uint32_t self = (uint32_t)(nodes.size() / BVH_STRIDE);
+        nodes.push_back(f4(box.lo[0], box.lo[1], box.lo[2], 0.0f));
+        nodes.push_back(f4(box.hi[0], box.hi[1], box.hi[2], 0.0f));
+        int axis = 0;
+        for (int k = 1; k < 3; ++k)
+            if (chi[k] - clo[k] > chi[axis] - clo[axis]) axis = k;
+        if (count <= 4 || depth >= (int)BVH_STACK - 2 || !(chi[axis] > clo[axis])) {
+            nodes[self * BVH_STRIDE].w = as_f(first);
+            nodes[self * BVH_STRIDE + 1].w = as_f(count | BVH_LEAF);
+            return self;
+        }
+        uint32_t mid = first + count / 2;
+        std::nth_element(order.begin() + first, order.begin() + mid, order.begin() + first + count,
+                         [&](uint32_t x, uint32_t y) { return b[x].lo[axis] + b[x].hi[axis] < b[y].lo[axis] + b[y].hi[axis]; });
+        uint32_t left = build(first, mid - first, depth + 1);
+        uint32_t right = build(mid, first + count - mid, depth + 1);
+        nodes[self * BVH_STRIDE].w = as_f(left);
+        nodes[self * BVH_STRIDE + 1].w = as_f(right | ((uint32_t)axis << 28));
+        return self;
+    }
+};
 
 }  // namespace
 
-FlatScene flatten(const Scene& scene) {
+FlatScene flatten(const Scene& scene, int accel) {
     FlatScene fs;
     std::memset(&fs.header, 0, sizeof fs.header);
     fs.diffuse_without_light = false;
@@ -850,6 +918,7 @@ FlatScene flatten(const Scene& scene) {
     }
 
     std::vector<float4> prims, lights;
+    std::vector<Bounds> bounds;
     bool any_diffuse = false;
     for (std::map<uint64_t, Object>::const_iterator it = scene.objects.begin(); it != scene.objects.end(); ++it) {
         const Object& o = it->second;
@@ -872,11 +941,16 @@ FlatScene flatten(const Scene& scene) {
             prims.push_back(f4(r * r, 3.14159265358979323846f * r * r, 0.0f, 0.0f));
             prims.push_back(f4(0, 0, 0, 0));
             prims.push_back(f4(0, 0, 0, 0));
-            prims.push_back(f4(as_f(PRIM_SPHERE), as_f(mat), as_f(vol), as_f(obj)));
+            prims.push_back(f4(as_f(PRIM_SPHERE | ((uint32_t)(prims.size() / PRIM_STRIDE) << 2)), as_f(mat), as_f(vol), as_f(obj)));
+            {
+                Bounds b;
+                for (int k = 0; k < 3; ++k) { b.lo[k] = tf.f[9 + k] - r; b.hi[k] = tf.f[9 + k] + r; }
+                bounds.push_back(b);
+            }
             n_prims = 1;
             any_diffuse |= scene.get_data(o.material).mat_kind == MAT_DIFFUSE;
         } else if (o.kind == OBJ_RECT) {
-            push_rect(prims, o.rect, tf, PRIM_RECT, resolve.material(o.rect.material), obj);
+            push_rect(prims, bounds, o.rect, tf, PRIM_RECT, resolve.material(o.rect.material), obj);
             n_prims = 1;
             any_diffuse |= scene.get_data(o.rect.material).mat_kind == MAT_DIFFUSE;
         } else if (o.kind == OBJ_CUBOID) {
@@ -886,7 +960,7 @@ FlatScene flatten(const Scene& scene) {
                 float t[3];
                 mat_vec(tf, o.face_offset[i], t);
                 for (int k = 0; k < 3; ++k) ftf.f[9 + k] = t[k] + tf.f[9 + k];
-                push_rect(prims, o.faces[i], ftf, PRIM_CUBOID_FACE, resolve.material(o.faces[i].material), obj);
+                push_rect(prims, bounds, o.faces[i], ftf, PRIM_CUBOID_FACE, resolve.material(o.faces[i].material), obj);
                 any_diffuse |= scene.get_data(o.faces[i].material).mat_kind == MAT_DIFFUSE;
             }
             n_prims = 6;
@@ -932,6 +1006,31 @@ FlatScene flatten(const Scene& scene) {
     h.n_vols = (uint32_t)(vols.size() / VOL_STRIDE);
     h.n_lens = (uint32_t)(lens.size() / LENS_STRIDE);
     h.prim_off = 0;
+    // acceleration structure: the linear scan of the reference for small scenes, a BVH beyond
+    bool use_bvh = accel == ACCEL_BVH || (accel == ACCEL_AUTO && h.n_prims > (uint32_t)BVH_AUTO_PRIMS);
+    if (h.has_volume_prims) use_bvh = false;  // hit_volumetric is scan-order dependent (mod.rs:414-424)
+    std::vector<float4> nodes;
+    for (uint32_t i = 0; i < h.n_prims; ++i) fs.prim_order.push_back(i);
+    if (use_bvh && h.n_prims > 0) {
+        BvhBuild bvh(bounds);
+        bvh.build(0, h.n_prims, 0);
+        std::vector<float4> sorted(prims.size());
+        std::vector<uint32_t> where(h.n_prims);
+        for (uint32_t pos = 0; pos < h.n_prims; ++pos) {
+            where[bvh.order[pos]] = pos;
+            for (int k = 0; k < PRIM_STRIDE; ++k) sorted[pos * PRIM_STRIDE + k] = prims[bvh.order[pos] * PRIM_STRIDE + k];
+        }
+        prims.swap(sorted);
+        fs.prim_order = bvh.order;
+        nodes.swap(bvh.nodes);
+        for (size_t l = 0; l < lights.size(); l += LIGHT_STRIDE) {  // lights point at their primitive record
+            uint32_t first;
+            std::memcpy(&first, &lights[l].y, 4);
+            uint32_t count;
+            std::memcpy(&count, &lights[l].z, 4);
+            if (count) lights[l].y = as_f(where[first]);
+        }
+    }
     fs.blob = prims;
     h.mat_off = (uint32_t)fs.blob.size();
     fs.blob.insert(fs.blob.end(), mats.begin(), mats.end());
@@ -941,7 +1040,14 @@ FlatScene flatten(const Scene& scene) {
     fs.blob.insert(fs.blob.end(), vols.begin(), vols.end());
     h.lens_off = (uint32_t)fs.blob.size();
     fs.blob.insert(fs.blob.end(), lens.begin(), lens.end());
+    h.bvh_off = (uint32_t)fs.blob.size();
+    h.n_bvh = (uint32_t)(nodes.size() / BVH_STRIDE);
+    fs.blob.insert(fs.blob.end(), nodes.begin(), nodes.end());
     h.blob_f4 = (uint32_t)fs.blob.size();
+    // shared-memory staging: everything for the linear scan; under a BVH the primitives and nodes
+    // stay in global memory (L2 / HBM) and only the small tables are staged
+    h.stage_off = h.n_bvh ? h.mat_off : 0;
+    h.stage_f4 = h.bvh_off - h.stage_off;
     h.kappa = scene.lens_config.kappa;
     h.h_min = scene.lens_config.h_min;
     h.h_max = scene.lens_config.h_max;

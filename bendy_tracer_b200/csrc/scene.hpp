@@ -114,10 +114,13 @@ struct FlatScene {
     std::vector<float4> blob;
     std::vector<float> grids;
     std::vector<uint64_t> object_refs;  // object index -> ObjectRef
+    std::vector<uint32_t> prim_order;   // record position -> canonical primitive index (identity without a BVH)
     bool diffuse_without_light;         // a Diffuse material is reachable but no LIGHT exists
     bool unsupported_light;             // a Cuboid carries ObjectFlags::LIGHT (not flattened yet)
 };
-FlatScene flatten(const Scene& scene);
+// accel: 0 = automatic (BVH above BVH_AUTO_PRIMS primitives), 1 = linear scan, 2 = BVH
+enum { ACCEL_AUTO = 0, ACCEL_LINEAR = 1, ACCEL_BVH = 2, BVH_AUTO_PRIMS = 64 };
+FlatScene flatten(const Scene& scene, int accel = ACCEL_AUTO);
 
 // Uniform<f32>::new / new_inclusive scale (rand 0.8.5 UniformFloat) -- host-side constants
 float uniform_scale(float low, float high);

@@ -131,6 +131,12 @@ int bt_scene_apply_transform(bt_scene* scene, uint64_t object_ref, const float a
 /* lens field: n point masses (x, y, z, r_s); cfg may be NULL for the defaults */
 int bt_scene_set_lenses(bt_scene* scene, const float* xyzr, uint32_t n, const bt_lens_config* cfg);
 void bt_lens_config_default(bt_lens_config* cfg);
+/* Closest-hit structure.  AUTO: the reference's linear scan (try_hit, src/tracer/mod.rs:389-402)
+ * over shared memory up to 64 flattened primitives, a BVH (global-memory nodes, shared-memory
+ * traversal stack) beyond.  Both give the same hits, exact-distance ties included.  Scenes with
+ * volumetric spheres always use the scan (hit_volumetric depends on the scan order, :414-424). */
+enum { BT_ACCEL_AUTO = 0, BT_ACCEL_LINEAR = 1, BT_ACCEL_BVH = 2 };
+int bt_scene_set_accel(bt_scene* scene, int accel);
 int bt_scene_get_info(const bt_scene* scene, bt_scene_info* info);
 
 /* ---- the hot path ---------------------------------------------------------------------- */

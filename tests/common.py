@@ -48,3 +48,77 @@ def engine_render(esc, cam, width, height, samples, subsample=0, output=0, seed=
 def mae_per_channel(a, b, n):
     """per-channel mean absolute error of the resolved (sum / samples) images"""
     return np.abs(a[..., :3].astype(np.float64) - b[..., :3].astype(np.float64)).mean(axis=(0, 1)) / n
+
+
+def synthetic_scene(n_spheres=200, n_rects=100, n_cuboids=20, seed=0, extent=6.0):
+    """A many-primitive scene in the reference's wire format: random diffuse / metallic / glass spheres,
+    rects and cuboids inside a box of half-size `extent`, a ground sphere, one emissive sphere light
+    (ObjectFlags::LIGHT) and the camera of scene.json.gz.  Exercises the BVH path."""
+    import json
+    rng = np.random.default_rng(seed)
+    base = O.read_scene_json(O.scene_path("scene"))
+    objs = {"0": base["objects"]["collection"]["0"]}          # camera
+    data = {
+        "0": {"inner": {"Material": {"Flat": {"albedo": {"r": 0.0, "g": 0.0, "b": 0.0}}}}},
+        "1": {"inner": {"Material": {"Emissive": {"albedo": {"r": 1.0, "g": 1.0, "b": 1.0}, "intensity": 0.3}}}},
+        "2": {"inner": {"Material": {"Emissive": {"albedo": {"r": 1.0, "g": 0.9, "b": 0.8}, "intensity": 12.0}}}},
+        "3": {"inner": {"Material": {"Diffuse": {"albedo": {"r": 0.3, "g": 0.4, "b": 0.6}, "roughness": 0.8}}}},
+    }
+    n_mats = 12
+    for m in range(n_mats):
+        a = [float(np.float32(x)) for x in rng.uniform(0.2, 0.9, 3)]
+        alb = {"r": a[0], "g": a[1], "b": a[2]}
+        kind = ["Diffuse", "Diffuse", "Metallic", "Glass"][m % 4]
+        body = {"albedo": alb, "roughness": float(np.float32(rng.uniform(0.0, 0.3)))}
+        if kind == "Glass":
+            body["ior"] = 1.4
+        data[str(4 + m)] = {"inner": {"Material": {kind: body}}}
+
+    def f(x):
+        return float(np.float32(x))
+
+    def obj(key, inner, t, flags=0, m=None):
+        m = m if m is not None else [1, 0, 0, 0, 1, 0, 0, 0, 1]
+        tf = [f(x) for x in m] + [f(x) for x in t]
+        objs[str(key)] = {"object_ref": key, "tag": None, "flags": {"bits": flags},
+                          "transform": {"transform_world": tf, "transform_local": tf, "transform_parent": None},
+                          "inner": inner, "children": None}
+
+    def rot():
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        w, x, y, z = q
+        return [1 - 2 * (y * y + z * z), 2 * (x * y + z * w), 2 * (x * z - y * w),
+                2 * (x * y - z * w), 1 - 2 * (x * x + z * z), 2 * (y * z + x * w),
+                2 * (x * z + y * w), 2 * (y * z - x * w), 1 - 2 * (x * x + y * y)]
+
+    def rect(mat, hw, hh, x=(1, 0, 0), y=(0, 1, 0)):
+        z = np.cross(x, y)
+        return {"material": mat, "half_width": f(hw), "half_height": f(hh), "x": [f(v) for v in x],
+                "y": [f(v) for v in y], "z": [f(v) for v in z]}
+
+    key = 1
+    obj(key, {"Sphere": {"material": 3, "volume": None, "radius": 100.0}}, (0, -101, 0)); key += 1
+    obj(key, {"Sphere": {"material": 2, "volume": None, "radius": 2.0}}, (6, 10, 0), flags=1); key += 1
+    for _ in range(n_spheres):
+        p = rng.uniform(-extent, extent, 3)
+        p[1] = rng.uniform(-0.5, extent)
+        obj(key, {"Sphere": {"material": int(rng.integers(4, 4 + n_mats)), "volume": None,
+                             "radius": f(rng.uniform(0.05, 0.35))}}, p); key += 1
+    for _ in range(n_rects):
+        p = rng.uniform(-extent, extent, 3)
+        p[1] = rng.uniform(-0.5, extent)
+        obj(key, {"Rect": rect(int(rng.integers(4, 4 + n_mats)), rng.uniform(0.1, 0.5), rng.uniform(0.1, 0.5))}, p, m=rot()); key += 1
+    for _ in range(n_cuboids):
+        p = rng.uniform(-extent, extent, 3)
+        p[1] = rng.uniform(-0.5, extent)
+        hx, hy, hz = rng.uniform(0.1, 0.4, 3)
+        mat = int(rng.integers(4, 4 + n_mats))
+        ex, ey, ez = np.eye(3)
+        faces = [[[0, 0, f(-hz)], rect(mat, hx, hy, ex, ey)], [[0, 0, f(hz)], rect(mat, hx, hy, -ex, ey)],
+                 [[f(-hx), 0, 0], rect(mat, hz, hy, ez, ey)], [[f(hx), 0, 0], rect(mat, hz, hy, -ez, ey)],
+                 [[0, f(-hy), 0], rect(mat, hx, hz, ex, ez)], [[0, f(hy), 0], rect(mat, hx, hz, ex, -ez)]]
+        obj(key, {"Cuboid": {"faces": faces}}, p, m=rot()); key += 1
+    scene = {"roots": [], "root_material": 1, "objects": {"collection": objs, "next_key": key},
+             "data": {"collection": data, "next_key": 4 + n_mats}}
+    return json.loads(json.dumps(scene))

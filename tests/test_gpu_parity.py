@@ -296,3 +296,48 @@ def test_full_size_properties():
     assert float((a.data - c.data).abs().max()) <= 1e-3 * float(a.data[..., :3].abs().max())
     m = (a.data[..., :3].mean(dim=(0, 1)) / a.samples()).cpu().numpy()
     assert (m > 0.05).all() and (m < 1.0).all()                      # a lit Cornell box
+
+
+# ---- BVH (scenes above the linear-scan budget) -------------------------------------------------
+@pytest.mark.parametrize("name,lens", [("cornell", None), ("scene", None), ("scene", LENS_SCENE)])
+def test_bvh_equals_linear_scan_on_shipped_scenes(name, lens):
+    """forcing the BVH on a shipped scene must not change a single bit of the image"""
+    w, h = _res(name)
+    _, esc, cam = load_pair(name, w, h, lenses=lens)
+    esc.set_accel("linear")
+    a, _, _ = engine_render(esc, cam, w, h, 2, 2, 0, seed=4)
+    esc.set_accel("bvh")
+    assert esc.info()["n_bvh_nodes"] > 0
+    b, _, _ = engine_render(esc, cam, w, h, 2, 2, 0, seed=4)
+    assert np.array_equal(a, b)
+
+
+def test_bvh_synthetic_scene_vs_oracle(oracle):
+    """a 500-primitive scene: BVH render == linear-scan render bit for bit, and both match the oracle"""
+    import json
+    import bendy_tracer_b200 as bt
+    from common import synthetic_scene
+    scene = synthetic_scene(200, 100, 20, seed=5)          # 2 + 200 + 100 + 120 = 422 flattened primitives
+    w, h = 128, 72
+    osc = O.OracleScene(scene)
+    esc = bt.Scene.from_json(json.dumps(scene))
+    cam = esc.find_by_tag("camera")
+    for s in (osc, esc):
+        s.set_camera_aspect(cam, w / h)
+    info = esc.info()
+    assert info["n_primitives"] == 422 and info["n_bvh_nodes"] > 100      # automatic above 64 primitives
+    ref, n, _ = oracle_render(osc, cam, w, h, 2, 2, 0, seed=6)
+    got, _, _ = engine_render(esc, cam, w, h, 2, 2, 0, seed=6)
+    mae = mae_per_channel(got, ref, n)
+    assert (mae <= IMAGE_MAE).all(), mae
+    esc.set_accel("linear")
+    lin, _, _ = engine_render(esc, cam, w, h, 2, 2, 0, seed=6)
+    assert np.array_equal(lin, got)
+    # first hits agree with the oracle's scan
+    ys, xs = np.mgrid[0:h, 0:w]
+    cfg = O.make_config(samples=1)
+    rays = osc.camera_rays(cam, cfg, w, h, xs.ravel(), ys.ravel(), np.zeros(w * h, np.uint64))
+    r = osc.probe(cfg, rays[:, :3], rays[:, 3:])
+    esc.set_accel("bvh")
+    g = bt.Tracer(bt.Config()).trace_segments(esc, rays[:, :3], rays[:, 3:])
+    assert ((g["face"] == r["face"]) & (g["object_ref"] == r["object_ref"])).mean() >= 0.9995
