@@ -341,3 +341,29 @@ def test_bvh_synthetic_scene_vs_oracle(oracle):
     esc.set_accel("bvh")
     g = bt.Tracer(bt.Config()).trace_segments(esc, rays[:, :3], rays[:, 3:])
     assert ((g["face"] == r["face"]) & (g["object_ref"] == r["object_ref"])).mean() >= 0.9995
+
+
+def test_cli_progressive_render_and_png(tmp_path):
+    """csrc/bendy_b200_cli: 1 pass per iteration until --samples, PNG screenshot == Buffer::preview of the
+    same progressive sequence through the Python mirror"""
+    import os
+    import subprocess
+    from PIL import Image
+    import bendy_tracer_b200 as bt
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "bendy_tracer_b200", "csrc", "bendy_b200_cli")
+    png = tmp_path / "shots" / "render.png"
+    r = subprocess.run([cli, "--output", "full", "--width", "96", "--height", "64", "--samples", "16", "--subsample", "2",
+                        "--scene", O.scene_path("scene"), "--screenshot", str(png), "--seed", "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "16/16 samples" in r.stderr and "saved screenshot" in r.stderr
+    img = np.asarray(Image.open(png))
+    assert img.shape == (64, 96, 4) and (img[..., 3] == 255).all() and img[..., :3].mean() > 10
+    scene = bt.Scene.load(O.scene_path("scene"))
+    cam = scene.find_by_tag("camera")
+    scene.set_camera_aspect(cam, float(np.float32(96) / np.float32(64)))
+    buf = bt.Buffer(96, 64, bt.ColorSpace.SRgb)
+    tracer = bt.Tracer(bt.Config(chunks_x=8, chunks_y=4), seed=3)
+    while buf.samples() < 16:                                      # main.rs:245-254
+        tracer.render(scene, cam, bt.RenderConfig.with_samples_subsample(1, bt.Subsample(2)), buf)
+    assert np.array_equal(buf.preview(), img)

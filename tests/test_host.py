@@ -192,3 +192,21 @@ def test_shard_passes_partition():
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in cuts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_cli_builtin_scene_and_flags(tmp_path):
+    """the headless CLI (csrc/cli.cpp): --output is required (clap), and with no scene file it builds the
+    Cornell box of main.rs:108-213 -- which is exactly what the reference shipped as cornell2.json.gz"""
+    import subprocess
+    cli = os.path.join(ROOT, "bendy_tracer_b200", "csrc", "bendy_b200_cli")
+    r = subprocess.run([cli, "--width", "8"], capture_output=True, text=True)
+    assert r.returncode != 0 and "--output" in r.stderr
+    out = tmp_path / "builtin.json"
+    r = subprocess.run([cli, "--output", "full", "--width", "100", "--height", "100", "--samples", "0",
+                        "--scene", str(tmp_path / "missing.json"), "--save-scene", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert json.load(open(out)) == json.load(gzip.open(O.scene_path("cornell2")))
+    r = subprocess.run([cli, "--output", "normal", "--width", "300", "--height", "200", "--samples", "0",
+                        "--scene", O.scene_path("scene"), "--save-scene", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0 and "loaded scene" in r.stderr
+    assert json.load(open(out))["objects"]["collection"]["0"]["inner"]["Camera"]["aspect_ratio"] == 1.5   # w / h
