@@ -331,6 +331,28 @@ def main():
             scenes[other] = {"workload": describe(other)["workload"], "ms": best,
                              "Msamples_per_s": ow * oh * describe(other)["spp"] / best / 1e3}
             del obuf
+        # ---- synthetic many-primitive scene: the BVH path (global-memory nodes, shared-memory stack) ----
+        import json as _json
+        from common import synthetic_scene
+        syn = bt.Scene.from_json(_json.dumps(synthetic_scene(20000, 6000, 1000, seed=1, extent=14.0)))
+        scam = syn.find_by_tag("camera")
+        sw, sh, sp = 1920, 1080, 4
+        syn.set_camera_aspect(scam, float(np.float32(sw) / np.float32(sh)))
+        sbuf = bt.Buffer(sw, sh, device=dev)
+        src = bt.RenderConfig.with_samples_subsample(sp, bt.Subsample(2))
+        tracer.render(syn, scam, src, sbuf)
+        best = None
+        for i in range(2):
+            sbuf.clear()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            tracer.render(syn, scam, src, sbuf, sample_base=(i + 1) * sp, sync=False)
+            e1.record()
+            torch.cuda.synchronize()
+            best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+        sinfo = syn.info()
+        scenes["S-bvh"] = {"workload": f"synthetic scene, {sinfo['n_primitives']} flattened primitives, {sinfo['n_bvh_nodes']} BVH nodes, "
+                                       f"{sw}x{sh} at {sp * 4} spp", "ms": best, "Msamples_per_s": sw * sh * sp * 4 / best / 1e3}
         result["scenes"] = scenes
         # ---- CPU baseline: the reference algorithm's restatement on this box's host cores ----
         v, cores, n, dt = cpu_sample(name, 4)

@@ -282,6 +282,15 @@ BT_DEV Hit scan_prims(const float4* prims, int n_prims, V3 o, V3 d, float tmin, 
 // (stack[level * blockDim.x + tid]: conflict-free).  Same per-primitive tests as the scan; an
 // exact-distance tie is decided by the canonical primitive index exactly as the reference's
 // scan order would: the later record wins unless it is a cuboid face (strict '<', cuboid.rs:97).
+BT_DEV float slab(float lx, float ly, float lz, float hx, float hy, float hz, V3 o, V3 inv, float tmin, float tmax, bool& hit) {
+    const float tx0 = (lx - o.x) * inv.x, tx1 = (hx - o.x) * inv.x;
+    const float ty0 = (ly - o.y) * inv.y, ty1 = (hy - o.y) * inv.y;
+    const float tz0 = (lz - o.z) * inv.z, tz1 = (hz - o.z) * inv.z;
+    const float tnear = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
+    const float tfar = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tmax));
+    hit = tnear <= tfar * 1.00001f + 1e-6f;  // inclusive and slightly generous: never cull a scan hit
+    return tnear;
+}
 BT_DEV Hit bvh_closest(const float4* __restrict__ prims, const float4* __restrict__ nodes, uint32_t* stack, V3 o, V3 d,
                        float tmin, float tmax) {
     Hit h;
@@ -292,63 +301,67 @@ BT_DEV Hit bvh_closest(const float4* __restrict__ prims, const float4* __restric
     bool best_strict = false;
     const V3 inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     const uint32_t lanes = blockDim.x, tid = threadIdx.x;
-    uint32_t sp = 0, node = 0;
+    float* stack_t = reinterpret_cast<float*>(stack + BVH_STACK * lanes);
+    uint32_t sp = 0, cur = 0;  // node 0 is always an inner node
     for (;;) {
-        const float4 b0 = __ldg(nodes + node * BVH_STRIDE), b1 = __ldg(nodes + node * BVH_STRIDE + 1);
-        // slab test against [tmin, h.t] (inclusive: equal-distance hits must still be visited)
-        const float tx0 = (b0.x - o.x) * inv.x, tx1 = (b1.x - o.x) * inv.x;
-        const float ty0 = (b0.y - o.y) * inv.y, ty1 = (b1.y - o.y) * inv.y;
-        const float tz0 = (b0.z - o.z) * inv.z, tz1 = (b1.z - o.z) * inv.z;
-        const float tnear = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
-        const float tfar = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), h.t));
-        const uint32_t a = __float_as_uint(b0.w), b = __float_as_uint(b1.w);
-        bool descend = false;
-        if (tnear <= tfar * 1.00001f + 1e-6f) {
-            if (b & BVH_LEAF) {
-                const uint32_t count = b & 0x7fffffffu;
-                for (uint32_t i = a; i < a + count; ++i) {
-                    const float4* q = prims + i * PRIM_STRIDE;
-                    const int meta = __float_as_int(__ldg(q + 4).x);
-                    const int type = meta & 3, canon = meta >> 2;
-                    const bool strict = type == PRIM_CUBOID_FACE;
-                    float t;
-                    bool front = true, ok;
-                    if (type == PRIM_SPHERE) {
-                        ok = sphere_roots(__ldg(q), __ldg(q + 1).x, o, d, tmin, h.t, t);
-                    } else {
-                        ok = rect_test(q, o, d, tmin, h.t, false, t, front);
-                    }
-                    if (ok) {
-                        // t <= h.t here.  Equal distance: the later canonical index wins unless strict.
-                        bool take = t < h.t;
-                        if (!take) take = canon > best_canon ? !strict : best_strict;
-                        if (take) {
-                            h.t = t;
-                            h.prim = (int)i;
-                            h.face = type == PRIM_SPHERE ? 8 : (front ? 0 : 1);
-                            best_canon = canon;
-                            best_strict = strict;
-                        }
+        if (cur & BVH_LEAF) {
+            const uint32_t first = cur & 0x00ffffffu, count = (cur >> 24) & 0x7fu;
+            for (uint32_t i = first; i < first + count; ++i) {
+                const float4* q = prims + i * PRIM_STRIDE;
+                const int meta = __float_as_int(__ldg(q + 4).x);
+                const int type = meta & 3, canon = meta >> 2;
+                const bool strict = type == PRIM_CUBOID_FACE;
+                float t;
+                bool front = true, ok;
+                if (type == PRIM_SPHERE)
+                    ok = sphere_roots(__ldg(q), __ldg(q + 1).x, o, d, tmin, h.t, t);
+                else
+                    ok = rect_test(q, o, d, tmin, h.t, false, t, front);
+                if (ok) {
+                    // t <= h.t here.  Equal distance: the later canonical index wins unless strict.
+                    bool take = t < h.t;
+                    if (!take) take = canon > best_canon ? !strict : best_strict;
+                    if (take) {
+                        h.t = t;
+                        h.prim = (int)i;
+                        h.face = type == PRIM_SPHERE ? 8 : (front ? 0 : 1);
+                        best_canon = canon;
+                        best_strict = strict;
                     }
                 }
-            } else {
-                // near child first: the sign of the direction on the split axis
-                const uint32_t right = b & 0x0fffffffu, axis = b >> 28;
-                const float da = axis == 0 ? d.x : (axis == 1 ? d.y : d.z);
-                const uint32_t first = da >= 0.0f ? a : right, second = da >= 0.0f ? right : a;
-                stack[sp * lanes + tid] = second;
-                ++sp;
-                node = first;
-                descend = true;
+            }
+            // pop, skipping subtrees that start beyond the hit found since they were pushed
+            for (;;) {
+                if (sp == 0) return h;
+                --sp;
+                cur = stack[sp * lanes + tid];
+                if (stack_t[sp * lanes + tid] <= h.t) break;
+            }
+            continue;
+        }
+        const float4* n = nodes + cur * BVH_STRIDE;
+        const float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3);
+        bool hl, hr;
+        const float tl = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, tmin, h.t, hl);
+        const float tr = slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, tmin, h.t, hr);
+        const uint32_t left = __float_as_uint(n3.x), right = __float_as_uint(n3.y);
+        if (hl && hr) {
+            const bool left_first = tl <= tr;
+            stack[sp * lanes + tid] = left_first ? right : left;
+            stack_t[sp * lanes + tid] = left_first ? tr : tl;
+            ++sp;
+            cur = left_first ? left : right;
+        } else if (hl || hr) {
+            cur = hl ? left : right;
+        } else {
+            for (;;) {
+                if (sp == 0) return h;
+                --sp;
+                cur = stack[sp * lanes + tid];
+                if (stack_t[sp * lanes + tid] <= h.t) break;
             }
         }
-        if (!descend) {
-            if (sp == 0) break;
-            --sp;
-            node = stack[sp * lanes + tid];
-        }
     }
-    return h;
 }
 
 struct Surface {  // Manifold (ray.rs:36-47) reduced to what shading reads

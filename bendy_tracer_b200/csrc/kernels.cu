@@ -560,7 +560,7 @@ cudaError_t ensure_smem(K kernel, size_t bytes) {
 }  // namespace
 
 size_t render_smem_bytes(const RenderParams& p) {
-    return (size_t)p.scene.stage_f4 * sizeof(float4) + (p.scene.n_bvh ? (size_t)BVH_STACK * 256 * sizeof(uint32_t) : 0);
+    return (size_t)p.scene.stage_f4 * sizeof(float4) + (p.scene.n_bvh ? (size_t)BVH_STACK * 256 * 2 * sizeof(uint32_t) : 0);
 }
 
 // picks <LENS, EXACT, NL, BVH> from the scene header

@@ -21,9 +21,10 @@ enum { PRIM_STRIDE = 5 };
 // and the canonical index decides exact-distance ties the way the reference's scan order does.
 
 // ---- BVH node: BVH_STRIDE float4 (extension: built when a scene exceeds the linear-scan budget)
-//   b0 = (min.xyz, a)  b1 = (max.xyz, b)
-//   inner: a = left child, b = right child | split axis << 28     leaf: a = first record, b = count | 1<<31
-enum { BVH_STRIDE = 2, BVH_LEAF = 0x80000000u, BVH_STACK = 32 };
+//   an inner node holds BOTH child boxes (so a child is only visited when its box is hit):
+//   n0 = (L.min.xyz, L.max.x)  n1 = (L.max.yz, R.min.xy)  n2 = (R.min.z, R.max.xyz)  n3 = (left, right, -, -)
+//   child reference: inner node index, or BVH_LEAF | count << 24 | first record   (count <= 127)
+enum { BVH_STRIDE = 4, BVH_LEAF = 0x80000000u, BVH_STACK = 24 };
 
 // ---- material record: MAT_STRIDE float4 (reference src/scene/data/material.rs:22-44) -------
 //   m0 = (albedo.rgb, kind)   m1 = (roughness, ior, intensity, -)

@@ -811,51 +811,116 @@ void push_rect(std::vector<float4>& blob, std::vector<Bounds>& bounds, const Rec
     blob.push_back(f4(as_f((uint32_t)type | ((uint32_t)(blob.size() / PRIM_STRIDE) << 2)), as_f(mat), area, as_f(obj)));
 }
 
-// ---- BVH: median split on the widest centroid axis, <= 4 primitives per leaf ----------------
+// ---- BVH2: binned-SAH build, <= 4 primitives per leaf; a node stores BOTH child boxes -----
 struct BvhBuild {
     const std::vector<Bounds>& b;
     std::vector<uint32_t> order;   // record position -> canonical primitive index
-    std::vector<float4> nodes;
+    std::vector<float4> nodes;     // BVH_STRIDE float4 per inner node
     explicit BvhBuild(const std::vector<Bounds>& bounds) : b(bounds) {
         for (uint32_t i = 0; i < b.size(); ++i) order.push_back(i);
     }
-    uint32_t build(uint32_t first, uint32_t count, int depth) {
-        Bounds box;
-        float clo[3], chi[3];
-        for (int k = 0; k < 3; ++k) { box.lo[k] = clo[k] = 3.0e38f; box.hi[k] = chi[k] = -3.0e38f; }
-        for (uint32_t i = first; i < first + count; ++i) {
-            const Bounds& p = b[order[i]];
-            for (int k = 0; k < 3; ++k) {
-                box.lo[k] = std::min(box.lo[k], p.lo[k]);
-                box.hi[k] = std::max(box.hi[k], p.hi[k]);
-                float c = 0.5f * (p.lo[k] + p.hi[k]);
-                clo[k] = std::min(clo[k], c);
-                chi[k] = std::max(chi[k], c);
-            }
+    static void grow(Bounds& box, const Bounds& p) {
+        for (int k = 0; k < 3; ++k) {
+            box.lo[k] = std::min(box.lo[k], p.lo[k]);
+            box.hi[k] = std::max(box.hi[k], p.hi[k]);
         }
-        for (int k = 0; k < 3; ++k) {  // conservative padding: the tree must never cull what the scan would hit
+    }
+    static Bounds empty() {
+        Bounds e;
+        for (int k = 0; k < 3; ++k) { e.lo[k] = 3.0e38f; e.hi[k] = -3.0e38f; }
+        return e;
+    }
+    static float area(const Bounds& x) {
+        float d[3] = {x.hi[0] - x.lo[0], x.hi[1] - x.lo[1], x.hi[2] - x.lo[2]};
+        if (d[0] < 0) return 0.0f;
+        return d[0] * d[1] + d[1] * d[2] + d[2] * d[0];
+    }
+    static Bounds padded(Bounds box) {  // conservative: the tree must never cull what the scan would hit
+        for (int k = 0; k < 3; ++k) {
             float pad = 1e-4f * std::max(1.0f, std::max(std::fabs(box.lo[k]), std::fabs(box.hi[k])));
             box.lo[k] -= pad;
             box.hi[k] += pad;
         }
+        return box;
+    }
+    static uint32_t leaf_ref(uint32_t first, uint32_t count) { return BVH_LEAF | (count << 24) | first; }
+    uint32_t make_inner(uint32_t left, const Bounds& lb, uint32_t right, const Bounds& rb) {
         uint32_t self = (uint32_t)(nodes.size() / BVH_STRIDE);
-        nodes.push_back(f4(box.lo[0], box.lo[1], box.lo[2], 0.0f));
-        nodes.push_back(f4(box.hi[0], box.hi[1], box.hi[2], 0.0f));
+        Bounds l = padded(lb), r = padded(rb);
+        nodes.push_back(f4(l.lo[0], l.lo[1], l.lo[2], l.hi[0]));
+        nodes.push_back(f4(l.hi[1], l.hi[2], r.lo[0], r.lo[1]));
+        nodes.push_back(f4(r.lo[2], r.hi[0], r.hi[1], r.hi[2]));
+        nodes.push_back(f4(as_f(left), as_f(right), 0.0f, 0.0f));
+        return self;
+    }
+    // returns a child reference (inner node index, or BVH_LEAF | count << 24 | first) and its box
+    uint32_t build(uint32_t first, uint32_t count, int depth, Bounds* box_out) {
+        Bounds box = empty(), cb = empty();
+        for (uint32_t i = first; i < first + count; ++i) {
+            const Bounds& p = b[order[i]];
+            grow(box, p);
+            Bounds c;
+            for (int k = 0; k < 3; ++k) c.lo[k] = c.hi[k] = 0.5f * (p.lo[k] + p.hi[k]);
+            grow(cb, c);
+        }
+        *box_out = box;
         int axis = 0;
         for (int k = 1; k < 3; ++k)
-            if (chi[k] - clo[k] > chi[axis] - clo[axis]) axis = k;
-        if (count <= 4 || depth >= (int)BVH_STACK - 2 || !(chi[axis] > clo[axis])) {
-            nodes[self * BVH_STRIDE].w = as_f(first);
-            nodes[self * BVH_STRIDE + 1].w = as_f(count | BVH_LEAF);
-            return self;
+            if (cb.hi[k] - cb.lo[k] > cb.hi[axis] - cb.lo[axis]) axis = k;
+        if (count <= 4 || depth >= (int)BVH_STACK - 2 || !(cb.hi[axis] > cb.lo[axis])) {
+            if (count > 127) throw SceneError("BVH: more than 127 coincident primitives in one leaf");
+            return leaf_ref(first, count);
         }
-        uint32_t mid = first + count / 2;
-        std::nth_element(order.begin() + first, order.begin() + mid, order.begin() + first + count,
-                         [&](uint32_t x, uint32_t y) { return b[x].lo[axis] + b[x].hi[axis] < b[y].lo[axis] + b[y].hi[axis]; });
-        uint32_t left = build(first, mid - first, depth + 1);
-        uint32_t right = build(mid, first + count - mid, depth + 1);
-        nodes[self * BVH_STRIDE].w = as_f(left);
-        nodes[self * BVH_STRIDE + 1].w = as_f(right | ((uint32_t)axis << 28));
+        // binned SAH on the widest centroid axis
+        const int NB = 16;
+        Bounds bin_box[NB];
+        uint32_t bin_n[NB];
+        for (int i = 0; i < NB; ++i) { bin_box[i] = empty(); bin_n[i] = 0; }
+        const float scale = (float)NB / (cb.hi[axis] - cb.lo[axis]);
+        auto bin_of = [&](uint32_t prim) {
+            int k = (int)((0.5f * (b[prim].lo[axis] + b[prim].hi[axis]) - cb.lo[axis]) * scale);
+            return std::min(std::max(k, 0), NB - 1);
+        };
+        for (uint32_t i = first; i < first + count; ++i) {
+            int k = bin_of(order[i]);
+            grow(bin_box[k], b[order[i]]);
+            bin_n[k]++;
+        }
+        float right_area[NB];
+        Bounds acc = empty();
+        for (int i = NB - 1; i > 0; --i) {
+            grow(acc, bin_box[i]);
+            right_area[i] = area(acc);
+        }
+        acc = empty();
+        uint32_t nl = 0;
+        int best = -1;
+        float best_cost = 3.0e38f;
+        for (int i = 0; i < NB - 1; ++i) {
+            grow(acc, bin_box[i]);
+            nl += bin_n[i];
+            if (nl == 0 || nl == count) continue;
+            float cost = area(acc) * (float)nl + right_area[i + 1] * (float)(count - nl);
+            if (cost < best_cost) { best_cost = cost; best = i; }
+        }
+        uint32_t mid;
+        if (best >= 0) {
+            mid = (uint32_t)(std::partition(order.begin() + first, order.begin() + first + count,
+                                            [&](uint32_t prim) { return bin_of(prim) <= best; }) - order.begin());
+        } else {
+            mid = first + count / 2;
+            std::nth_element(order.begin() + first, order.begin() + mid, order.begin() + first + count,
+                             [&](uint32_t x, uint32_t y) { return b[x].lo[axis] + b[x].hi[axis] < b[y].lo[axis] + b[y].hi[axis]; });
+        }
+        Bounds lb, rb;
+        uint32_t self = make_inner(0, box, 0, box);  // reserve the slot before the children (root = node 0)
+        uint32_t left = build(first, mid - first, depth + 1, &lb);
+        uint32_t right = build(mid, first + count - mid, depth + 1, &rb);
+        Bounds l = padded(lb), r = padded(rb);
+        nodes[self * BVH_STRIDE] = f4(l.lo[0], l.lo[1], l.lo[2], l.hi[0]);
+        nodes[self * BVH_STRIDE + 1] = f4(l.hi[1], l.hi[2], r.lo[0], r.lo[1]);
+        nodes[self * BVH_STRIDE + 2] = f4(r.lo[2], r.hi[0], r.hi[1], r.hi[2]);
+        nodes[self * BVH_STRIDE + 3] = f4(as_f(left), as_f(right), 0.0f, 0.0f);
         return self;
     }
 };
@@ -1013,7 +1078,34 @@ FlatScene flatten(const Scene& scene, int accel) {
     for (uint32_t i = 0; i < h.n_prims; ++i) fs.prim_order.push_back(i);
     if (use_bvh && h.n_prims > 0) {
         BvhBuild bvh(bounds);
-        bvh.build(0, h.n_prims, 0);
+        // primitives that span a large part of the scene (a ground sphere of radius 100 ...) would
+        // bloat every node they fall into: they go to one leaf beside the tree of the rest
+        std::vector<float> diag(h.n_prims);
+        for (uint32_t i = 0; i < h.n_prims; ++i) {
+            float d2 = 0.0f;
+            for (int k = 0; k < 3; ++k) d2 += (bounds[i].hi[k] - bounds[i].lo[k]) * (bounds[i].hi[k] - bounds[i].lo[k]);
+            diag[i] = std::sqrt(d2);
+        }
+        std::vector<float> sorted_diag(diag);
+        std::nth_element(sorted_diag.begin(), sorted_diag.begin() + sorted_diag.size() / 2, sorted_diag.end());
+        const float big_cut = 16.0f * std::max(sorted_diag[sorted_diag.size() / 2], 1e-6f);
+        uint32_t n_big = (uint32_t)(std::stable_partition(bvh.order.begin(), bvh.order.end(),
+                                                          [&](uint32_t i) { return diag[i] > big_cut; }) - bvh.order.begin());
+        Bounds all = BvhBuild::empty();
+        for (uint32_t i = 0; i < h.n_prims; ++i) BvhBuild::grow(all, bounds[i]);
+        if (n_big == 0 || n_big == h.n_prims) n_big = 0;
+        // node 0 is always an inner node: (left = big-primitive leaf or empty leaf, right = the tree)
+        bvh.make_inner(0, all, 0, all);
+        Bounds rest_box;
+        uint32_t rest = bvh.build(n_big, h.n_prims - n_big, 1, &rest_box);
+        uint32_t big = BvhBuild::leaf_ref(0, n_big);
+        if (n_big > 127) throw SceneError("BVH: more than 127 scene-spanning primitives");
+        Bounds lb = n_big ? all : BvhBuild::empty(), rb = BvhBuild::padded(rest_box);
+        if (n_big) lb = BvhBuild::padded(lb);
+        bvh.nodes[0] = f4(lb.lo[0], lb.lo[1], lb.lo[2], lb.hi[0]);
+        bvh.nodes[1] = f4(lb.hi[1], lb.hi[2], rb.lo[0], rb.lo[1]);
+        bvh.nodes[2] = f4(rb.lo[2], rb.hi[0], rb.hi[1], rb.hi[2]);
+        bvh.nodes[3] = f4(as_f(big), as_f(rest), 0.0f, 0.0f);
         std::vector<float4> sorted(prims.size());
         std::vector<uint32_t> where(h.n_prims);
         for (uint32_t pos = 0; pos < h.n_prims; ++pos) {
