@@ -147,6 +147,10 @@ int build_params(bt_scene* s, uint64_t camera_ref, bool need_camera, const bt_co
     p.clip_min = m.clip_min;
     p.clip_max = m.clip_max;
     p.volume_step = m.volume_step;
+    p.compact_lanes = 8;
+    p.compact_patience = 16;
+    if (const char* e = std::getenv("BT_COMPACT_LANES")) p.compact_lanes = (uint32_t)std::atoi(e);
+    if (const char* e = std::getenv("BT_COMPACT_PATIENCE")) p.compact_patience = (uint32_t)std::atoi(e);
     p.tau_scale = uniform_scale_inclusive(0.0f, 6.28318530717958647692f);
     p.one_scale = uniform_scale_inclusive(0.0f, 1.0f);
     *out = p;

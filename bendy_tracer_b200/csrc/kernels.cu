@@ -50,73 +50,100 @@ struct Traced {
     bool captured;
 };
 
-// One "ray" of the render loop.  Flat field (or inside a volume march): exactly try_hit /
-// try_hit_volume.  Lens field: RK4 chords, each intersected with the same scan (ONE scan call
-// site: the kernel must stay inside the instruction cache).
+// try_hit / try_hit_volume of the reference: one straight segment.
+template <bool BVH>
+BT_DEV Traced trace_straight(const RenderParams& p, const SceneView& sc, V3 o, V3 d, float tmin, float tmax, int vol_obj) {
+    Traced r;
+    if (BVH)
+        r.h = bvh_closest(sc.prims, sc.nodes, sc.stack, o, d, tmin, tmax);
+    else
+        r.h = scan_prims(sc.prims, (int)p.scene.n_prims, o, d, tmin, tmax, vol_obj);
+    r.steps = 0;
+    r.scans = 1;
+    r.captured = false;
+    r.o = o;
+    r.d = d;
+    r.t_total = r.h.t;
+    return r;
+}
+
+// A geodesic in flight: the state a lane carries between steps (x, v live in the caller's o, d).
+struct Flight {
+    float travelled;
+    uint32_t steps, scans;
+};
+// ONE RK4 step of a bent ray + the intersection of its chord.  Returns true when the segment is
+// resolved (hit, escape, capture; `r` filled), false when the ray flies on (x, v, f advanced).
+template <bool EXACT, bool BVH, class L>
+BT_DEV bool geodesic_advance(const RenderParams& p, const SceneView& sc, const L& lens, V3& x, V3& v, Flight& f, float tmin,
+                             float tmax, Traced& r) {
+    float rmin;
+    bool captured, far;
+    D0Cache<L> cache;
+    const V3 k1 = lens_accel<2, EXACT, 0>(lens, cache, x, 0.0f, v, v, rmin, captured, far);
+    r.captured = false;
+    if (captured) {
+        r.captured = true;
+        r.h.prim = -1;
+        r.h.t = 0.0f;
+        r.h.face = 0;
+        r.o = x;
+        r.d = v;
+        r.t_total = f.travelled;
+        r.steps = f.steps;
+        r.scans = f.scans;
+        return true;
+    }
+    const float remaining = tmax - f.travelled;
+    const float cmin = fmaxf(tmin - f.travelled, 0.0f);
+    V3 dir, x1 = x, v1 = v;
+    float len = 0.0f, cmax = remaining;
+    if (far) {  // beyond r_far of every mass and receding: one straight segment to clip_max
+        dir = normalize_fma(v, 0);
+    } else {
+        rk4_from_k1<EXACT>(lens, cache, x1, v1, k1, step_size(p.scene.kappa, p.scene.h_min, p.scene.h_max, rmin));
+        dir = normalize_fma(x1 - x, &len);
+        cmax = fminf(len, remaining);
+    }
+    if (BVH)
+        r.h = bvh_closest(sc.prims, sc.nodes, sc.stack, x, dir, cmin, cmax);
+    else
+        r.h = scan_prims(sc.prims, (int)p.scene.n_prims, x, dir, cmin, cmax, -1);
+    f.scans++;
+    if (r.h.prim >= 0 || far) {
+        r.o = x;
+        r.d = dir;
+        r.t_total = f.travelled + r.h.t;
+        r.steps = f.steps;
+        r.scans = f.scans;
+        return true;
+    }
+    f.travelled += len;
+    x = x1;
+    v = v1;
+    f.steps++;
+    if (f.travelled >= tmax || f.steps >= p.scene.max_steps) {
+        r.o = x;
+        r.d = normalize_fma(v, 0);
+        r.t_total = f.travelled;
+        r.steps = f.steps;
+        r.scans = f.scans;
+        return true;
+    }
+    return false;
+}
+
+// One "ray" of the render loop, start to end (the probe kernel; the render kernel interleaves the
+// steps of its 32 lanes instead, see render_body).
 template <bool LENS, bool EXACT, bool BVH, class L>
 BT_DEV Traced trace_ray(const RenderParams& p, const SceneView& sc, const L& lens, V3 o, V3 d, float tmin, float tmax, int vol_obj) {
+    if (!LENS || vol_obj >= 0) return trace_straight<BVH>(p, sc, o, d, tmin, tmax, vol_obj);
     Traced r;
-    r.steps = 0;
-    r.scans = 0;
-    r.captured = false;
-    const int n_prims = (int)p.scene.n_prims;
-    const bool bent = LENS && vol_obj < 0;
-    V3 x = o, v = d;
-    float travelled = 0.0f;
+    Flight f = {0.0f, 0u, 0u};
 #pragma unroll 1
-    for (;;) {
-        V3 dir = d, x1 = x, v1 = v;
-        float cmin = tmin, cmax = tmax, len = 0.0f;
-        bool last = true;
-        if (bent) {
-            float rmin;
-            bool captured, far;
-            D0Cache<L> cache;
-            const V3 k1 = lens_accel<2, EXACT, 0>(lens, cache, x, 0.0f, v, v, rmin, captured, far);
-            if (captured) {
-                r.captured = true;
-                r.h.prim = -1;
-                r.h.t = 0.0f;
-                r.h.face = 0;
-                r.o = x;
-                r.d = v;
-                r.t_total = travelled;
-                return r;
-            }
-            const float remaining = tmax - travelled;
-            cmin = fmaxf(tmin - travelled, 0.0f);
-            if (far) {
-                dir = normalize_fma(v, 0);
-                cmax = remaining;
-            } else {
-                rk4_from_k1<EXACT>(lens, cache, x1, v1, k1, step_size(p.scene.kappa, p.scene.h_min, p.scene.h_max, rmin));
-                dir = normalize_fma(x1 - x, &len);
-                cmax = fminf(len, remaining);
-                last = false;
-            }
-        }
-        if (BVH)
-            r.h = bvh_closest(sc.prims, sc.nodes, sc.stack, x, dir, cmin, cmax);
-        else
-            r.h = scan_prims(sc.prims, n_prims, x, dir, cmin, cmax, vol_obj);
-        r.scans++;
-        if (r.h.prim >= 0 || last) {
-            r.o = x;
-            r.d = dir;
-            r.t_total = travelled + r.h.t;
-            return r;
-        }
-        travelled += len;
-        x = x1;
-        v = v1;
-        r.steps++;
-        if (travelled >= tmax || r.steps >= p.scene.max_steps) {
-            r.o = x;
-            r.d = normalize_fma(v, 0);
-            r.t_total = travelled;
-            return r;
-        }
+    while (!geodesic_advance<EXACT, BVH>(p, sc, lens, o, d, f, tmin, tmax, r)) {
     }
+    return r;
 }
 
 // NL: 0 = lens table walked in shared memory, N > 0 = exactly N masses held in registers
@@ -170,6 +197,7 @@ BT_DEV void render_body(const RenderParams& p) {
     V3 o, d, T;
     uint32_t bounce = 0, vb = 0;
     int vol_obj = -1;
+    Flight fl = {0.0f, 0u, 0u};  // LENS: the geodesic this lane is flying (x, v alias o, d)
     bool latched = false;
     V3 aov_albedo, aov_normal;
     float aov_depth = inf;
@@ -184,6 +212,8 @@ BT_DEV void render_body(const RenderParams& p) {
                 bounce = 0;
                 vb = 0;
                 vol_obj = -1;
+                fl.travelled = 0.0f;
+                fl.steps = fl.scans = 0;
                 latched = false;
                 aov_albedo = v3(0.0f, 0.0f, 0.0f);
                 aov_normal = v3(0.0f, 0.0f, 0.0f);
@@ -208,9 +238,28 @@ BT_DEV void render_body(const RenderParams& p) {
         bool vol_scatter = false;
         const bool in_volume = vol_obj >= 0;
 
-        if (alive) {
-            const Traced tr = trace_ray<LENS, EXACT, BVH>(p, sc, lens, o, d, in_volume ? 0.0f : p.clip_min,
-                                                     in_volume ? p.volume_step : p.clip_max, vol_obj);
+        // Per-warp step compaction: a bent ray is NOT traced to its end here.  Every lane in flight
+        // takes one RK4 step (+ chord scan) per turn of the loop below; the warp leaves the loop to
+        // shade / regenerate as soon as enough lanes hold a resolved segment, and the lanes still in
+        // flight simply resume next time.  Lanes therefore never idle through another lane's long orbit.
+        Traced tr;
+        bool has_event = false;
+        if (alive && (!LENS || in_volume)) {
+            tr = trace_straight<BVH>(p, sc, o, d, in_volume ? 0.0f : p.clip_min, in_volume ? p.volume_step : p.clip_max, vol_obj);
+            has_event = true;
+        }
+        if (LENS) {
+            const uint32_t patience = __any_sync(0xffffffffu, has_event) ? 4u : p.compact_patience;  // straight (volume-march) lanes wait less
+            uint32_t waited = 0;
+            for (;;) {
+                if (alive && !has_event) has_event = geodesic_advance<EXACT, BVH>(p, sc, lens, o, d, fl, p.clip_min, p.clip_max, tr);
+                const unsigned flying = __ballot_sync(0xffffffffu, alive && !has_event);
+                const unsigned waiting = __ballot_sync(0xffffffffu, alive && has_event);
+                if (flying == 0) break;
+                if (waiting != 0 && ((uint32_t)__popc(waiting) >= p.compact_lanes || ++waited >= patience)) break;
+            }
+        }
+        if (alive && has_event) {
             din = tr.d;
             hit_t = tr.t_total;
             if (STATS) {
@@ -323,6 +372,8 @@ BT_DEV void render_body(const RenderParams& p) {
 
         // ---- 3. the scattered ray ------------------------------------------------------------
         if (ev != EV_TERMINAL) {
+            fl.travelled = 0.0f;  // the scattered ray starts a new flight
+            fl.steps = fl.scans = 0;
             V3 dirvec = vec;  // Cosine, volume scatter
             if (ev == EV_DIFFUSE && sk != SK_COSINE) {  // Pdf::Light: random_point(light) - origin
                 V3 point = v3(light[1]);                                        // POINT: the translation

@@ -93,6 +93,7 @@ struct RenderParams {
     uint32_t max_bounces, max_volume_bounces;
     float clip_min, clip_max, volume_step;
     float tau_scale, one_scale;      // Uniform::new_inclusive(0, TAU).scale, (0, 1).scale
+    uint32_t compact_lanes, compact_patience;  // per-warp step compaction thresholds (LENS kernels)
     unsigned long long* stats;       // render_kernel_stats only: {paths, scan calls, RK4 steps, events}
 };
 
