@@ -127,10 +127,11 @@ class LensConfig:
     r_far: float = 500.0
     max_steps: int = 4096
     exact_rsqrt: bool = False   # BT_LENS_EXACT_RSQRT: bit-identical to the CPU oracle, slower
+    no_skip: bool = False       # BT_LENS_NO_SKIP: intersect every chord (the oracle's literal loop)
 
     def _c(self):
         return _ffi.BtLensConfig(self.kappa, self.h_min, self.h_max, self.r_far, self.max_steps,
-                                 1 if self.exact_rsqrt else 0)
+                                 (1 if self.exact_rsqrt else 0) | (2 if self.no_skip else 0))
 
 
 class Engine:

@@ -199,12 +199,11 @@ BT_DEV float sdiv(float p, float q) { return __fdividef(p, q); }
 #endif
 
 // Sphere::hit roots (sphere.rs:121-148).  Returns true and the accepted root.
-BT_DEV bool sphere_roots(float4 q0, float r2, V3 o, V3 d, float tmin, float tmax, float& t_out) {
+BT_DEV bool sphere_roots_oc(V3 oc, float l2, float r2, V3 d, float tmin, float tmax, float& t_out) {
     // always the reference's rounding: |oc|^2 - r^2 cancels catastrophically for large spheres, and
     // a 1e-5 shift of a volume entry point flips Bernoulli scatter decisions at a visible rate
-    V3 oc = o - v3(q0);
     float half_b = dot(oc, d);
-    float c = dot(oc, oc) - r2;
+    float c = l2 - r2;
     float disc = half_b * half_b - c;
     if (signbit(disc)) return false;  // most rays miss most spheres: a (mostly warp-uniform) early-out
     float sqrtd = sqrtf(disc);
@@ -212,6 +211,15 @@ BT_DEV bool sphere_roots(float4 q0, float r2, V3 o, V3 d, float tmin, float tmax
     bool in0 = !(t0 < tmin || t0 > tmax), in1 = !(t1 < tmin || t1 > tmax);
     t_out = in0 ? t0 : t1;
     return in0 || in1;
+}
+BT_DEV bool sphere_roots(float4 q0, float r2, V3 o, V3 d, float tmin, float tmax, float& t_out) {
+    V3 oc = o - v3(q0);
+    return sphere_roots_oc(oc, dot(oc, oc), r2, d, tmin, tmax, t_out);
+}
+BT_DEV float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 // Rect::hit (rect.rs:110-155) on a pre-transformed record.  strict: Cuboid::hit's `t < best`.
 BT_DEV bool rect_test(const float4* q, V3 o, V3 d, float tmin, float tmax, bool strict, float& t_out, bool& front) {
@@ -237,11 +245,18 @@ BT_DEV bool rect_test(const float4* q, V3 o, V3 d, float tmin, float tmax, bool 
 
 // ChunkState::try_hit / try_hit_volume (mod.rs:389-427): linear scan in canonical object order
 // with a shrinking clip.max.  volume_obj >= 0 selects hit_volumetric for that object's sphere.
-BT_DEV Hit scan_prims(const float4* prims, int n_prims, V3 o, V3 d, float tmin, float tmax, int volume_obj) {
+// DIST: the same pass also returns a conservative lower bound on the distance from `o` to the
+// nearest primitive surface (spheres: ||o - c| - r|; rects: L-infinity distance to the world
+// AABB), minus a margin that covers the rounding of the hit tests themselves -- a ray that starts
+// at `o` cannot be reported as hitting anything within that distance (the stepper's chord skip).
+template <bool DIST>
+BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, int n_prims, V3 o, V3 d, float tmin, float tmax,
+                        int volume_obj, float* free_out) {
     Hit h;
     h.t = tmax;
     h.prim = -1;
     h.face = 0;
+    float free = __int_as_float(0x7f800000);
     for (int i = 0; i < n_prims; ++i) {
         const float4* q = prims + i * PRIM_STRIDE;
         float4 meta = q[4];
@@ -259,7 +274,15 @@ BT_DEV Hit scan_prims(const float4* prims, int n_prims, V3 o, V3 d, float tmin, 
                 }
             }
             float t;
-            if (sphere_roots(q0, r2, o, d, tmin, h.t, t)) {
+            const V3 oc = o - v3(q0);
+            const float l2 = dot(oc, oc);
+            if (DIST) {
+                // the root test may place a grazing hit up to sqrt(3 ulp(|oc|^2)) ~ 6e-4 |oc| away from
+                // the true surface: 1e-3 (|oc| + r) covers it and the approximate square root
+                const float dc = sqrt_approx(l2);
+                free = fminf(free, fabsf(dc - q0.w) - 1e-3f * (dc + q0.w));
+            }
+            if (sphere_roots_oc(oc, l2, r2, d, tmin, h.t, t)) {
                 h.t = t;
                 h.prim = i;
                 h.face = 8;  // resolved after the scan (needs the normal)
@@ -267,6 +290,12 @@ BT_DEV Hit scan_prims(const float4* prims, int n_prims, V3 o, V3 d, float tmin, 
         } else {
             float t;
             bool front;
+            if (DIST) {
+                const float4 lo = bounds[i * BOUND_STRIDE], hi = bounds[i * BOUND_STRIDE + 1];
+                const float dx = fmaxf(lo.x - o.x, o.x - hi.x), dy = fmaxf(lo.y - o.y, o.y - hi.y), dz = fmaxf(lo.z - o.z, o.z - hi.z);
+                const float m = 1e-4f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + fabsf(hi.x - lo.x) + fabsf(hi.y - lo.y) + fabsf(hi.z - lo.z)) + 1e-4f;
+                free = fminf(free, fmaxf(fmaxf(dx, dy), dz) - m);
+            }
             if (rect_test(q, o, d, tmin, h.t, type == PRIM_CUBOID_FACE, t, front)) {
                 h.t = t;
                 h.prim = i;
@@ -274,7 +303,11 @@ BT_DEV Hit scan_prims(const float4* prims, int n_prims, V3 o, V3 d, float tmin, 
             }
         }
     }
+    if (DIST) *free_out = free;
     return h;
+}
+BT_DEV Hit scan_prims(const float4* prims, int n_prims, V3 o, V3 d, float tmin, float tmax, int volume_obj) {
+    return scan_prims_t<false>(prims, nullptr, n_prims, o, d, tmin, tmax, volume_obj, nullptr);
 }
 
 // Closest hit through the BVH (extension; scenes above the linear-scan budget).  Records and
@@ -633,9 +666,12 @@ BT_DEV void rk4_from_k1(const L& lens, D0Cache<L>& cache, V3& x, V3& v, V3 k1, f
     v = axpy(h6, sk, v);
 }
 BT_DEV float step_size(float kappa, float h_min, float h_max, float rmin) { return fminf(fmaxf(kappa * rmin, h_min), h_max); }
+// chord direction and length.  EXACT: IEEE square root and reciprocal (the oracle's values);
+// otherwise one MUFU.RSQ (<= 2 ulp), like the stepper's own 1/|d|.
+template <bool EXACT>
 BT_DEV V3 normalize_fma(V3 a, float* len_out) {
     float l2 = fmaf(a.z, a.z, fmaf(a.y, a.y, a.x * a.x));
-    float inv = 1.0f / sqrtf(l2);
+    float inv = EXACT ? 1.0f / sqrtf(l2) : rsqrt_approx(l2);
     if (len_out) *len_out = l2 * inv;
     return a * inv;
 }

@@ -151,6 +151,11 @@ int build_params(bt_scene* s, uint64_t camera_ref, bool need_camera, const bt_co
     p.compact_patience = 16;
     if (const char* e = std::getenv("BT_COMPACT_LANES")) p.compact_lanes = (uint32_t)std::atoi(e);
     if (const char* e = std::getenv("BT_COMPACT_PATIENCE")) p.compact_patience = (uint32_t)std::atoi(e);
+    p.scan_lanes = 12;
+    p.scan_patience = 4;
+    if (const char* e = std::getenv("BT_SCAN_LANES")) p.scan_lanes = (uint32_t)std::atoi(e);
+    if (const char* e = std::getenv("BT_SCAN_PATIENCE")) p.scan_patience = (uint32_t)std::atoi(e);
+    if (std::getenv("BT_LENS_NO_SKIP")) p.scene.lens_skip = 0;
     p.tau_scale = uniform_scale_inclusive(0.0f, 6.28318530717958647692f);
     p.one_scale = uniform_scale_inclusive(0.0f, 1.0f);
     *out = p;

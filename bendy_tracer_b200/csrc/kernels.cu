@@ -6,6 +6,8 @@
 // with in-register path regeneration").  Path state lives in registers, the scene blob in shared
 // memory; HBM traffic is one float4 read-modify-write per pixel per call (buffer.rs:159-178).
 // Pixel sums are formed in the reference's order, so the result is deterministic.
+#include <cstdlib>
+
 #include "device.cuh"
 #include "kernels.h"
 
@@ -21,6 +23,7 @@ struct SceneView {
     const float4* lights;
     const float4* vols;
     const float4* lens;
+    const float4* bounds;  // per-primitive AABBs (lensed scan scenes)
     const float* grids;
 };
 
@@ -37,6 +40,7 @@ BT_DEV SceneView stage_scene(const RenderParams& p, float4* smem) {
     s.lights = smem + (p.scene.light_off - base);
     s.vols = smem + (p.scene.vol_off - base);
     s.lens = smem + (p.scene.lens_off - base);
+    s.bounds = smem + (p.scene.bound_off - base);
     s.grids = p.grids;
     return s;
 }
@@ -68,82 +72,111 @@ BT_DEV Traced trace_straight(const RenderParams& p, const SceneView& sc, V3 o, V
 }
 
 // A geodesic in flight: the state a lane carries between steps (x, v live in the caller's o, d).
+// Nothing else is written inside the flight loop: the event a resolved flight hands to shading is
+// rebuilt from this state afterwards (flight_result), which keeps the loop free of merge copies.
 struct Flight {
     float travelled;
     uint32_t steps, scans;
+    float free;  // no primitive surface lies within this distance of x (<= 0: unknown)
+    V3 xp;       // start of the last chord xp -> x that needed / needs an intersection test
+    Hit h;       // FL_HIT / FL_HIT_FAR: the hit on that chord (t relative to its start)
 };
-// ONE RK4 step of a bent ray + the intersection of its chord.  Returns true when the segment is
-// resolved (hit, escape, capture; `r` filled), false when the ray flies on (x, v, f advanced).
-template <bool EXACT, bool BVH, class L>
-BT_DEV bool geodesic_advance(const RenderParams& p, const SceneView& sc, const L& lens, V3& x, V3& v, Flight& f, float tmin,
-                             float tmax, Traced& r) {
+// Lane states.  In flight: FL_FLY ready for the next RK4 step; FL_PEND the step is taken (x, v
+// advanced) but its chord awaits the intersection phase; FL_PEND_FAR beyond r_far of every mass and
+// receding -- the rest of the ray is one straight segment.  Resolved (bit 2): FL_HIT on the chord,
+// FL_HIT_FAR on the final straight segment, FL_ESCAPED, FL_CAPTURED.  Not a flight (bit 3): FL_IDLE
+// (no path), FL_STRAIGHT (a straight segment traced by try_hit / try_hit_volume, event ready).
+enum { FL_FLY = 0, FL_PEND = 1, FL_PEND_FAR = 2, FL_HIT = 4, FL_HIT_FAR = 5, FL_ESCAPED = 6, FL_CAPTURED = 7, FL_IDLE = 8,
+       FL_STRAIGHT = 12 };
+
+BT_DEV void flight_reset(Flight& f) {
+    f.travelled = 0.0f;
+    f.steps = f.scans = 0;
+    f.free = 0.0f;
+    f.xp = v3(0.0f, 0.0f, 0.0f);
+    f.h.t = 0.0f;
+    f.h.prim = -1;
+    f.h.face = 0;
+}
+// STEP phase: one RK4 step of a bent ray.  A chord shorter than the free distance cannot touch
+// anything and is committed at once; otherwise it is left pending for the intersection phase.
+template <bool EXACT, class L>
+BT_DEV int geodesic_step(const RenderParams& p, const L& lens, V3& x, V3& v, Flight& f, float tmax) {
     float rmin;
     bool captured, far;
     D0Cache<L> cache;
     const V3 k1 = lens_accel<2, EXACT, 0>(lens, cache, x, 0.0f, v, v, rmin, captured, far);
-    r.captured = false;
-    if (captured) {
-        r.captured = true;
-        r.h.prim = -1;
-        r.h.t = 0.0f;
-        r.h.face = 0;
-        r.o = x;
-        r.d = v;
-        r.t_total = f.travelled;
-        r.steps = f.steps;
-        r.scans = f.scans;
-        return true;
+    if (captured) return FL_CAPTURED;
+    if (far) return FL_PEND_FAR;
+    const V3 x0 = x;
+    rk4_from_k1<EXACT>(lens, cache, x, v, k1, step_size(p.scene.kappa, p.scene.h_min, p.scene.h_max, rmin));
+    float len;
+    (void)normalize_fma<EXACT>(x - x0, &len);
+    if (len * 1.02f < f.free) {  // nothing within reach: the chord needs no intersection test
+        f.free -= len;
+        f.travelled += len;
+        f.steps++;
+        return (f.travelled >= tmax || f.steps >= p.scene.max_steps) ? FL_ESCAPED : FL_FLY;
     }
+    f.xp = x0;
+    return FL_PEND;
+}
+// INTERSECTION phase: the pending chord (or the final straight segment) against the scene; the
+// same pass refreshes the free distance.  Returns a resolved state or FL_FLY.
+template <bool EXACT, bool BVH>
+BT_DEV int geodesic_scan(const RenderParams& p, const SceneView& sc, V3 x, V3 v, Flight& f, int state, float tmin, float tmax) {
+    const bool far = state == FL_PEND_FAR;
     const float remaining = tmax - f.travelled;
     const float cmin = fmaxf(tmin - f.travelled, 0.0f);
-    V3 dir, x1 = x, v1 = v;
-    float len = 0.0f, cmax = remaining;
-    if (far) {  // beyond r_far of every mass and receding: one straight segment to clip_max
-        dir = normalize_fma(v, 0);
-    } else {
-        rk4_from_k1<EXACT>(lens, cache, x1, v1, k1, step_size(p.scene.kappa, p.scene.h_min, p.scene.h_max, rmin));
-        dir = normalize_fma(x1 - x, &len);
-        cmax = fminf(len, remaining);
-    }
+    const V3 o = far ? x : f.xp;
+    float len;
+    const V3 dir = normalize_fma<EXACT>(far ? v : x - f.xp, &len);
+    const float cmax = far ? remaining : fminf(len, remaining);
+    float bound = 0.0f;
     if (BVH)
-        r.h = bvh_closest(sc.prims, sc.nodes, sc.stack, x, dir, cmin, cmax);
+        f.h = bvh_closest(sc.prims, sc.nodes, sc.stack, o, dir, cmin, cmax);
+    else if (p.scene.lens_skip)
+        f.h = scan_prims_t<true>(sc.prims, sc.bounds, (int)p.scene.n_prims, o, dir, cmin, cmax, -1, &bound);
     else
-        r.h = scan_prims(sc.prims, (int)p.scene.n_prims, x, dir, cmin, cmax, -1);
+        f.h = scan_prims(sc.prims, (int)p.scene.n_prims, o, dir, cmin, cmax, -1);
     f.scans++;
-    if (r.h.prim >= 0 || far) {
-        r.o = x;
-        r.d = dir;
-        r.t_total = f.travelled + r.h.t;
-        r.steps = f.steps;
-        r.scans = f.scans;
-        return true;
-    }
+    if (f.h.prim >= 0) return far ? FL_HIT_FAR : FL_HIT;
+    if (far) return FL_ESCAPED;
     f.travelled += len;
-    x = x1;
-    v = v1;
     f.steps++;
-    if (f.travelled >= tmax || f.steps >= p.scene.max_steps) {
-        r.o = x;
-        r.d = normalize_fma(v, 0);
-        r.t_total = f.travelled;
-        r.steps = f.steps;
-        r.scans = f.scans;
-        return true;
-    }
-    return false;
+    f.free = bound - len;  // the bound was taken at the chord's start
+    return (f.travelled >= tmax || f.steps >= p.scene.max_steps) ? FL_ESCAPED : FL_FLY;
+}
+// the event of a resolved flight
+template <bool EXACT>
+BT_DEV Traced flight_result(int state, V3 x, V3 v, const Flight& f) {
+    Traced r;
+    const bool chord = state == FL_HIT;
+    r.o = chord ? f.xp : x;
+    r.d = normalize_fma<EXACT>(chord ? x - f.xp : v, 0);
+    r.h = f.h;
+    if (state >= FL_ESCAPED) r.h.prim = -1;
+    r.captured = state == FL_CAPTURED;
+    r.t_total = f.travelled + f.h.t;
+    r.steps = f.steps;
+    r.scans = f.scans;
+    return r;
 }
 
 // One "ray" of the render loop, start to end (the probe kernel; the render kernel interleaves the
-// steps of its 32 lanes instead, see render_body).
+// phases of its 32 lanes instead, see render_body).
 template <bool LENS, bool EXACT, bool BVH, class L>
 BT_DEV Traced trace_ray(const RenderParams& p, const SceneView& sc, const L& lens, V3 o, V3 d, float tmin, float tmax, int vol_obj) {
     if (!LENS || vol_obj >= 0) return trace_straight<BVH>(p, sc, o, d, tmin, tmax, vol_obj);
-    Traced r;
-    Flight f = {0.0f, 0u, 0u};
+    Flight f;
+    flight_reset(f);
+    int st = FL_FLY;
 #pragma unroll 1
-    while (!geodesic_advance<EXACT, BVH>(p, sc, lens, o, d, f, tmin, tmax, r)) {
+    while (st < FL_HIT) {
+        st = geodesic_step<EXACT>(p, lens, o, d, f, tmax);
+        if (st == FL_PEND || st == FL_PEND_FAR) st = geodesic_scan<EXACT, BVH>(p, sc, o, d, f, st, tmin, tmax);
     }
-    return r;
+    return flight_result<EXACT>(st, o, d, f);
 }
 
 // NL: 0 = lens table walked in shared memory, N > 0 = exactly N masses held in registers
@@ -197,7 +230,9 @@ BT_DEV void render_body(const RenderParams& p) {
     V3 o, d, T;
     uint32_t bounce = 0, vb = 0;
     int vol_obj = -1;
-    Flight fl = {0.0f, 0u, 0u};  // LENS: the geodesic this lane is flying (x, v alias o, d)
+    Flight fl;  // LENS: the geodesic this lane is flying (x, v alias o, d)
+    flight_reset(fl);
+    int fstate = FL_FLY;
     bool latched = false;
     V3 aov_albedo, aov_normal;
     float aov_depth = inf;
@@ -212,8 +247,8 @@ BT_DEV void render_body(const RenderParams& p) {
                 bounce = 0;
                 vb = 0;
                 vol_obj = -1;
-                fl.travelled = 0.0f;
-                fl.steps = fl.scans = 0;
+                flight_reset(fl);
+                fstate = FL_FLY;
                 latched = false;
                 aov_albedo = v3(0.0f, 0.0f, 0.0f);
                 aov_normal = v3(0.0f, 0.0f, 0.0f);
@@ -238,10 +273,13 @@ BT_DEV void render_body(const RenderParams& p) {
         bool vol_scatter = false;
         const bool in_volume = vol_obj >= 0;
 
-        // Per-warp step compaction: a bent ray is NOT traced to its end here.  Every lane in flight
-        // takes one RK4 step (+ chord scan) per turn of the loop below; the warp leaves the loop to
-        // shade / regenerate as soon as enough lanes hold a resolved segment, and the lanes still in
-        // flight simply resume next time.  Lanes therefore never idle through another lane's long orbit.
+        // Per-warp phase compaction: a bent ray is NOT traced to its end here.  Lanes in flight are
+        // in one of two phases -- STEP (an RK4 step; chords shorter than the free distance commit at
+        // once) or INTERSECT (a pending chord against the scene).  Every turn of the loop below runs
+        // the STEP phase for the lanes that can step, and the INTERSECT phase only once enough lanes
+        // have a chord pending (ballot / popc), so the expensive scan runs with a well-filled warp.
+        // The warp leaves the loop to shade / regenerate as soon as enough lanes hold a resolved
+        // segment; lanes still in flight keep their phase and resume next time.
         Traced tr;
         bool has_event = false;
         if (alive && (!LENS || in_volume)) {
@@ -249,14 +287,31 @@ BT_DEV void render_body(const RenderParams& p) {
             has_event = true;
         }
         if (LENS) {
-            const uint32_t patience = __any_sync(0xffffffffu, has_event) ? 4u : p.compact_patience;  // straight (volume-march) lanes wait less
-            uint32_t waited = 0;
+            int ls = !alive ? FL_IDLE : (in_volume ? FL_STRAIGHT : fstate);
+            const uint32_t patience = __any_sync(0xffffffffu, ls == FL_STRAIGHT) ? 4u : p.compact_patience;  // straight (volume-march) lanes wait less
+            uint32_t waited = 0, scan_waited = 0;
+#pragma unroll 1
             for (;;) {
-                if (alive && !has_event) has_event = geodesic_advance<EXACT, BVH>(p, sc, lens, o, d, fl, p.clip_min, p.clip_max, tr);
-                const unsigned flying = __ballot_sync(0xffffffffu, alive && !has_event);
-                const unsigned waiting = __ballot_sync(0xffffffffu, alive && has_event);
-                if (flying == 0) break;
+                if (ls == FL_FLY) ls = geodesic_step<EXACT>(p, lens, o, d, fl, p.clip_max);
+                const bool pend = ls == FL_PEND || ls == FL_PEND_FAR;
+                unsigned m_pend = __ballot_sync(0xffffffffu, pend);
+                unsigned m_fly = __ballot_sync(0xffffffffu, ls == FL_FLY);
+                if (m_pend != 0 && (m_fly == 0 || (uint32_t)__popc(m_pend) >= p.scan_lanes || ++scan_waited >= p.scan_patience)) {
+                    scan_waited = 0;
+                    if (pend) ls = geodesic_scan<EXACT, BVH>(p, sc, o, d, fl, ls, p.clip_min, p.clip_max);
+                    m_pend = 0;
+                    m_fly = __ballot_sync(0xffffffffu, ls == FL_FLY);
+                }
+                if ((m_fly | m_pend) == 0) break;
+                const unsigned waiting = __ballot_sync(0xffffffffu, (ls & 4) != 0);
                 if (waiting != 0 && ((uint32_t)__popc(waiting) >= p.compact_lanes || ++waited >= patience)) break;
+            }
+            if (ls < FL_IDLE) {
+                fstate = ls;
+                if (ls >= FL_HIT) {
+                    tr = flight_result<EXACT>(ls, o, d, fl);
+                    has_event = true;
+                }
             }
         }
         if (alive && has_event) {
@@ -372,8 +427,8 @@ BT_DEV void render_body(const RenderParams& p) {
 
         // ---- 3. the scattered ray ------------------------------------------------------------
         if (ev != EV_TERMINAL) {
-            fl.travelled = 0.0f;  // the scattered ray starts a new flight
-            fl.steps = fl.scans = 0;
+            flight_reset(fl);  // the scattered ray starts a new flight
+            fstate = FL_FLY;
             V3 dirvec = vec;  // Cosine, volume scatter
             if (ev == EV_DIFFUSE && sk != SK_COSINE) {  // Pdf::Light: random_point(light) - origin
                 V3 point = v3(light[1]);                                        // POINT: the translation
@@ -473,6 +528,11 @@ BT_DEV void render_body(const RenderParams& p) {
 
 template <bool LENS, bool EXACT, int NL, bool BVH>
 __global__ void __launch_bounds__(256, 3) render_kernel(const __grid_constant__ RenderParams p) {
+    render_body<false, LENS, EXACT, NL, BVH>(p);
+}
+// experiment: the lensed kernels with 2 CTAs / SM (128 registers, no spills)
+template <bool LENS, bool EXACT, int NL, bool BVH>
+__global__ void __launch_bounds__(256, 2) render_kernel_wide(const __grid_constant__ RenderParams p) {
     render_body<false, LENS, EXACT, NL, BVH>(p);
 }
 // the same kernel + work counters for bench.py's roofline accounting (never timed)
@@ -635,8 +695,11 @@ size_t render_smem_bytes(const RenderParams& p) {
 cudaError_t launch_render(const RenderParams& p, cudaStream_t stream, uint64_t* launches) {
     dim3 grid((p.width + 15) / 16, (p.height + 15) / 16), block(256);
     size_t smem = render_smem_bytes(p);
+    static const bool wide = std::getenv("BT_LENS_WIDE") != nullptr;
     if (p.stats)
         BT_DISPATCH_LENS(render_kernel_stats, grid, block, smem, stream, p);
+    else if (wide && p.scene.n_lens)
+        BT_DISPATCH_LENS(render_kernel_wide, grid, block, smem, stream, p);
     else
         BT_DISPATCH_LENS(render_kernel, grid, block, smem, stream, p);
     ++*launches;

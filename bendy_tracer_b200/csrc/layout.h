@@ -48,12 +48,17 @@ enum { VOL_STRIDE = 2 };
 //   e0 = (c.xyz, -1.5 r_s)   e1 = (r_s, r_far * r_s, -, -)   (stage evaluations read e0 only)
 enum { LENS_STRIDE = 2 };
 
+// ---- primitive bound record: BOUND_STRIDE float4 (extension; free-distance query of the stepper)
+//   b0 = (lo.xyz, -)   b1 = (hi.xyz, -)   world AABB of a rect; unused for spheres (exact formula)
+enum { BOUND_STRIDE = 2 };
+
 struct SceneHeader {
     uint32_t n_prims, prim_off;      // offsets in float4 units into the blob
     uint32_t n_mats, mat_off;
     uint32_t n_lights, light_off;
     uint32_t n_vols, vol_off;
     uint32_t n_lens, lens_off;
+    uint32_t bound_off;              // per-primitive world AABBs, BOUND_STRIDE float4 each (lensed linear-scan scenes)
     uint32_t blob_f4;                // total float4 count
     uint32_t n_bvh, bvh_off;         // BVH nodes (0: linear scan over shared memory)
     uint32_t stage_off, stage_f4;    // the part of the blob every CTA stages into shared memory
@@ -65,6 +70,7 @@ struct SceneHeader {
     float kappa, h_min, h_max;
     uint32_t max_steps;
     uint32_t lens_exact;             // BT_LENS_EXACT_RSQRT
+    uint32_t lens_skip;              // 1: chords shorter than the free distance are not intersected (!BT_LENS_NO_SKIP)
 };
 
 struct CameraBlock {                 // reference src/tracer/mod.rs:244-267 hoisted per render call
@@ -94,6 +100,7 @@ struct RenderParams {
     float clip_min, clip_max, volume_step;
     float tau_scale, one_scale;      // Uniform::new_inclusive(0, TAU).scale, (0, 1).scale
     uint32_t compact_lanes, compact_patience;  // per-warp step compaction thresholds (LENS kernels)
+    uint32_t scan_lanes, scan_patience;        // pending chords a warp collects before it runs the intersection phase
     unsigned long long* stats;       // render_kernel_stats only: {paths, scan calls, RK4 steps, events}
 };
 

@@ -1132,6 +1132,16 @@ FlatScene flatten(const Scene& scene, int accel) {
     fs.blob.insert(fs.blob.end(), vols.begin(), vols.end());
     h.lens_off = (uint32_t)fs.blob.size();
     fs.blob.insert(fs.blob.end(), lens.begin(), lens.end());
+    // world AABBs for the stepper's free-distance query (scan scenes under a lens field only)
+    h.bound_off = (uint32_t)fs.blob.size();
+    h.lens_skip = 0;
+    if (h.n_lens > 0 && nodes.empty() && !(scene.lens_config.flags & 2u)) {
+        h.lens_skip = 1;
+        for (uint32_t i = 0; i < h.n_prims; ++i) {
+            fs.blob.push_back(f4(bounds[i].lo[0], bounds[i].lo[1], bounds[i].lo[2], 0.0f));
+            fs.blob.push_back(f4(bounds[i].hi[0], bounds[i].hi[1], bounds[i].hi[2], 0.0f));
+        }
+    }
     h.bvh_off = (uint32_t)fs.blob.size();
     h.n_bvh = (uint32_t)(nodes.size() / BVH_STRIDE);
     fs.blob.insert(fs.blob.end(), nodes.begin(), nodes.end());

@@ -78,7 +78,11 @@ typedef struct {
  * BT_LENS_EXACT_RSQRT: the stepper's 1/|d| is correctly rounded (__frsqrt_rn) instead of
  * MUFU.RSQ (<= 2 ulp); every other operation is already IEEE, so the lensed path becomes
  * bit-identical to the CPU oracle.  Costs ~18 extra instructions per mass per evaluation. */
-enum { BT_LENS_EXACT_RSQRT = 1 };
+/* BT_LENS_NO_SKIP: intersect every chord with the scene, as the spec's loop is written.  By default
+ * a chord is intersected only when it is at least as long as a conservative lower bound on the
+ * distance from its start to the nearest primitive (refreshed by every intersection pass), which
+ * cannot change a result -- the flag exists so that tests can prove that. */
+enum { BT_LENS_EXACT_RSQRT = 1, BT_LENS_NO_SKIP = 2 };
 typedef struct {
     float kappa, h_min, h_max, r_far;
     uint32_t max_steps;

@@ -272,6 +272,29 @@ def test_render_parity_lensed_fast(oracle, name, lens):
     assert abs(m_got - m_ref) <= 0.02 * abs(m_ref) + 5e-3
 
 
+@pytest.mark.parametrize("name,lens", [("scene", LENS_SCENE), ("cloud", LENS_VOLUME), ("cornell2", np.array([[0.3, 2.2, 2.0, 0.1]], np.float32))])
+def test_chord_skip_changes_nothing(name, lens):
+    """The stepper intersects a chord only when it is at least as long as the free distance around
+    its start (a conservative bound refreshed by every intersection pass).  BT_LENS_NO_SKIP tests
+    every chord, as the spec's loop is written: images and probe segments must be bit-identical."""
+    import bendy_tracer_b200 as bt
+    w, h = 192, 108
+    _, esc, cam = load_pair(name, w, h)
+    imgs, segs = [], []
+    ys, xs = np.mgrid[0:h, 0:w]
+    for no_skip in (False, True):
+        esc.set_lenses(lens, bt.LensConfig(no_skip=no_skip))
+        imgs.append(engine_render(esc, cam, w, h, 2, 2, 0, seed=5)[0].copy())
+        tracer = bt.Tracer(bt.Config(), seed=5)
+        rays = tracer.camera_rays(esc, cam, bt.RenderConfig.with_samples(1), w, h, xs.ravel(), ys.ravel(),
+                                  np.zeros(w * h, np.uint64))
+        segs.append(tracer.trace_segments(esc, rays[:, :3], rays[:, 3:]))
+    assert np.array_equal(imgs[0], imgs[1])
+    for k in ("face", "steps", "object_ref", "t", "position", "normal", "direction"):
+        assert np.array_equal(segs[0][k], segs[1][k]), k
+    assert (segs[0]["steps"] > 10).mean() > 0.5                      # long flights: the skip had work to do
+
+
 # ---- full-size properties (BASELINE configs C2 / C4) ------------------------------------------
 def test_full_size_properties():
     """1920x1080: determinism, pass-range additivity (the multi-GPU sharding law), alpha, finiteness"""
