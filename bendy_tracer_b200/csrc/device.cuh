@@ -252,6 +252,7 @@ BT_DEV bool rect_test(const float4* q, V3 o, V3 d, float tmin, float tmax, bool 
 template <bool DIST>
 BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, int n_prims, V3 o, V3 d, float tmin, float tmax,
                         int volume_obj, float* free_out) {
+    (void)bounds;
     Hit h;
     h.t = tmax;
     h.prim = -1;
@@ -263,8 +264,9 @@ BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, int n_prims, 
         int type = __float_as_int(meta.x) & 3;
         if (type == PRIM_SPHERE) {
             float4 q0 = q[0];
-            float r2 = q[1].x;
-            if (volume_obj >= 0 && __float_as_int(meta.w) == volume_obj) {
+            const float4 q1 = q[1];
+            float r2 = q1.x;
+            if (!DIST && volume_obj >= 0 && __float_as_int(meta.w) == volume_obj) {
                 // Sphere::hit_volumetric, sphere.rs:150-166
                 V3 e = (o + h.t * d) - v3(q0);
                 if (dot(e, e) <= r2) {
@@ -277,10 +279,12 @@ BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, int n_prims, 
             const V3 oc = o - v3(q0);
             const float l2 = dot(oc, oc);
             if (DIST) {
-                // the root test may place a grazing hit up to sqrt(3 ulp(|oc|^2)) ~ 6e-4 |oc| away from
-                // the true surface: 1e-3 (|oc| + r) covers it and the approximate square root
+                // A reported root t puts the point o + t d within ~1e-6 |oc|^2 / r of the true surface
+                // (the residual of the quadratic, however ill-conditioned t itself is for a grazing
+                // ray), so dist(o, surface) <= t + that: the margin below is 20x it, plus the rounding
+                // of this bound.  q1.z = 2e-5 / r.
                 const float dc = sqrt_approx(l2);
-                free = fminf(free, fabsf(dc - q0.w) - 1e-3f * (dc + q0.w));
+                free = fminf(free, fabsf(dc - q0.w) - (l2 * q1.z + 2e-5f * (dc + q0.w) + 1e-6f));
             }
             if (sphere_roots_oc(oc, l2, r2, d, tmin, h.t, t)) {
                 h.t = t;

@@ -147,8 +147,8 @@ int build_params(bt_scene* s, uint64_t camera_ref, bool need_camera, const bt_co
     p.clip_min = m.clip_min;
     p.clip_max = m.clip_max;
     p.volume_step = m.volume_step;
-    p.compact_lanes = 8;
-    p.compact_patience = 16;
+    p.compact_lanes = 16;
+    p.compact_patience = 32;
     if (const char* e = std::getenv("BT_COMPACT_LANES")) p.compact_lanes = (uint32_t)std::atoi(e);
     if (const char* e = std::getenv("BT_COMPACT_PATIENCE")) p.compact_patience = (uint32_t)std::atoi(e);
     p.scan_lanes = 12;

@@ -6,8 +6,6 @@
 // with in-register path regeneration").  Path state lives in registers, the scene blob in shared
 // memory; HBM traffic is one float4 read-modify-write per pixel per call (buffer.rs:159-178).
 // Pixel sums are formed in the reference's order, so the result is deterministic.
-#include <cstdlib>
-
 #include "device.cuh"
 #include "kernels.h"
 
@@ -530,11 +528,6 @@ template <bool LENS, bool EXACT, int NL, bool BVH>
 __global__ void __launch_bounds__(256, 3) render_kernel(const __grid_constant__ RenderParams p) {
     render_body<false, LENS, EXACT, NL, BVH>(p);
 }
-// experiment: the lensed kernels with 2 CTAs / SM (128 registers, no spills)
-template <bool LENS, bool EXACT, int NL, bool BVH>
-__global__ void __launch_bounds__(256, 2) render_kernel_wide(const __grid_constant__ RenderParams p) {
-    render_body<false, LENS, EXACT, NL, BVH>(p);
-}
 // the same kernel + work counters for bench.py's roofline accounting (never timed)
 template <bool LENS, bool EXACT, int NL, bool BVH>
 __global__ void __launch_bounds__(256, 2) render_kernel_stats(const __grid_constant__ RenderParams p) {
@@ -695,11 +688,8 @@ size_t render_smem_bytes(const RenderParams& p) {
 cudaError_t launch_render(const RenderParams& p, cudaStream_t stream, uint64_t* launches) {
     dim3 grid((p.width + 15) / 16, (p.height + 15) / 16), block(256);
     size_t smem = render_smem_bytes(p);
-    static const bool wide = std::getenv("BT_LENS_WIDE") != nullptr;
     if (p.stats)
         BT_DISPATCH_LENS(render_kernel_stats, grid, block, smem, stream, p);
-    else if (wide && p.scene.n_lens)
-        BT_DISPATCH_LENS(render_kernel_wide, grid, block, smem, stream, p);
     else
         BT_DISPATCH_LENS(render_kernel, grid, block, smem, stream, p);
     ++*launches;

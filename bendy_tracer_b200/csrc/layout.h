@@ -10,7 +10,7 @@ namespace bt {
 // ---- primitive record: PRIM_STRIDE float4 -------------------------------------------------
 //   q4 = (type, material index, volume index | rect area, object index)   [int bits except area]
 // SPHERE (reference src/scene/object/sphere.rs:11-16; translation only, :121-148)
-//   q0 = (cx, cy, cz, r)   q1 = (r*r, PI*r*r, -, -)
+//   q0 = (cx, cy, cz, r)   q1 = (r*r, PI*r*r, 2e-5/r [free-distance margin], -)
 // RECT / CUBOID_FACE (reference rect.rs:110-155 with everything ray-independent hoisted:
 //   n = M*z, the full affine inverse and the local axes folded into two plane equations)
 //   q0 = (n.xyz, hw^2/|x|^2)  q1 = (T.xyz, hh^2/|y|^2)

@@ -1003,7 +1003,7 @@ FlatScene flatten(const Scene& scene, int accel) {
             }
             float r = o.radius;
             prims.push_back(f4(tf.f[9], tf.f[10], tf.f[11], r));
-            prims.push_back(f4(r * r, 3.14159265358979323846f * r * r, 0.0f, 0.0f));
+            prims.push_back(f4(r * r, 3.14159265358979323846f * r * r, r > 0.0f ? 2e-5f / r : 3.0e38f, 0.0f));
             prims.push_back(f4(0, 0, 0, 0));
             prims.push_back(f4(0, 0, 0, 0));
             prims.push_back(f4(as_f(PRIM_SPHERE | ((uint32_t)(prims.size() / PRIM_STRIDE) << 2)), as_f(mat), as_f(vol), as_f(obj)));

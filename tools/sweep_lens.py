@@ -1,5 +1,5 @@
 """Sweep of the lensed render kernel's scheduling knobs (env: BT_SCAN_LANES, BT_SCAN_PATIENCE,
-BT_COMPACT_LANES, BT_COMPACT_PATIENCE, BT_LENS_NO_SKIP, BT_LENS_WIDE) on the C3 / lensed-cloud frames
+BT_COMPACT_LANES, BT_COMPACT_PATIENCE, BT_LENS_NO_SKIP) on the C3 / lensed-cloud frames
 at reduced spp.  Each configuration runs in its own process (some knobs are read once).
 
     python tools/sweep_lens.py            # the sweep
@@ -58,12 +58,8 @@ def main():
         {"BT_SCAN_LANES": "16", "BT_SCAN_PATIENCE": "8"},
         {"BT_SCAN_LANES": "24", "BT_SCAN_PATIENCE": "8"},
         {"BT_SCAN_LANES": "24", "BT_SCAN_PATIENCE": "16"},
-        {"BT_LENS_WIDE": "1"},
-        {"BT_LENS_WIDE": "1", "BT_SCAN_LANES": "16", "BT_SCAN_PATIENCE": "8"},
-        {"BT_LENS_WIDE": "1", "BT_SCAN_LANES": "24", "BT_SCAN_PATIENCE": "16"},
         {"BT_COMPACT_LANES": "16", "BT_COMPACT_PATIENCE": "32"},
         {"BT_COMPACT_LANES": "4", "BT_COMPACT_PATIENCE": "8"},
-        {"BT_LENS_WIDE": "1", "BT_COMPACT_LANES": "16", "BT_COMPACT_PATIENCE": "32", "BT_SCAN_LANES": "16", "BT_SCAN_PATIENCE": "8"},
     ]
     for c in configs:
         env = dict(os.environ)
