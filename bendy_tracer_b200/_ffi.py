@@ -41,7 +41,7 @@ class BtSegment(C.Structure):
 class BtSceneInfo(C.Structure):
     _fields_ = [("n_objects", C.c_uint32), ("n_data", C.c_uint32), ("n_primitives", C.c_uint32),
                 ("n_lights", C.c_uint32), ("n_volumes", C.c_uint32), ("n_lenses", C.c_uint32),
-                ("n_bvh_nodes", C.c_uint32), ("root_material", C.c_uint64)]
+                ("n_bvh_nodes", C.c_uint32), ("n_boxes", C.c_uint32), ("root_material", C.c_uint64)]
 
 
 # every symbol include/bendy_b200.h declares: (restype, argtypes)

@@ -248,8 +248,9 @@ class Scene:
         check(lib.bt_scene_set_lenses(self.handle, xyzr.ctypes.data, len(xyzr), C.byref(cfg)))
 
     def set_accel(self, accel):
-        """closest-hit structure: "auto" (linear scan up to 64 primitives, BVH beyond), "linear", "bvh" """
-        check(lib.bt_scene_set_accel(self.handle, {"auto": 0, "linear": 1, "bvh": 2}[accel]))
+        """closest-hit structure: "auto" (linear scan up to 64 primitives, BVH beyond), "linear", "bvh",
+        "linear_faces" (the scan with every cuboid as six rect tests, no box slab test)"""
+        check(lib.bt_scene_set_accel(self.handle, {"auto": 0, "linear": 1, "bvh": 2, "linear_faces": 3}[accel]))
 
     def info(self):
         i = _ffi.BtSceneInfo()

@@ -243,6 +243,52 @@ BT_DEV bool rect_test(const float4* q, V3 o, V3 d, float tmin, float tmax, bool 
     return ok;
 }
 
+// Cuboid::hit (cuboid.rs:83-105) for a cuboid whose six faces form one box: the smallest face
+// distance in [tmin, tmax) from one slab test.  The per-face t equals Rect::hit's p / q for that
+// face up to rounding; the rect's inside test becomes the slab-interval test.  Returns the face
+// (0..5, the reference's face order) and Rect::hit's `p < 0` (front) for it.
+BT_DEV float rcp_approx(float x) {  // MUFU.RCP, <= 1 ulp; callers guarantee 1e-5 < |x| <= ~1
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// *dist_out (optional): |L-infinity distance| from o to the box surface (outside: to the box; inside: to the nearest face)
+BT_DEV bool box_test(const float4* b, V3 o, V3 d, float tmin, float tmax, float& t_out, int& face_out, bool& front_out,
+                     float* dist_out = nullptr) {
+    const float4 b0 = b[0], b1 = b[1], b2 = b[2], b3 = b[3];
+    const V3 oc = v3(b0) - o;
+    const float inf = __int_as_float(0x7f800000);
+    // per axis k: p = (C - o) . a_k, q = d . a_k; the ray meets the planes at (p -/+ h) / q
+    const float p0 = sdot(oc, v3(b1)), q0 = sdot(d, v3(b1)), h0 = b0.w;
+    const float p1 = sdot(oc, v3(b2)), q1 = sdot(d, v3(b2)), h1 = b1.w;
+    const float p2 = sdot(oc, v3(b3)), q2 = sdot(d, v3(b3)), h2 = b2.w;
+    // Rect::hit's parallel-ray cut-off (rect.rs:122-124): such a pair of faces cannot be hit, and the
+    // ray must lie inside their slab to hit any of the other four
+    const bool par0 = !(fabsf(q0) > 1e-5f), par1 = !(fabsf(q1) > 1e-5f), par2 = !(fabsf(q2) > 1e-5f);
+    const float i0 = rcp_approx(par0 ? 1.0f : q0), i1 = rcp_approx(par1 ? 1.0f : q1), i2 = rcp_approx(par2 ? 1.0f : q2);
+    const float s0 = copysignf(h0, q0), s1 = copysignf(h1, q1), s2 = copysignf(h2, q2);
+    const float n0 = par0 ? -inf : (p0 - s0) * i0, f0 = par0 ? inf : (p0 + s0) * i0;
+    const float n1 = par1 ? -inf : (p1 - s1) * i1, f1 = par1 ? inf : (p1 + s1) * i1;
+    const float n2 = par2 ? -inf : (p2 - s2) * i2, f2 = par2 ? inf : (p2 + s2) * i2;
+    const float tn = fmaxf(fmaxf(n0, n1), n2), tf = fminf(fminf(f0, f1), f2);
+    bool ok = tn <= tf && !(par0 && fabsf(p0) > h0) && !(par1 && fabsf(p1) > h1) && !(par2 && fabsf(p2) > h2);
+    const bool near = tn >= tmin;  // the entry face if it is in range, else the exit face
+    const float t = near ? tn : tf;
+    ok = ok && !(t < tmin) && t < tmax;
+    const int k = near ? (tn == n0 ? 0 : (tn == n1 ? 1 : 2)) : (tf == f0 ? 0 : (tf == f1 ? 1 : 2));
+    const float p = k == 0 ? p0 : (k == 1 ? p1 : p2), q = k == 0 ? q0 : (k == 1 ? q1 : q2), h = k == 0 ? h0 : (k == 1 ? h1 : h2);
+    // entering through the face on the side the ray comes from, leaving through the opposite one
+    const bool plus = near ? q < 0.0f : q > 0.0f;
+    const int face = 2 * k + (plus ? 1 : 0);
+    const bool flipped = (__float_as_uint(b3.w) >> face) & 1u;  // stored normal = -a_k
+    const float pface = p + (plus ? h : -h);                     // (T_face - o) . a_k
+    t_out = t;
+    face_out = face;
+    front_out = flipped ? pface > 0.0f : pface < 0.0f;
+    if (dist_out) *dist_out = fabsf(fmaxf(fmaxf(fabsf(p0) - h0, fabsf(p1) - h1), fabsf(p2) - h2));
+    return ok;
+}
+
 // ChunkState::try_hit / try_hit_volume (mod.rs:389-427): linear scan in canonical object order
 // with a shrinking clip.max.  volume_obj >= 0 selects hit_volumetric for that object's sphere.
 // DIST: the same pass also returns a conservative lower bound on the distance from `o` to the
@@ -250,9 +296,10 @@ BT_DEV bool rect_test(const float4* q, V3 o, V3 d, float tmin, float tmax, bool 
 // AABB), minus a margin that covers the rounding of the hit tests themselves -- a ray that starts
 // at `o` cannot be reported as hitting anything within that distance (the stepper's chord skip).
 template <bool DIST>
-BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, int n_prims, V3 o, V3 d, float tmin, float tmax,
-                        int volume_obj, float* free_out) {
+BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, const float4* boxes, int n_prims, V3 o, V3 d, float tmin,
+                        float tmax, int volume_obj, float* free_out) {
     (void)bounds;
+    (void)boxes;
     Hit h;
     h.t = tmax;
     h.prim = -1;
@@ -294,6 +341,20 @@ BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, int n_prims, 
         } else {
             float t;
             bool front;
+            if (type == PRIM_CUBOID_FACE && __float_as_int(meta.z) > 0) {
+                // the first face of a box-shaped cuboid: all six faces in one slab test
+                int face;
+                float bd;
+                const bool hit = box_test(boxes + (__float_as_int(meta.z) - 1) * BOX_STRIDE, o, d, tmin, h.t, t, face, front, DIST ? &bd : nullptr);
+                if (DIST) free = fminf(free, bd - (1e-4f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + bd) + 1e-4f));
+                if (hit) {
+                    h.t = t;
+                    h.prim = i + face;
+                    h.face = front ? 0 : 1;
+                }
+                i += 5;
+                continue;
+            }
             if (DIST) {
                 const float4 lo = bounds[i * BOUND_STRIDE], hi = bounds[i * BOUND_STRIDE + 1];
                 const float dx = fmaxf(lo.x - o.x, o.x - hi.x), dy = fmaxf(lo.y - o.y, o.y - hi.y), dz = fmaxf(lo.z - o.z, o.z - hi.z);
@@ -310,8 +371,8 @@ BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, int n_prims, 
     if (DIST) *free_out = free;
     return h;
 }
-BT_DEV Hit scan_prims(const float4* prims, int n_prims, V3 o, V3 d, float tmin, float tmax, int volume_obj) {
-    return scan_prims_t<false>(prims, nullptr, n_prims, o, d, tmin, tmax, volume_obj, nullptr);
+BT_DEV Hit scan_prims(const float4* prims, const float4* boxes, int n_prims, V3 o, V3 d, float tmin, float tmax, int volume_obj) {
+    return scan_prims_t<false>(prims, nullptr, boxes, n_prims, o, d, tmin, tmax, volume_obj, nullptr);
 }
 
 // Closest hit through the BVH (extension; scenes above the linear-scan budget).  Records and

@@ -330,7 +330,7 @@ int bt_scene_set_lenses(bt_scene* scene, const float* xyzr, uint32_t n, const bt
 
 int bt_scene_set_accel(bt_scene* scene, int accel) {
     if (!scene) return fail(BT_ERR_INVALID_ARG, "NULL argument");
-    if (accel < ACCEL_AUTO || accel > ACCEL_BVH) return fail(BT_ERR_INVALID_ARG, "accel must be BT_ACCEL_AUTO, _LINEAR or _BVH");
+    if (accel < ACCEL_AUTO || accel > ACCEL_LINEAR_FACES) return fail(BT_ERR_INVALID_ARG, "accel must be BT_ACCEL_AUTO, _LINEAR, _BVH or _LINEAR_FACES");
     scene->accel = accel;
     scene->flat_dirty = true;
     return BT_OK;
@@ -352,6 +352,7 @@ int bt_scene_get_info(const bt_scene* scene, bt_scene_info* info) {
     info->n_volumes = f->header.n_vols;
     info->n_lenses = f->header.n_lens;
     info->n_bvh_nodes = f->header.n_bvh;
+    info->n_boxes = f->header.n_boxes;
     info->root_material = scene->scene.root_material;
     return BT_OK;
     GUARD_END

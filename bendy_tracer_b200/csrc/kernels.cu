@@ -22,6 +22,7 @@ struct SceneView {
     const float4* vols;
     const float4* lens;
     const float4* bounds;  // per-primitive AABBs (lensed scan scenes)
+    const float4* boxes;   // BOX records of box-shaped cuboids (scan scenes)
     const float* grids;
 };
 
@@ -39,6 +40,7 @@ BT_DEV SceneView stage_scene(const RenderParams& p, float4* smem) {
     s.vols = smem + (p.scene.vol_off - base);
     s.lens = smem + (p.scene.lens_off - base);
     s.bounds = smem + (p.scene.bound_off - base);
+    s.boxes = smem + (p.scene.box_off - base);
     s.grids = p.grids;
     return s;
 }
@@ -59,7 +61,7 @@ BT_DEV Traced trace_straight(const RenderParams& p, const SceneView& sc, V3 o, V
     if (BVH)
         r.h = bvh_closest(sc.prims, sc.nodes, sc.stack, o, d, tmin, tmax);
     else
-        r.h = scan_prims(sc.prims, (int)p.scene.n_prims, o, d, tmin, tmax, vol_obj);
+        r.h = scan_prims(sc.prims, sc.boxes, (int)p.scene.n_prims, o, d, tmin, tmax, vol_obj);
     r.steps = 0;
     r.scans = 1;
     r.captured = false;
@@ -134,9 +136,9 @@ BT_DEV int geodesic_scan(const RenderParams& p, const SceneView& sc, V3 x, V3 v,
     if (BVH)
         f.h = bvh_closest(sc.prims, sc.nodes, sc.stack, o, dir, cmin, cmax);
     else if (p.scene.lens_skip)
-        f.h = scan_prims_t<true>(sc.prims, sc.bounds, (int)p.scene.n_prims, o, dir, cmin, cmax, -1, &bound);
+        f.h = scan_prims_t<true>(sc.prims, sc.bounds, sc.boxes, (int)p.scene.n_prims, o, dir, cmin, cmax, -1, &bound);
     else
-        f.h = scan_prims(sc.prims, (int)p.scene.n_prims, o, dir, cmin, cmax, -1);
+        f.h = scan_prims(sc.prims, sc.boxes, (int)p.scene.n_prims, o, dir, cmin, cmax, -1);
     f.scans++;
     if (f.h.prim >= 0) return far ? FL_HIT_FAR : FL_HIT;
     if (far) return FL_ESCAPED;

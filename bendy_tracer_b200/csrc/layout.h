@@ -48,6 +48,13 @@ enum { VOL_STRIDE = 2 };
 //   e0 = (c.xyz, -1.5 r_s)   e1 = (r_s, r_far * r_s, -, -)   (stage evaluations read e0 only)
 enum { LENS_STRIDE = 2 };
 
+// ---- box record: BOX_STRIDE float4 (a Cuboid whose faces form one rectangular box) ------------
+//   b0 = (C.xyz, h0)  b1 = (a0.xyz, h1)  b2 = (a1.xyz, h2)  b3 = (a2.xyz, bits)
+//   centre, unit axes, half extents; faces 2k / 2k+1 sit at -h_k / +h_k along a_k; bit i: the
+//   stored normal of face i points along -a_k.  The FIRST face record of such a cuboid carries
+//   1 + box index in q4.z (0: test the six rects).
+enum { BOX_STRIDE = 4 };
+
 // ---- primitive bound record: BOUND_STRIDE float4 (extension; free-distance query of the stepper)
 //   b0 = (lo.xyz, -)   b1 = (hi.xyz, -)   world AABB of a rect; unused for spheres (exact formula)
 enum { BOUND_STRIDE = 2 };
@@ -58,6 +65,7 @@ struct SceneHeader {
     uint32_t n_lights, light_off;
     uint32_t n_vols, vol_off;
     uint32_t n_lens, lens_off;
+    uint32_t n_boxes, box_off;       // BOX records (linear-scan scenes)
     uint32_t bound_off;              // per-primitive world AABBs, BOUND_STRIDE float4 each (lensed linear-scan scenes)
     uint32_t blob_f4;                // total float4 count
     uint32_t n_bvh, bvh_off;         // BVH nodes (0: linear scan over shared memory)

@@ -808,7 +808,62 @@ void push_rect(std::vector<float4>& blob, std::vector<Bounds>& bounds, const Rec
     blob.push_back(f4(tf.f[9], tf.f[10], tf.f[11], hh2));
     blob.push_back(f4((float)ax[0], (float)ax[1], (float)ax[2], (float)cx));
     blob.push_back(f4((float)ay[0], (float)ay[1], (float)ay[2], (float)cy));
-    blob.push_back(f4(as_f((uint32_t)type | ((uint32_t)(blob.size() / PRIM_STRIDE) << 2)), as_f(mat), area, as_f(obj)));
+    blob.push_back(f4(as_f((uint32_t)type | ((uint32_t)(blob.size() / PRIM_STRIDE) << 2)), as_f(mat), type == PRIM_RECT ? area : as_f(0u), as_f(obj)));
+}
+
+// A Cuboid whose six faces really are the faces of one rectangular box (Cuboid::new, cuboid.rs:19-30,
+// under a rigid transform) gets a BOX record: the scan then finds the closest face with one slab
+// test instead of six rect tests.  Anything else (hand-edited faces, sheared transforms) keeps the
+// six rect tests.  Faces come in opposite pairs (0,1) (2,3) (4,5).
+bool make_box(const Object& o, const Affine& tf, float4 out[BOX_STRIDE]) {
+    double c[6][3], n[6][3], ex[6][3], ey[6][3], C[3] = {0, 0, 0};
+    for (int i = 0; i < 6; ++i) {
+        float t[3], v[3];
+        mat_vec(tf, o.face_offset[i], t);
+        for (int k = 0; k < 3; ++k) { c[i][k] = (double)t[k] + tf.f[9 + k]; C[k] += c[i][k] / 6.0; }
+        mat_vec(tf, o.faces[i].z, v);
+        for (int k = 0; k < 3; ++k) n[i][k] = v[k];
+        mat_vec(tf, o.faces[i].x, v);
+        for (int k = 0; k < 3; ++k) ex[i][k] = (double)v[k] * o.faces[i].half_width;
+        mat_vec(tf, o.faces[i].y, v);
+        for (int k = 0; k < 3; ++k) ey[i][k] = (double)v[k] * o.faces[i].half_height;
+    }
+    auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+    auto len = [&](const double* a) { return std::sqrt(dot(a, a)); };
+    double a[3][3], h[3];
+    for (int k = 0; k < 3; ++k) {
+        double d[3], m[3];
+        for (int j = 0; j < 3; ++j) { d[j] = c[2 * k + 1][j] - c[2 * k][j]; m[j] = c[2 * k + 1][j] + c[2 * k][j] - 2.0 * C[j]; }
+        h[k] = 0.5 * len(d);
+        if (!(h[k] > 1e-12)) return false;
+        for (int j = 0; j < 3; ++j) a[k][j] = d[j] / (2.0 * h[k]);
+        if (len(m) > 1e-4 * (h[0] + h[k] + 1e-12)) return false;
+    }
+    const double scale = h[0] + h[1] + h[2];
+    const double tol = 1e-4;
+    for (int k = 0; k < 3; ++k)
+        if (std::fabs(dot(a[k], a[(k + 1) % 3])) > tol) return false;
+    uint32_t bits = 0;
+    for (int i = 0; i < 6; ++i) {
+        const int k = i / 2, k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+        const double nl = len(n[i]);
+        if (!(nl > 1e-12)) return false;
+        const double na = dot(n[i], a[k]) / nl;
+        if (std::fabs(std::fabs(na) - 1.0) > tol) return false;          // the face normal is the pair's axis
+        if (na < 0) bits |= 1u << i;
+        // the rect's extents are the other two axes' half-extents (either assignment)
+        const double x1 = std::fabs(dot(ex[i], a[k1])), x2 = std::fabs(dot(ex[i], a[k2]));
+        const double y1 = std::fabs(dot(ey[i], a[k1])), y2 = std::fabs(dot(ey[i], a[k2]));
+        const bool direct = std::fabs(x1 - h[k1]) <= tol * scale && x2 <= tol * scale && std::fabs(y2 - h[k2]) <= tol * scale && y1 <= tol * scale;
+        const bool swapped = std::fabs(x2 - h[k2]) <= tol * scale && x1 <= tol * scale && std::fabs(y1 - h[k1]) <= tol * scale && y2 <= tol * scale;
+        if (!direct && !swapped) return false;
+        if (std::fabs(dot(ex[i], a[k])) > tol * scale || std::fabs(dot(ey[i], a[k])) > tol * scale) return false;
+    }
+    out[0] = f4((float)C[0], (float)C[1], (float)C[2], (float)h[0]);
+    out[1] = f4((float)a[0][0], (float)a[0][1], (float)a[0][2], (float)h[1]);
+    out[2] = f4((float)a[1][0], (float)a[1][1], (float)a[1][2], (float)h[2]);
+    out[3] = f4((float)a[2][0], (float)a[2][1], (float)a[2][2], as_f(bits));
+    return true;
 }
 
 // ---- BVH2: binned-SAH build, <= 4 primitives per leaf; a node stores BOTH child boxes -----
@@ -982,7 +1037,8 @@ FlatScene flatten(const Scene& scene, int accel) {
         h.root_keeps_normal = d.mat_kind == MAT_EMISSIVE ? 0u : 1u;
     }
 
-    std::vector<float4> prims, lights;
+    std::vector<float4> prims, lights, boxes;
+    std::vector<std::pair<uint32_t, uint32_t> > box_of_prim;  // (first face record, box index)
     std::vector<Bounds> bounds;
     bool any_diffuse = false;
     for (std::map<uint64_t, Object>::const_iterator it = scene.objects.begin(); it != scene.objects.end(); ++it) {
@@ -1027,6 +1083,11 @@ FlatScene flatten(const Scene& scene, int accel) {
                 for (int k = 0; k < 3; ++k) ftf.f[9 + k] = t[k] + tf.f[9 + k];
                 push_rect(prims, bounds, o.faces[i], ftf, PRIM_CUBOID_FACE, resolve.material(o.faces[i].material), obj);
                 any_diffuse |= scene.get_data(o.faces[i].material).mat_kind == MAT_DIFFUSE;
+            }
+            float4 box[BOX_STRIDE];
+            if (make_box(o, tf, box)) {  // q4.z of the first face: 1 + box index (cuboid faces carry no area)
+                box_of_prim.push_back(std::make_pair((uint32_t)(prims.size() / PRIM_STRIDE) - 6u, (uint32_t)(boxes.size() / BOX_STRIDE)));
+                boxes.insert(boxes.end(), box, box + BOX_STRIDE);
             }
             n_prims = 6;
         }
@@ -1132,6 +1193,15 @@ FlatScene flatten(const Scene& scene, int accel) {
     fs.blob.insert(fs.blob.end(), vols.begin(), vols.end());
     h.lens_off = (uint32_t)fs.blob.size();
     fs.blob.insert(fs.blob.end(), lens.begin(), lens.end());
+    // BOX records (linear-scan scenes): the first face of each box-shaped cuboid points at its record
+    h.box_off = (uint32_t)fs.blob.size();
+    h.n_boxes = 0;
+    if (nodes.empty() && accel != ACCEL_LINEAR_FACES) {
+        h.n_boxes = (uint32_t)(boxes.size() / BOX_STRIDE);
+        fs.blob.insert(fs.blob.end(), boxes.begin(), boxes.end());
+        for (size_t i = 0; i < box_of_prim.size(); ++i)
+            fs.blob[(size_t)box_of_prim[i].first * PRIM_STRIDE + 4].z = as_f(box_of_prim[i].second + 1u);
+    }
     // world AABBs for the stepper's free-distance query (scan scenes under a lens field only)
     h.bound_off = (uint32_t)fs.blob.size();
     h.lens_skip = 0;

@@ -119,7 +119,7 @@ struct FlatScene {
     bool unsupported_light;             // a Cuboid carries ObjectFlags::LIGHT (not flattened yet)
 };
 // accel: 0 = automatic (BVH above BVH_AUTO_PRIMS primitives), 1 = linear scan, 2 = BVH
-enum { ACCEL_AUTO = 0, ACCEL_LINEAR = 1, ACCEL_BVH = 2, BVH_AUTO_PRIMS = 64 };
+enum { ACCEL_AUTO = 0, ACCEL_LINEAR = 1, ACCEL_BVH = 2, ACCEL_LINEAR_FACES = 3, BVH_AUTO_PRIMS = 64 };
 FlatScene flatten(const Scene& scene, int accel = ACCEL_AUTO);
 
 // Uniform<f32>::new / new_inclusive scale (rand 0.8.5 UniformFloat) -- host-side constants

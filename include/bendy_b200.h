@@ -102,7 +102,8 @@ typedef struct {
 
 typedef struct {
     uint32_t n_objects, n_data, n_primitives /* flattened: spheres + rects + 6 per cuboid */,
-             n_lights, n_volumes, n_lenses, n_bvh_nodes;
+             n_lights, n_volumes, n_lenses, n_bvh_nodes,
+             n_boxes /* cuboids recognised as one rectangular box: one slab test instead of six rect tests */;
     uint64_t root_material;
 } bt_scene_info;
 
@@ -139,7 +140,9 @@ void bt_lens_config_default(bt_lens_config* cfg);
  * over shared memory up to 64 flattened primitives, a BVH (global-memory nodes, shared-memory
  * traversal stack) beyond.  Both give the same hits, exact-distance ties included.  Scenes with
  * volumetric spheres always use the scan (hit_volumetric depends on the scan order, :414-424). */
-enum { BT_ACCEL_AUTO = 0, BT_ACCEL_LINEAR = 1, BT_ACCEL_BVH = 2 };
+enum { BT_ACCEL_AUTO = 0, BT_ACCEL_LINEAR = 1, BT_ACCEL_BVH = 2,
+       BT_ACCEL_LINEAR_FACES = 3 /* the scan with every Cuboid as its six Rect::hit tests (cuboid.rs:83-105, literally);
+                                    the other modes test a box-shaped cuboid with one slab test */ };
 int bt_scene_set_accel(bt_scene* scene, int accel);
 int bt_scene_get_info(const bt_scene* scene, bt_scene_info* info);
 

@@ -148,6 +148,42 @@ def test_resolve_u8(oracle, cs):
     assert np.array_equal(dev.preview(), got)
 
 
+@pytest.mark.parametrize("name", ["cornell", "cornell2"])
+def test_box_slab_test_equals_six_rect_tests(oracle, name):
+    """A box-shaped cuboid is intersected with one slab test; BT_ACCEL_LINEAR_FACES runs the reference's
+    six Rect::hit tests per cuboid (cuboid.rs:83-105).  Same closest face for (almost) every ray --
+    rays through a box edge within rounding may pick the neighbouring face -- and the same image."""
+    import bendy_tracer_b200 as bt
+    w, h = 256, 256
+    _, esc, cam = load_pair(name, w, h)
+    rng = np.random.default_rng(11)
+    n = 200000
+    # rays from inside the room in every direction, and from inside the boxes outwards
+    origins = np.concatenate([rng.uniform([-2.4, 0.1, -4.9], [2.4, 4.9, 4.0], (n, 3)),
+                              rng.normal(0, 0.1, (n // 4, 3)) + [-1.2, 1.0, -3.2],
+                              rng.normal(0, 0.1, (n // 4, 3)) + [1.2, 0.5, -1.8]]).astype(np.float32)
+    dirs = rng.normal(size=origins.shape)
+    dirs = (dirs / np.linalg.norm(dirs, axis=1, keepdims=True)).astype(np.float32)
+    tracer = bt.Tracer(bt.Config(), seed=1)
+    assert esc.info()["n_boxes"] == 2
+    box = tracer.trace_segments(esc, origins, dirs)
+    img_box = engine_render(esc, cam, w, h, 2, 2, 0, seed=4)[0].copy()
+    esc.set_accel("linear_faces")
+    assert esc.info()["n_boxes"] == 0
+    faces = tracer.trace_segments(esc, origins, dirs)
+    img_faces = engine_render(esc, cam, w, h, 2, 2, 0, seed=4)[0].copy()
+    same = (box["face"] == faces["face"]) & (box["object_ref"] == faces["object_ref"])
+    assert same.mean() >= 0.9999, (~same).sum()
+    on_box = same & (box["object_ref"] >= 7)
+    assert on_box.mean() > 0.1                                               # the boxes really were hit
+    terr = np.abs(box["t"][same] - faces["t"][same]) / (1.0 + faces["t"][same])
+    assert terr.max() <= 2e-5 and np.quantile(terr, 0.999) <= 2e-6, (terr.max(), np.quantile(terr, 0.999))
+    assert np.abs(box["normal"][same] - faces["normal"][same]).max() == 0.0  # the same face record
+    assert (mae_per_channel(img_box, img_faces, 8) <= 1e-4).all()
+    ref, nref, _ = oracle_render(load_pair(name, w, h)[0], cam, w, h, 2, 2, 0, seed=4)
+    assert (mae_per_channel(img_box, ref, nref) <= IMAGE_MAE).all()
+
+
 # ---- lens field -----------------------------------------------------------------------------
 def test_flat_limit_is_exact(oracle):
     """r_s = 0 masses must reproduce the unlensed image bit for bit"""
@@ -324,10 +360,11 @@ def test_full_size_properties():
 # ---- BVH (scenes above the linear-scan budget) -------------------------------------------------
 @pytest.mark.parametrize("name,lens", [("cornell", None), ("scene", None), ("scene", LENS_SCENE)])
 def test_bvh_equals_linear_scan_on_shipped_scenes(name, lens):
-    """forcing the BVH on a shipped scene must not change a single bit of the image"""
+    """forcing the BVH on a shipped scene must not change a single bit of the image (against the scan
+    with the same per-face rect tests; the box slab test of the default scan has its own test)"""
     w, h = _res(name)
     _, esc, cam = load_pair(name, w, h, lenses=lens)
-    esc.set_accel("linear")
+    esc.set_accel("linear_faces")
     a, _, _ = engine_render(esc, cam, w, h, 2, 2, 0, seed=4)
     esc.set_accel("bvh")
     assert esc.info()["n_bvh_nodes"] > 0
@@ -353,7 +390,7 @@ def test_bvh_synthetic_scene_vs_oracle(oracle):
     got, _, _ = engine_render(esc, cam, w, h, 2, 2, 0, seed=6)
     mae = mae_per_channel(got, ref, n)
     assert (mae <= IMAGE_MAE).all(), mae
-    esc.set_accel("linear")
+    esc.set_accel("linear_faces")
     lin, _, _ = engine_render(esc, cam, w, h, 2, 2, 0, seed=6)
     assert np.array_equal(lin, got)
     # first hits agree with the oracle's scan

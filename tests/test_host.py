@@ -137,6 +137,26 @@ def test_apply_transform_propagates_to_children():
         s.apply_transform(42, shift)
 
 
+def test_box_shaped_cuboids_are_recognised():
+    """Cuboid::new boxes under a rigid transform flatten to one BOX record each (one slab test instead
+    of six rect tests); a cuboid whose faces no longer form a box keeps its six rect tests."""
+    doc = O.read_scene_json(O.scene_path("cornell"))
+    sc = bt.Scene.from_json(json.dumps(doc))
+    assert sc.info()["n_boxes"] == 2 and sc.info()["n_primitives"] == 18
+    sc.set_accel("linear_faces")
+    assert sc.info()["n_boxes"] == 0
+    sc.set_accel("bvh")
+    assert sc.info()["n_boxes"] == 0
+    cub = [o for o in doc["objects"]["collection"].values() if "Cuboid" in o["inner"]]
+    assert len(cub) == 2
+    cub[0]["inner"]["Cuboid"]["faces"][0][1]["half_width"] *= 0.5      # a face that no longer spans the box
+    assert bt.Scene.from_json(json.dumps(doc)).info()["n_boxes"] == 1
+    m = cub[1]["transform"]["transform_world"]
+    m[3] += 0.3 * m[0]; m[4] += 0.3 * m[1]; m[5] += 0.3 * m[2]          # shear: y axis leans along x
+    cub[1]["transform"]["transform_local"] = list(m)
+    assert bt.Scene.from_json(json.dumps(doc)).info()["n_boxes"] == 0
+
+
 def test_camera_aspect_update():
     s = bt.Scene.load(O.scene_path("cornell"))
     s.set_camera_aspect(0, 1.7777778)
