@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libbendy_b200.so")
+LIB_PATH = os.environ.get("BENDY_B200_LIB") or os.path.join(_HERE, "csrc", "libbendy_b200.so")
 
 OK, ERR_INVALID_ARG, ERR_PARSE, ERR_SCENE, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -60,6 +60,7 @@ SIGNATURES = {
     "bt_scene_set_lenses": (C.c_int, [_P, _P, C.c_uint32, C.POINTER(BtLensConfig)]),
     "bt_lens_config_default": (None, [C.POINTER(BtLensConfig)]),
     "bt_scene_set_accel": (C.c_int, [_P, C.c_int]),
+    "bt_scene_set_precision": (C.c_int, [_P, C.c_int]),
     "bt_scene_get_info": (C.c_int, [_P, C.POINTER(BtSceneInfo)]),
     "bt_config_default": (None, [C.POINTER(BtConfig)]),
     "bt_render_config_default": (None, [C.POINTER(BtRenderConfig)]),

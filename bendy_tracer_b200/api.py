@@ -252,6 +252,11 @@ class Scene:
         "linear_faces" (the scan with every cuboid as six rect tests, no box slab test)"""
         check(lib.bt_scene_set_accel(self.handle, {"auto": 0, "linear": 1, "bvh": 2, "linear_faces": 3}[accel]))
 
+    def set_precision(self, precision):
+        """arithmetic flavour of the kernels: "auto" (exact for volumetric scenes, fast otherwise),
+        "fast" (MUFU reciprocals / square roots, ~1 ulp) or "exact" (IEEE, bit-identical to the oracle)"""
+        check(lib.bt_scene_set_precision(self.handle, {"auto": 0, "fast": 1, "exact": 2}[precision]))
+
     def info(self):
         i = _ffi.BtSceneInfo()
         check(lib.bt_scene_get_info(self.handle, C.byref(i)))

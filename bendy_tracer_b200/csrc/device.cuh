@@ -31,11 +31,62 @@ BT_DEV V3 operator/(V3 a, float s) { return v3(a.x / s, a.y / s, a.z / s); }
 BT_DEV V3 operator/(V3 a, V3 b) { return v3(a.x / b.x, a.y / b.y, a.z / b.z); }
 BT_DEV float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 BT_DEV V3 cross(V3 a, V3 b) { return v3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
-// Vec3A::normalize: v / sqrt(dot);  Vec3::normalize: v * (1 / sqrt(dot))
+// Two arithmetic flavours (compile time).  BT_EXACT_SCAN: every division / square root is the IEEE
+// operation the Rust reference performs, so values are bit-identical to the CPU oracle.  Default:
+// MUFU-based reciprocal / square root / reciprocal square root, each within ~1 ulp of the IEEE
+// result (PTX rcp.approx / sqrt.approx: <= 1 ulp; rsqrt.approx + one Newton step), a fraction of
+// the instructions.  The parity tests hold the default build to the north-star tolerances.
+#ifdef BT_EXACT_SCAN
+#define BT_X_RCP 1
+#define BT_X_SQRT 1
+#define BT_X_RSQRT 1
+#define BT_X_DIV 1
+#define BT_X_NORM 1
+#endif
+#ifdef BT_X_RCP
+BT_DEV float m_rcp(float x) { return 1.0f / x; }
+#else
+BT_DEV float m_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+#endif
+#ifdef BT_X_SQRT
+BT_DEV float m_sqrt(float x) { return sqrtf(x); }
+#else
+BT_DEV float m_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+#endif
+#ifdef BT_X_RSQRT
+BT_DEV float m_rsqrt(float x) { return 1.0f / sqrtf(x); }
+#else
+BT_DEV float m_rsqrt(float x) {  // MUFU.RSQ + one Newton step
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    const float e = fmaf(-(x * y), y, 1.0f);
+    return fmaf(0.5f * y, e, y);
+}
+#endif
+#ifdef BT_X_DIV
+BT_DEV V3 m_div(V3 a, float s) { return v3(a.x / s, a.y / s, a.z / s); }
+BT_DEV V3 m_div(V3 a, V3 b) { return v3(a.x / b.x, a.y / b.y, a.z / b.z); }
+#else
+BT_DEV V3 m_div(V3 a, float s) { return a * m_rcp(s); }
+BT_DEV V3 m_div(V3 a, V3 b) { return v3(a.x * m_rcp(b.x), a.y * m_rcp(b.y), a.z * m_rcp(b.z)); }
+#endif
+#ifdef BT_X_NORM
 BT_DEV V3 normalize_a(V3 a) { return a / sqrtf(dot(a, a)); }
-BT_DEV V3 normalize_s(V3 a) { return a * (1.0f / sqrtf(dot(a, a))); }
+#else
+BT_DEV V3 normalize_a(V3 a) { return a * m_rsqrt(dot(a, a)); }
+#endif
+// Vec3A::normalize: v / sqrt(dot);  Vec3::normalize: v * (1 / sqrt(dot))
+BT_DEV V3 normalize_s(V3 a) { return a * m_rsqrt(dot(a, a)); }
 BT_DEV V3 normalize_or_zero_s(V3 a) {
-    float rcp = 1.0f / sqrtf(dot(a, a));
+    float rcp = m_rsqrt(dot(a, a));
     if (isfinite(rcp) && rcp > 0.0f) return a * rcp;
     return v3(0.0f, 0.0f, 0.0f);
 }
@@ -45,7 +96,7 @@ BT_DEV V3 mat_vec(V3 c0, V3 c1, V3 c2, V3 v) { return (c0 * v.x + c1 * v.y) + c2
 // Vec3::any_orthonormal_pair (glam)
 BT_DEV void any_orthonormal_pair(V3 n, V3& a_out, V3& b_out) {
     float sign = copysignf(1.0f, n.z);
-    float a = -1.0f / (sign + n.z);
+    float a = -m_rcp(sign + n.z);
     float b = n.x * n.y * a;
     a_out = v3(1.0f + sign * n.x * n.x * a, sign * b, -sign * n.x);
     b_out = v3(b, sign + n.y * n.y * a, -n.y);
@@ -55,12 +106,12 @@ BT_DEV V3 reflect(V3 d, V3 n) { return d - (2.0f * dot(d, n)) * n; }            
 BT_DEV V3 refract(V3 d, V3 n, float ior) {                                          // math/mod.rs:43-48
     float cos_theta = fminf(dot(-d, n), 1.0f);
     V3 perp = (n * cos_theta + d) * ior;
-    V3 parallel = n * -sqrtf(fabsf(1.0f - dot(perp, perp)));
+    V3 parallel = n * -m_sqrt(fabsf(1.0f - dot(perp, perp)));
     return perp + parallel;
 }
 BT_DEV float fresnel(V3 d, V3 n, float ior) {                                       // math/mod.rs:50-55
     float cos_theta = fminf(dot(-d, n), 1.0f);
-    float r0 = (1.0f - ior) / (1.0f + ior);
+    float r0 = (1.0f - ior) * m_rcp(1.0f + ior);
     r0 = r0 * r0;
     float x = 1.0f - cos_theta;
     float x2 = x * x;
@@ -487,7 +538,7 @@ BT_DEV Surface resolve_hit(const float4* prims, const Hit& h, V3 o, V3 d) {
             s.normal = v3(0.0f, 0.0f, 0.0f);
             s.face = 2;
         } else {            // generate_surface_manifold, sphere.rs:85-119
-            V3 normal = (s.position - s.center) / q0.w;
+            V3 normal = m_div(s.position - s.center, q0.w);
             bool front = dot(d, normal) < 0.0f;
             s.normal = front ? normal : -normal;
             s.face = (s.vol >= 0 ? 3 : 0) + (front ? 0 : 1);

@@ -44,11 +44,15 @@ struct bt_engine {
     int clock_khz;
 };
 
+struct bt_scene;
+static bool use_exact(const bt_engine* e, const bt_scene* s);
+
 struct bt_scene {
     bt_engine* engine;
     Scene scene;
     FlatScene flat;
     int accel;          // ACCEL_AUTO / ACCEL_LINEAR / ACCEL_BVH
+    int precision;      // BT_PRECISION_AUTO / _FAST / _EXACT
     bool flat_dirty;    // host flattening out of date
     bool device_dirty;  // device copy out of date
     float4* d_blob;
@@ -56,6 +60,15 @@ struct bt_scene {
     float* d_grids;
     size_t grids_cap;
 };
+
+// Which arithmetic flavour of the kernels renders this scene.  AUTO: volumetric scenes are chaotic
+// in their rounding (steep density gradients turn a 1-ulp position difference into a flipped
+// scatter decision on ~5e-4 of the paths), so they get the bit-exact flavour; surface-only scenes
+// get the fast one (image MAE vs the oracle ~1e-8 .. 1e-5).
+static bool use_exact(const bt_engine*, const bt_scene* s) {
+    if (s->precision == BT_PRECISION_AUTO) return s->flat.header.has_volume_prims != 0;
+    return s->precision == BT_PRECISION_EXACT;
+}
 
 namespace {
 
@@ -233,6 +246,9 @@ int bt_scene_create_json(bt_engine* engine, const void* bytes, size_t n, bt_scen
     s->blob_cap = s->grids_cap = 0;
     try {
         s->accel = ACCEL_AUTO;
+        s->precision = BT_PRECISION_AUTO;
+        if (const char* e = std::getenv("BT_PRECISION"))
+            s->precision = !std::strcmp(e, "fast") ? BT_PRECISION_FAST : (!std::strcmp(e, "exact") ? BT_PRECISION_EXACT : BT_PRECISION_AUTO);
         s->scene = Scene::from_json(bytes, n);
         s->flat = flatten(s->scene, s->accel);
     } catch (...) {
@@ -336,6 +352,14 @@ int bt_scene_set_accel(bt_scene* scene, int accel) {
     return BT_OK;
 }
 
+int bt_scene_set_precision(bt_scene* scene, int precision) {
+    if (!scene) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    if (precision < BT_PRECISION_AUTO || precision > BT_PRECISION_EXACT)
+        return fail(BT_ERR_INVALID_ARG, "precision must be BT_PRECISION_AUTO, _FAST or _EXACT");
+    scene->precision = precision;
+    return BT_OK;
+}
+
 int bt_scene_get_info(const bt_scene* scene, bt_scene_info* info) {
     if (!scene || !info) return fail(BT_ERR_INVALID_ARG, "NULL argument");
     GUARD_BEGIN
@@ -399,7 +423,7 @@ int bt_render_async(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, con
     RenderParams p;
     if ((rcode = build_params(scene, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return rcode;
     p.fb = (float4*)rgba32f_device;
-    CK(launch_render(p, stream, &engine->launches));
+    CK(use_exact(engine, scene) ? launch_render_exact(p, stream, &engine->launches) : launch_render_fast(p, stream, &engine->launches));
     if (samples_inout) *samples_inout += rc->samples * p.sub_count;  // mod.rs:199
     *status = BT_STATUS_IN_PROGRESS;
     return BT_OK;
@@ -426,7 +450,7 @@ int bt_render_stats(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, con
     CK(cudaMemsetAsync(engine->d_scratch, 0, fb_bytes + 64, engine->stream));
     p.fb = (float4*)engine->d_scratch;
     p.stats = (unsigned long long*)((char*)engine->d_scratch + fb_bytes);
-    CK(launch_render(p, engine->stream, &engine->launches));
+    CK(use_exact(engine, scene) ? launch_render_exact(p, engine->stream, &engine->launches) : launch_render_fast(p, engine->stream, &engine->launches));
     unsigned long long host[4];
     CK(cudaMemcpyAsync(host, p.stats, sizeof host, cudaMemcpyDeviceToHost, engine->stream));
     CK(cudaStreamSynchronize(engine->stream));
@@ -510,7 +534,7 @@ int bt_trace_segments(bt_engine* engine, bt_scene* scene, const bt_config* confi
     char* base = (char*)engine->d_scratch;
     CK(cudaMemcpyAsync(base, origins, in_bytes, cudaMemcpyHostToDevice, engine->stream));
     CK(cudaMemcpyAsync(base + off_d, dirs, in_bytes, cudaMemcpyHostToDevice, engine->stream));
-    CK(launch_trace(p, n, (const float*)base, (const float*)(base + off_d), (DeviceSegment*)(base + off_o), engine->stream, &engine->launches));
+    CK((use_exact(engine, scene) ? launch_trace_exact : launch_trace_fast)(p, n, (const float*)base, (const float*)(base + off_d), (DeviceSegment*)(base + off_o), engine->stream, &engine->launches));
     std::vector<DeviceSegment> host(n);
     CK(cudaMemcpyAsync(host.data(), base + off_o, out_bytes, cudaMemcpyDeviceToHost, engine->stream));
     CK(cudaStreamSynchronize(engine->stream));
@@ -547,7 +571,7 @@ int bt_camera_rays(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, cons
     CK(cudaMemcpyAsync(base, xs, (size_t)n * 4, cudaMemcpyHostToDevice, engine->stream));
     CK(cudaMemcpyAsync(base + b32, ys, (size_t)n * 4, cudaMemcpyHostToDevice, engine->stream));
     CK(cudaMemcpyAsync(base + 2 * b32, path_index, (size_t)n * 8, cudaMemcpyHostToDevice, engine->stream));
-    CK(launch_camera_rays(p, n, (const uint32_t*)base, (const uint32_t*)(base + b32), (const uint64_t*)(base + 2 * b32),
+    CK((use_exact(engine, scene) ? launch_camera_rays_exact : launch_camera_rays_fast)(p, n, (const uint32_t*)base, (const uint32_t*)(base + b32), (const uint64_t*)(base + 2 * b32),
                           (float*)(base + 2 * b32 + b64), engine->stream, &engine->launches));
     CK(cudaMemcpyAsync(out, base + 2 * b32 + b64, bo, cudaMemcpyDeviceToHost, engine->stream));
     CK(cudaStreamSynchronize(engine->stream));

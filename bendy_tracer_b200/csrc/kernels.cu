@@ -9,6 +9,12 @@
 #include "device.cuh"
 #include "kernels.h"
 
+#ifdef BT_EXACT_SCAN
+#define BT_SFX(name) name##_exact
+#else
+#define BT_SFX(name) name##_fast
+#endif
+
 namespace bt {
 
 namespace {
@@ -368,9 +374,9 @@ BT_DEV void render_body(const RenderParams& p) {
                             dir0 = reflect(din, nrm);
                         } else {  // MAT_GLASS, material.rs:231-261
                             float ior = m1.y;
-                            if (s.face == 0) ior = 1.0f / ior;
+                            if (s.face == 0) ior = m_rcp(ior);
                             const float cos_theta = fminf(dot(-din, nrm), 1.0f);
-                            const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+                            const float sin_theta = m_sqrt(1.0f - cos_theta * cos_theta);
                             const float fr = fresnel(din, nrm, ior);
                             if (ior * sin_theta > 1.0f || gen_bool(rng, fr))
                                 dir0 = reflect(din, nrm);
@@ -384,7 +390,7 @@ BT_DEV void render_body(const RenderParams& p) {
                     if (!in_volume) vb = 0;  // entered from sample(): volume_bounce = 0
                     const V3 bmin = v3(s.center.x - s.radius, s.center.y - s.radius, s.center.z - s.radius);
                     const V3 bmax = v3(s.center.x + s.radius, s.center.y + s.radius, s.center.z + s.radius);
-                    const V3 coord = (s.position - bmin) / (bmax - bmin);
+                    const V3 coord = m_div(s.position - bmin, bmax - bmin);
                     const float density = p.volume_step * density_trilinear(sc.vols + s.vol * VOL_STRIDE, sc.grids, coord);
                     if (density >= 1.0f || gen_bool(rng, density)) {
                         vol_scatter = true;
@@ -409,11 +415,11 @@ BT_DEV void render_body(const RenderParams& p) {
             if (!rect) {
                 float s, c;
                 sincosf(r1, &s, &c);
-                const float w = sqrtf(sk == SK_COSINE ? r2 : r2 * (1.0f - r2));
+                const float w = m_sqrt(sk == SK_COSINE ? r2 : r2 * (1.0f - r2));
                 const float two = sk == SK_COSINE ? 1.0f : 2.0f;
                 cx = c * two * w;
                 sy = s * two * w;
-                z = sk == SK_COSINE ? sqrtf(1.0f - r2) : (sk == SK_HEMI ? 1.0f - r2 : 1.0f - 2.0f * r2);
+                z = sk == SK_COSINE ? m_sqrt(1.0f - r2) : (sk == SK_HEMI ? 1.0f - r2 : 1.0f - 2.0f * r2);
                 X = v3(1.0f, 0.0f, 0.0f);
                 Y = v3(0.0f, 1.0f, 0.0f);
                 Z = v3(0.0f, 0.0f, 1.0f);
@@ -477,7 +483,7 @@ BT_DEV void render_body(const RenderParams& p) {
                         aov_normal = nrm;
                         aov_depth = hit_t;
                     }
-                    T = T * ((A * mpdf) * (1.0f / pdf));
+                    T = T * ((A * mpdf) * m_rcp(pdf));
                     o = pos;
                     d = nd;
                     vol_obj = -1;
@@ -498,7 +504,7 @@ BT_DEV void render_body(const RenderParams& p) {
                 case 1: acc = acc + aov_albedo; break;
                 case 2: acc = acc + aov_normal; break;
                 default: {
-                    float dn = (aov_depth - p.clip_min) / (p.clip_max - p.clip_min);
+                    float dn = (aov_depth - p.clip_min) * m_rcp(p.clip_max - p.clip_min);
                     dn = fminf(fmaxf(dn, 0.0f), 1.0f);
                     acc = acc + v3(dn, dn, dn);
                 }
@@ -665,9 +671,12 @@ cudaError_t ensure_smem(K kernel, size_t bytes) {
 
 }  // namespace
 
+#ifndef BT_EXACT_SCAN
 size_t render_smem_bytes(const RenderParams& p) {
     return (size_t)p.scene.stage_f4 * sizeof(float4) + (p.scene.n_bvh ? (size_t)BVH_STACK * 256 * 2 * sizeof(uint32_t) : 0);
 }
+
+#endif
 
 // picks <LENS, EXACT, NL, BVH> from the scene header
 #define BT_LAUNCH_(KERNEL, L, E, N, B, GRID, BLOCK, SMEM, STREAM, ...)                                 \
@@ -687,7 +696,7 @@ size_t render_smem_bytes(const RenderParams& p) {
         else BT_LAUNCH_(KERNEL, true, true, 0, false, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);                                      \
     } while (0)
 
-cudaError_t launch_render(const RenderParams& p, cudaStream_t stream, uint64_t* launches) {
+cudaError_t BT_SFX(launch_render)(const RenderParams& p, cudaStream_t stream, uint64_t* launches) {
     dim3 grid((p.width + 15) / 16, (p.height + 15) / 16), block(256);
     size_t smem = render_smem_bytes(p);
     if (p.stats)
@@ -698,7 +707,7 @@ cudaError_t launch_render(const RenderParams& p, cudaStream_t stream, uint64_t* 
     return cudaGetLastError();
 }
 
-cudaError_t launch_trace(const RenderParams& p, uint32_t n, const float* origins, const float* dirs,
+cudaError_t BT_SFX(launch_trace)(const RenderParams& p, uint32_t n, const float* origins, const float* dirs,
                          DeviceSegment* out, cudaStream_t stream, uint64_t* launches) {
     if (n == 0) return cudaSuccess;
     size_t smem = render_smem_bytes(p);
@@ -707,7 +716,7 @@ cudaError_t launch_trace(const RenderParams& p, uint32_t n, const float* origins
     return cudaGetLastError();
 }
 
-cudaError_t launch_camera_rays(const RenderParams& p, uint32_t n, const uint32_t* xs, const uint32_t* ys,
+cudaError_t BT_SFX(launch_camera_rays)(const RenderParams& p, uint32_t n, const uint32_t* xs, const uint32_t* ys,
                                const uint64_t* path_index, float* out, cudaStream_t stream, uint64_t* launches) {
     if (n == 0) return cudaSuccess;
     camera_rays_kernel<<<(n + 255) / 256, 256, 0, stream>>>(p, n, xs, ys, path_index, out);
@@ -715,6 +724,7 @@ cudaError_t launch_camera_rays(const RenderParams& p, uint32_t n, const uint32_t
     return cudaGetLastError();
 }
 
+#ifndef BT_EXACT_SCAN
 cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t stream, uint64_t* launches) {
     if (p.n == 0) return cudaSuccess;
     size_t smem = (size_t)p.n_lens * LENS_STRIDE * sizeof(float4);
@@ -749,5 +759,7 @@ cudaError_t launch_fp32_peak(float* out, uint32_t iters, int blocks, cudaStream_
     ++*launches;
     return cudaGetLastError();
 }
+
+#endif  // !BT_EXACT_SCAN
 
 }  // namespace bt

@@ -24,12 +24,19 @@ struct IntegrateParams {
     uint32_t exact;       // correctly rounded rsqrt (bit-identical to the CPU oracle)
 };
 
-// each returns the cudaError_t of the launch; `launches` is incremented per kernel launched
-cudaError_t launch_render(const RenderParams& p, cudaStream_t stream, uint64_t* launches);
-cudaError_t launch_trace(const RenderParams& p, uint32_t n, const float* origins, const float* dirs,
-                         DeviceSegment* out, cudaStream_t stream, uint64_t* launches);
-cudaError_t launch_camera_rays(const RenderParams& p, uint32_t n, const uint32_t* xs, const uint32_t* ys,
-                               const uint64_t* path_index, float* out, cudaStream_t stream, uint64_t* launches);
+// Each returns the cudaError_t of the launch; `launches` is incremented per kernel launched.
+// kernels.cu is compiled twice: the `_fast` flavour (MUFU-based reciprocal / square roots, FMA rect
+// tests: ~1 ulp from IEEE) and the `_exact` flavour (-DBT_EXACT_SCAN: every operation is the IEEE
+// one the reference performs; bit-identical to the CPU oracle).  engine.cu picks per scene.
+#define BT_DECLARE_LAUNCHERS(SFX)                                                                                        \
+    cudaError_t launch_render##SFX(const RenderParams& p, cudaStream_t stream, uint64_t* launches);                      \
+    cudaError_t launch_trace##SFX(const RenderParams& p, uint32_t n, const float* origins, const float* dirs,           \
+                                  DeviceSegment* out, cudaStream_t stream, uint64_t* launches);                         \
+    cudaError_t launch_camera_rays##SFX(const RenderParams& p, uint32_t n, const uint32_t* xs, const uint32_t* ys,      \
+                                        const uint64_t* path_index, float* out, cudaStream_t stream, uint64_t* launches);
+BT_DECLARE_LAUNCHERS(_fast)
+BT_DECLARE_LAUNCHERS(_exact)
+#undef BT_DECLARE_LAUNCHERS
 cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t stream, uint64_t* launches);
 cudaError_t launch_resolve(const float4* fb, uint32_t n_pixels, uint64_t samples, int color_space, uchar4* out,
                            cudaStream_t stream, uint64_t* launches);

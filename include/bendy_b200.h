@@ -144,6 +144,15 @@ enum { BT_ACCEL_AUTO = 0, BT_ACCEL_LINEAR = 1, BT_ACCEL_BVH = 2,
        BT_ACCEL_LINEAR_FACES = 3 /* the scan with every Cuboid as its six Rect::hit tests (cuboid.rs:83-105, literally);
                                     the other modes test a box-shaped cuboid with one slab test */ };
 int bt_scene_set_accel(bt_scene* scene, int accel);
+/* Arithmetic flavour of the render / trace / camera-ray kernels for this scene.  EXACT: every
+ * division, square root and dot product is the IEEE operation sequence of the reference (values
+ * bit-identical to the CPU oracle up to libm's sin/cos/pow).  FAST: MUFU reciprocal / square
+ * roots and FMA-contracted rect tests, each within ~1 ulp (image MAE vs the oracle 1e-8 .. 1e-5 on
+ * surface scenes).  AUTO (default): EXACT for scenes with volumetric spheres -- their steep density
+ * gradients turn ulp-level differences into flipped scatter decisions -- FAST otherwise.
+ * Environment override for new scenes: BT_PRECISION=fast|exact|auto. */
+enum { BT_PRECISION_AUTO = 0, BT_PRECISION_FAST = 1, BT_PRECISION_EXACT = 2 };
+int bt_scene_set_precision(bt_scene* scene, int precision);
 int bt_scene_get_info(const bt_scene* scene, bt_scene_info* info);
 
 /* ---- the hot path ---------------------------------------------------------------------- */

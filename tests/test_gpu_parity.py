@@ -77,6 +77,32 @@ def test_render_parity(oracle, name, output):
         assert (mae <= 1e-4).all(), mae
 
 
+@pytest.mark.parametrize("name", SCENES)
+def test_arithmetic_flavours(oracle, name):
+    """The kernels exist in two arithmetic flavours (bt_scene_set_precision).  EXACT performs the
+    reference's IEEE operation sequence: the image equals the oracle's to rounding of libm's sin / cos
+    (MAE <= 1e-6, a handful of pixels).  FAST (MUFU reciprocal / square roots, FMA rect tests, ~1 ulp
+    each) is held to the north-star bar; on the volumetric scenes ulp-level differences flip scatter
+    decisions on ~5e-4 of the paths, which is why AUTO renders those with the exact flavour."""
+    w, h = 128, 72
+    osc, esc, cam = load_pair(name, w, h)
+    ref, n, _ = oracle_render(osc, cam, w, h, 2, 2, 0, seed=2)
+    esc.set_precision("exact")
+    exact = engine_render(esc, cam, w, h, 2, 2, 0, seed=2)[0].copy()
+    esc.set_precision("fast")
+    fast = engine_render(esc, cam, w, h, 2, 2, 0, seed=2)[0].copy()
+    esc.set_precision("auto")
+    auto = engine_render(esc, cam, w, h, 2, 2, 0, seed=2)[0].copy()
+    volumetric = name in ("cloud", "volume")
+    assert (mae_per_channel(exact, ref, n) <= 1e-6).all(), mae_per_channel(exact, ref, n)
+    d = np.abs(exact[..., :3] - ref[..., :3]).sum(-1) / n
+    assert (d > 1e-5).mean() < 2e-3
+    assert (mae_per_channel(fast, ref, n) <= IMAGE_MAE).all(), mae_per_channel(fast, ref, n)
+    if not volumetric:
+        assert (mae_per_channel(fast, ref, n) <= 1e-4).all(), mae_per_channel(fast, ref, n)
+    assert np.array_equal(auto, exact if volumetric else fast)
+
+
 def test_render_c1_cornell_512(oracle):
     """BASELINE config C1: cornell.json.gz 512x512 at 16 spp"""
     w = h = 512

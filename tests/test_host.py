@@ -157,6 +157,15 @@ def test_box_shaped_cuboids_are_recognised():
     assert bt.Scene.from_json(json.dumps(doc)).info()["n_boxes"] == 0
 
 
+def test_precision_and_accel_arguments():
+    s = bt.Scene.load(O.scene_path("cloud"))
+    for mode in ("auto", "fast", "exact"):
+        s.set_precision(mode)
+    assert _ffi.lib.bt_scene_set_precision(s.handle, 3) == _ffi.ERR_INVALID_ARG
+    assert _ffi.lib.bt_scene_set_accel(s.handle, 4) == _ffi.ERR_INVALID_ARG
+    assert _ffi.lib.bt_scene_set_accel(s.handle, 3) == _ffi.OK
+
+
 def test_camera_aspect_update():
     s = bt.Scene.load(O.scene_path("cornell"))
     s.set_camera_aspect(0, 1.7777778)
