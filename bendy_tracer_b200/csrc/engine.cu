@@ -164,6 +164,10 @@ int build_params(bt_scene* s, uint64_t camera_ref, bool need_camera, const bt_co
     p.compact_patience = 32;
     if (const char* e = std::getenv("BT_COMPACT_LANES")) p.compact_lanes = (uint32_t)std::atoi(e);
     if (const char* e = std::getenv("BT_COMPACT_PATIENCE")) p.compact_patience = (uint32_t)std::atoi(e);
+    p.regen_lanes = 12;
+    p.regen_patience = 16;
+    if (const char* e = std::getenv("BT_REGEN_LANES")) p.regen_lanes = (uint32_t)std::atoi(e);
+    if (const char* e = std::getenv("BT_REGEN_PATIENCE")) p.regen_patience = (uint32_t)std::atoi(e);
     p.scan_lanes = 12;
     p.scan_patience = 4;
     if (const char* e = std::getenv("BT_SCAN_LANES")) p.scan_lanes = (uint32_t)std::atoi(e);

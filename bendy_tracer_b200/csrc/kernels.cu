@@ -244,8 +244,17 @@ BT_DEV void render_body(const RenderParams& p) {
     float aov_depth = inf;
 
 #pragma unroll 1
+    uint32_t regen_waited = 0;
     for (;;) {
-        if (!alive && !done) {
+        // Regeneration phase (ray generation is ~400 instructions): run it for all idle lanes at once,
+        // and only when enough of them are idle -- in a warp that marches through a volume or flies
+        // long geodesics a lane ends a path every few iterations, and regenerating one lane at a time
+        // would execute this block nearly every iteration with 1/32 of the warp.
+        const unsigned m_idle = __ballot_sync(0xffffffffu, !alive && !done);
+        const bool regen = m_idle != 0 && ((uint32_t)__popc(m_idle) >= p.regen_lanes || ++regen_waited >= p.regen_patience ||
+                                           !__any_sync(0xffffffffu, alive));
+        if (regen) regen_waited = 0;
+        if (regen && !alive && !done) {
             if (path < p.paths_per_pixel) {
                 rng.seed_from_u64(splitmix_mix(pixel_key + 0xd1342543de82ef95ULL * (p.path_base + path + 1)));
                 camera_ray(p.cam, k, rng, px, py, path % p.sub_count, o, d);
