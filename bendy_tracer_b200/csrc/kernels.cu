@@ -423,7 +423,7 @@ BT_DEV void render_body(const RenderParams& p) {
             V3 X = v3(l1), Y = v3(l2), Z = v3(0.0f, 0.0f, 0.0f);
             if (!rect) {
                 float s, c;
-                sincosf(r1, &s, &c);
+                bt_sincos(r1, &s, &c);
                 const float w = m_sqrt(sk == SK_COSINE ? r2 : r2 * (1.0f - r2));
                 const float two = sk == SK_COSINE ? 1.0f : 2.0f;
                 cx = c * two * w;
