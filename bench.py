@@ -30,7 +30,11 @@ WORKLOADS = {
     "C3": ("scene", 3840, 2160, 16, 2, (1.362, 1.577, 6.114, 0.2)),
     "C4-cloud": ("cloud", 1920, 1080, 64, 2, None),
     "C4-volume": ("volume", 1920, 1080, 64, 2, None),
+    # strong scaling: the 1024 spp of ONE frame are split across the ranks (BASELINE configs[4])
+    "C5": ("scene", 7680, 4320, 256, 2, (1.362, 1.577, 6.114, 0.2)),
 }
+WORKLOADS["C5-128"] = ("scene", 7680, 4320, 32, 2, (1.362, 1.577, 6.114, 0.2))   # the C5 frame at 128 spp (a sweep that fits 1 GPU)
+STRONG = {"C5", "C5-128"}
 METRIC = "Msamples/s"
 SCENE_DIR = os.path.join(ROOT, "tests", "golden", "scenes")
 FLOPS_RECT, FLOPS_SPHERE = 35, 25      # SURVEY 8d per-test algorithmic flops
@@ -91,18 +95,22 @@ def load_oracle_scene(name):
 
 
 def cpu_sample(name, passes):
-    """the reference algorithm (CPU restatement, all host threads) on `passes` passes of the frame"""
+    """the reference algorithm (CPU restatement, all host threads) on `passes` passes of the frame
+    (frames above 1080p are sampled at 1920x1080 with the same camera: throughput per sample is
+    resolution-independent, and the CPU leg has to stay within tens of seconds)"""
     O, osc, cam = load_oracle_scene(name)
     scene, w, h, _, sub, _ = WORKLOADS[name]
+    if w * h > 1920 * 1080:
+        w, h = 1920, 1080
     cores = os.cpu_count() or 1
     cfg = O.make_config(samples=passes, subsample=sub)
     t0 = time.perf_counter()
     _, n, _ = osc.render(cam, cfg, w, h, seed=0, n_threads=cores)
     dt = time.perf_counter() - t0
-    return w * h * n / dt / 1e6, cores, n, dt
+    return w * h * n / dt / 1e6, cores, n, dt, (w, h)
 
 
-def run_reference(args):
+def run_reference(args, json_out):
     """--impl reference: the reference's CPU implementation of the path on the box's host cores"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -114,12 +122,12 @@ def run_reference(args):
         cpu_sample(name, passes)
     vals, t = [], 0.0
     for _ in range(args.steps):
-        v, cores, n, dt = cpu_sample(name, passes)
+        v, cores, n, dt, (sw, sh) = cpu_sample(name, passes)
         vals.append(v)
         t += dt
-    value = d["width"] * d["height"] * n * args.steps / t / 1e6
-    sample = f"{n} spp of the {d['width']}x{d['height']} frame per step (the full step is {d['spp']} spp)"
-    print(json.dumps({
+    value = sw * sh * n * args.steps / t / 1e6
+    sample = f"{n} spp of the frame at {sw}x{sh} per step (the full step is {d['spp']} spp at {d['width']}x{d['height']})"
+    json_out.write(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -127,7 +135,16 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": METRIC, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference algorithm restated in C++ (oracle/), all host threads; the Rust crate cannot be built here",
-    }))
+    }) + "\n")
+    json_out.flush()
+
+
+def algorithmic_flops(st, scene_name, n_lens):
+    """SURVEY 8d accounting of the work counters of one render call"""
+    n_rect, n_sph = PRIMS[scene_name]
+    fl_scan = n_rect * FLOPS_RECT + n_sph * FLOPS_SPHERE
+    fl_step = 136 * n_lens + 78 if n_lens else 0
+    return st["scans"] * fl_scan + st["rk4_steps"] * fl_step, fl_scan, fl_step
 
 
 def stepper_roofline(engine, torch, peak_tflops, n_rays=1 << 22, n_steps=512):
@@ -163,6 +180,11 @@ def stepper_roofline(engine, torch, peak_tflops, n_rays=1 << 22, n_steps=512):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: anything a library prints on fd 1 meanwhile (NCCL's version
+    # banner under NCCL_DEBUG=VERSION, ...) is sent to stderr instead
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -172,7 +194,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / stepper roofline / e2e legs")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, json_out)
 
     import torch
     import torch.distributed as dist
@@ -197,6 +219,11 @@ def main():
         scene.set_lenses(np.array([lens], np.float32))
     engine = bt.Engine.default(local)
     tracer = bt.Tracer(bt.Config(chunks_x=8, chunks_y=4), engine=engine, seed=0)
+    strong = name in STRONG
+    if strong:
+        if passes % world:
+            raise SystemExit(f"{name}: {passes} passes do not split across {world} ranks")
+        passes //= world                      # this rank's share of the frame's passes
     rc = bt.RenderConfig.with_samples_subsample(passes, bt.Subsample(sub))
     frame = bt.Buffer(w, h, device=dev)       # this rank's slice of the frame
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -238,15 +265,17 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    samples_per_step = w * h * d["spp"] * world
+    samples_per_step = w * h * d["spp"] * (1 if strong else world)
     value = samples_per_step * args.steps / (ms * 1e-3) / 1e6
 
     result = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": d["workload"] + (f"; each of {world} ranks renders its own {d['spp']}-spp pass slice, "
-                                                 "one NCCL reduce per step" if world > 1 else ""),
+        "config": {"workload": d["workload"] + ((f"; the {d['spp']} spp are split across {world} ranks ({passes * sub * sub} spp each), "
+                                                  "one NCCL reduce per step" if strong else
+                                                  f"; each of {world} ranks renders its own {d['spp']}-spp pass slice, "
+                                                  "one NCCL reduce per step") if world > 1 else ""),
                    "l2": "256 MiB device memset between timed steps (L2 flush)", "seed": 0,
                    "timing": "CUDA events per step on torch's current stream (the launch stream), summed; max over ranks"},
         "gpu_launches": launches, "clocks": clocks, "wall_s": t_wall,
@@ -281,9 +310,7 @@ def main():
         # exact work counters of the first timed step (deterministic paths): an instrumented copy of
         # the kernel, run outside the timed region
         st = tracer.render_stats(scene, cam, rc, w, h, sample_base=args.warmup * world * passes)
-        n_rect, n_sph = PRIMS[scene_name]
-        n_lens = 1 if lens else 0
-        flops = st["scans"] * (n_rect * FLOPS_RECT + n_sph * FLOPS_SPHERE) + st["rk4_steps"] * (136 * n_lens + 78 if n_lens else 0)
+        flops, fl_scan, fl_step = algorithmic_flops(st, scene_name, 1 if lens else 0)
         step_s = ms / args.steps * 1e-3
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -295,11 +322,12 @@ def main():
             "bound": "fp32", "kernel": "render_kernel", "unit": "TFLOP/s", "peak": peak,
             "achieved": flops / step_s / 1e12, "frac": flops / step_s / 1e12 / peak, "traffic": traffic,
             "work": {**st, "segments_per_path": st["events"] / max(st["paths"], 1),
-                     "flops_per_scan": n_rect * FLOPS_RECT + n_sph * FLOPS_SPHERE, "flops_per_rk4_step": 136 * n_lens + 78 if n_lens else 0},
+                     "flops_per_scan": fl_scan, "flops_per_rk4_step": fl_step},
             "note": "CUDA-core FP32 issue bound (no dense contraction on this path: neither the hbm nor the tensor "
-                    "roofline binds); achieved = algorithmic flops (SURVEY 8d: 35 per rect test, 25 per sphere test, "
-                    "136M+78 per RK4 step; shading, RNG and ray generation count as 0) / CUDA-event step time; "
-                    "peak = live FMA-chain measurement (of measured)",
+                    "roofline binds); achieved = algorithmic flops of the work EXECUTED (SURVEY 8d: a scan = every "
+                    "primitive of the reference's try_hit loop, 35 flops per rect test -- a cuboid is six -- and 25 per "
+                    "sphere test; 136M+78 per RK4 step; chords skipped by the free-distance test, shading, RNG and ray "
+                    "generation count as 0) / CUDA-event step time; peak = live FMA-chain measurement",
             "hbm": {"algorithmic_bytes_per_launch": w * h * 32, "achieved_gbs": w * h * 32 / step_s / 1e9,
                     "peak_gbs": hbm_peak, "peak_source": hbm_src},
         }
@@ -328,8 +356,17 @@ def main():
                 torch.cuda.synchronize()
                 t_ms = e0.elapsed_time(e1)
                 best = t_ms if best is None else min(best, t_ms)
+            # work counters from one pass (per-path averages are stable), scaled to the timed call
+            ost = tracer.render_stats(osc, ocam, bt.RenderConfig.with_samples_subsample(1, bt.Subsample(osub)), ow, oh, sample_base=op)
+            oflops, _, _ = algorithmic_flops(ost, sn, 1 if olens else 0)
+            scale = ow * oh * describe(other)["spp"] / max(ost["paths"], 1)
+            tf = oflops * scale / (best * 1e-3) / 1e12
             scenes[other] = {"workload": describe(other)["workload"], "ms": best,
-                             "Msamples_per_s": ow * oh * describe(other)["spp"] / best / 1e3}
+                             "Msamples_per_s": ow * oh * describe(other)["spp"] / best / 1e3,
+                             "segments_per_path": ost["events"] / max(ost["paths"], 1),
+                             "scans_per_path": ost["scans"] / max(ost["paths"], 1),
+                             "rk4_steps_per_path": ost["rk4_steps"] / max(ost["paths"], 1),
+                             "fp32_tflops": tf, "fp32_frac": tf / peak}
             del obuf
         # ---- synthetic many-primitive scene: the BVH path (global-memory nodes, shared-memory stack) ----
         import json as _json
@@ -355,11 +392,12 @@ def main():
                                        f"{sw}x{sh} at {sp * 4} spp", "ms": best, "Msamples_per_s": sw * sh * sp * 4 / best / 1e3}
         result["scenes"] = scenes
         # ---- CPU baseline: the reference algorithm's restatement on this box's host cores ----
-        v, cores, n, dt = cpu_sample(name, 4)
+        v, cores, n, dt, (sw, sh) = cpu_sample(name, 4 if not lens else 1)
         result["cpu_baseline"] = {"value": v, "unit": METRIC, "cores": cores, "kind": "port",
-                                  "sample": f"{n} spp of the {w}x{h} frame ({dt:.1f} s wall on {cores} threads)"}
+                                  "sample": f"{n} spp of the frame at {sw}x{sh} ({dt:.1f} s wall on {cores} threads)"}
     if rank == 0:
-        print(json.dumps(result))
+        json_out.write(json.dumps(result) + "\n")
+        json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 
