@@ -478,65 +478,71 @@ BT_DEV Hit bvh_closest(const float4* __restrict__ prims, const float4* __restric
     const uint32_t lanes = blockDim.x, tid = threadIdx.x;
     float* stack_t = reinterpret_cast<float*>(stack + BVH_STACK * lanes);
     uint32_t sp = 0, cur = 0;  // node 0 is always an inner node
+    const uint32_t DONE = 0xffffffffu;  // (leaf bit set: ends the descent loop)
+    // pop, skipping subtrees that start beyond the hit found since they were pushed
+#define BT_BVH_POP()                                         \
+    for (;;) {                                               \
+        if (sp == 0) {                                       \
+            cur = DONE;                                      \
+            break;                                           \
+        }                                                    \
+        --sp;                                                \
+        cur = stack[sp * lanes + tid];                       \
+        if (stack_t[sp * lanes + tid] <= h.t) break;         \
+    }
+    // "while-while" traversal: every lane first descends inner nodes until it holds a leaf (lanes that
+    // already do wait), then all lanes test their leaves -- the two phases never interleave inside a
+    // warp, which is what keeps it converged for incoherent rays.
     for (;;) {
-        if (cur & BVH_LEAF) {
-            const uint32_t first = cur & 0x00ffffffu, count = (cur >> 24) & 0x7fu;
-            for (uint32_t i = first; i < first + count; ++i) {
-                const float4* q = prims + i * PRIM_STRIDE;
-                const int meta = __float_as_int(__ldg(q + 4).x);
-                const int type = meta & 3, canon = meta >> 2;
-                const bool strict = type == PRIM_CUBOID_FACE;
-                float t;
-                bool front = true, ok;
-                if (type == PRIM_SPHERE)
-                    ok = sphere_roots(__ldg(q), __ldg(q + 1).x, o, d, tmin, h.t, t);
-                else
-                    ok = rect_test(q, o, d, tmin, h.t, false, t, front);
-                if (ok) {
-                    // t <= h.t here.  Equal distance: the later canonical index wins unless strict.
-                    bool take = t < h.t;
-                    if (!take) take = canon > best_canon ? !strict : best_strict;
-                    if (take) {
-                        h.t = t;
-                        h.prim = (int)i;
-                        h.face = type == PRIM_SPHERE ? 8 : (front ? 0 : 1);
-                        best_canon = canon;
-                        best_strict = strict;
-                    }
+        while (!(cur & BVH_LEAF)) {
+            const float4* n = nodes + cur * BVH_STRIDE;
+            const float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3);
+            bool hl, hr;
+            const float tl = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, tmin, h.t, hl);
+            const float tr = slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, tmin, h.t, hr);
+            const uint32_t left = __float_as_uint(n3.x), right = __float_as_uint(n3.y);
+            if (hl && hr) {
+                const bool left_first = tl <= tr;
+                stack[sp * lanes + tid] = left_first ? right : left;
+                stack_t[sp * lanes + tid] = left_first ? tr : tl;
+                ++sp;
+                cur = left_first ? left : right;
+            } else if (hl || hr) {
+                cur = hl ? left : right;
+            } else {
+                BT_BVH_POP()
+            }
+        }
+        if (cur == DONE) break;
+        const uint32_t first = cur & 0x00ffffffu, count = (cur >> 24) & 0x7fu;
+        for (uint32_t i = first; i < first + count; ++i) {
+            const float4* q = prims + i * PRIM_STRIDE;
+            const int meta = __float_as_int(__ldg(q + 4).x);
+            const int type = meta & 3, canon = meta >> 2;
+            const bool strict = type == PRIM_CUBOID_FACE;
+            float t;
+            bool front = true, ok;
+            if (type == PRIM_SPHERE)
+                ok = sphere_roots(__ldg(q), __ldg(q + 1).x, o, d, tmin, h.t, t);
+            else
+                ok = rect_test(q, o, d, tmin, h.t, false, t, front);
+            if (ok) {
+                // t <= h.t here.  Equal distance: the later canonical index wins unless strict.
+                bool take = t < h.t;
+                if (!take) take = canon > best_canon ? !strict : best_strict;
+                if (take) {
+                    h.t = t;
+                    h.prim = (int)i;
+                    h.face = type == PRIM_SPHERE ? 8 : (front ? 0 : 1);
+                    best_canon = canon;
+                    best_strict = strict;
                 }
             }
-            // pop, skipping subtrees that start beyond the hit found since they were pushed
-            for (;;) {
-                if (sp == 0) return h;
-                --sp;
-                cur = stack[sp * lanes + tid];
-                if (stack_t[sp * lanes + tid] <= h.t) break;
-            }
-            continue;
         }
-        const float4* n = nodes + cur * BVH_STRIDE;
-        const float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3);
-        bool hl, hr;
-        const float tl = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, tmin, h.t, hl);
-        const float tr = slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, tmin, h.t, hr);
-        const uint32_t left = __float_as_uint(n3.x), right = __float_as_uint(n3.y);
-        if (hl && hr) {
-            const bool left_first = tl <= tr;
-            stack[sp * lanes + tid] = left_first ? right : left;
-            stack_t[sp * lanes + tid] = left_first ? tr : tl;
-            ++sp;
-            cur = left_first ? left : right;
-        } else if (hl || hr) {
-            cur = hl ? left : right;
-        } else {
-            for (;;) {
-                if (sp == 0) return h;
-                --sp;
-                cur = stack[sp * lanes + tid];
-                if (stack_t[sp * lanes + tid] <= h.t) break;
-            }
-        }
+        BT_BVH_POP()
     }
+#undef BT_BVH_POP
+    return h;
 }
 
 struct Surface {  // Manifold (ray.rs:36-47) reduced to what shading reads
