@@ -466,83 +466,104 @@ BT_DEV float slab(float lx, float ly, float lz, float hx, float hy, float hz, V3
     hit = tnear <= tfar * 1.00001f + 1e-6f;  // inclusive and slightly generous: never cull a scan hit
     return tnear;
 }
-BT_DEV Hit bvh_closest(const float4* __restrict__ prims, const float4* __restrict__ nodes, uint32_t* stack, V3 o, V3 d,
-                       float tmin, float tmax) {
+// A closest-hit traversal in progress (resumable: the render kernel advances all lanes of a warp one
+// unit at a time and leaves the loop when enough of them are done -- step compaction, as for the
+// geodesic flights).
+struct BvhTrav {
+    uint32_t cur, sp;
     Hit h;
-    h.t = tmax;
-    h.prim = -1;
-    h.face = 0;
-    int best_canon = -1;
-    bool best_strict = false;
-    const V3 inv = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    int best_canon;
+    bool best_strict;
+};
+enum : uint32_t { BVH_DONE = 0xffffffffu };  // (leaf bit set: ends the descent loop)
+BT_DEV void bvh_begin(BvhTrav& t, float tmax) {
+    t.cur = 0;  // node 0 is always an inner node
+    t.sp = 0;
+    t.h.t = tmax;
+    t.h.prim = -1;
+    t.h.face = 0;
+    t.best_canon = -1;
+    t.best_strict = false;
+}
+// One unit of "while-while" traversal: descend inner nodes until a leaf is held, test the leaf, pop.
+// Inside a warp the two phases never interleave, which keeps it converged for incoherent rays.
+// Returns true when the traversal is complete (t.h is the closest hit).
+BT_DEV bool bvh_unit(BvhTrav& t, const float4* __restrict__ prims, const float4* __restrict__ nodes, uint32_t* stack, V3 o, V3 d,
+                     float tmin) {
+    const V3 inv = v3(m_rcp(d.x), m_rcp(d.y), m_rcp(d.z));
     const uint32_t lanes = blockDim.x, tid = threadIdx.x;
     float* stack_t = reinterpret_cast<float*>(stack + BVH_STACK * lanes);
-    uint32_t sp = 0, cur = 0;  // node 0 is always an inner node
-    const uint32_t DONE = 0xffffffffu;  // (leaf bit set: ends the descent loop)
+    uint32_t cur = t.cur, sp = t.sp;
     // pop, skipping subtrees that start beyond the hit found since they were pushed
 #define BT_BVH_POP()                                         \
     for (;;) {                                               \
         if (sp == 0) {                                       \
-            cur = DONE;                                      \
+            cur = BVH_DONE;                                  \
             break;                                           \
         }                                                    \
         --sp;                                                \
         cur = stack[sp * lanes + tid];                       \
-        if (stack_t[sp * lanes + tid] <= h.t) break;         \
+        if (stack_t[sp * lanes + tid] <= t.h.t) break;       \
     }
-    // "while-while" traversal: every lane first descends inner nodes until it holds a leaf (lanes that
-    // already do wait), then all lanes test their leaves -- the two phases never interleave inside a
-    // warp, which is what keeps it converged for incoherent rays.
-    for (;;) {
-        while (!(cur & BVH_LEAF)) {
-            const float4* n = nodes + cur * BVH_STRIDE;
-            const float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3);
-            bool hl, hr;
-            const float tl = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, tmin, h.t, hl);
-            const float tr = slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, tmin, h.t, hr);
-            const uint32_t left = __float_as_uint(n3.x), right = __float_as_uint(n3.y);
-            if (hl && hr) {
-                const bool left_first = tl <= tr;
-                stack[sp * lanes + tid] = left_first ? right : left;
-                stack_t[sp * lanes + tid] = left_first ? tr : tl;
-                ++sp;
-                cur = left_first ? left : right;
-            } else if (hl || hr) {
-                cur = hl ? left : right;
-            } else {
-                BT_BVH_POP()
-            }
+    while (!(cur & BVH_LEAF)) {
+        const float4* n = nodes + cur * BVH_STRIDE;
+        const float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3);
+        bool hl, hr;
+        const float tl = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, tmin, t.h.t, hl);
+        const float tr = slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, tmin, t.h.t, hr);
+        const uint32_t left = __float_as_uint(n3.x), right = __float_as_uint(n3.y);
+        if (hl && hr) {
+            const bool left_first = tl <= tr;
+            stack[sp * lanes + tid] = left_first ? right : left;
+            stack_t[sp * lanes + tid] = left_first ? tr : tl;
+            ++sp;
+            cur = left_first ? left : right;
+        } else if (hl || hr) {
+            cur = hl ? left : right;
+        } else {
+            BT_BVH_POP()
         }
-        if (cur == DONE) break;
+    }
+    if (cur != BVH_DONE) {
         const uint32_t first = cur & 0x00ffffffu, count = (cur >> 24) & 0x7fu;
         for (uint32_t i = first; i < first + count; ++i) {
             const float4* q = prims + i * PRIM_STRIDE;
             const int meta = __float_as_int(__ldg(q + 4).x);
             const int type = meta & 3, canon = meta >> 2;
             const bool strict = type == PRIM_CUBOID_FACE;
-            float t;
+            float tt;
             bool front = true, ok;
             if (type == PRIM_SPHERE)
-                ok = sphere_roots(__ldg(q), __ldg(q + 1).x, o, d, tmin, h.t, t);
+                ok = sphere_roots(__ldg(q), __ldg(q + 1).x, o, d, tmin, t.h.t, tt);
             else
-                ok = rect_test(q, o, d, tmin, h.t, false, t, front);
+                ok = rect_test(q, o, d, tmin, t.h.t, false, tt, front);
             if (ok) {
-                // t <= h.t here.  Equal distance: the later canonical index wins unless strict.
-                bool take = t < h.t;
-                if (!take) take = canon > best_canon ? !strict : best_strict;
+                // tt <= h.t here.  Equal distance: the later canonical index wins unless strict.
+                bool take = tt < t.h.t;
+                if (!take) take = canon > t.best_canon ? !strict : t.best_strict;
                 if (take) {
-                    h.t = t;
-                    h.prim = (int)i;
-                    h.face = type == PRIM_SPHERE ? 8 : (front ? 0 : 1);
-                    best_canon = canon;
-                    best_strict = strict;
+                    t.h.t = tt;
+                    t.h.prim = (int)i;
+                    t.h.face = type == PRIM_SPHERE ? 8 : (front ? 0 : 1);
+                    t.best_canon = canon;
+                    t.best_strict = strict;
                 }
             }
         }
         BT_BVH_POP()
     }
 #undef BT_BVH_POP
-    return h;
+    t.cur = cur;
+    t.sp = sp;
+    return cur == BVH_DONE;
+}
+BT_DEV Hit bvh_closest(const float4* __restrict__ prims, const float4* __restrict__ nodes, uint32_t* stack, V3 o, V3 d,
+                       float tmin, float tmax) {
+    BvhTrav t;
+    bvh_begin(t, tmax);
+    while (!bvh_unit(t, prims, nodes, stack, o, d, tmin)) {
+    }
+    return t.h;
 }
 
 struct Surface {  // Manifold (ray.rs:36-47) reduced to what shading reads

@@ -239,6 +239,9 @@ BT_DEV void render_body(const RenderParams& p) {
     Flight fl;  // LENS: the geodesic this lane is flying (x, v alias o, d)
     flight_reset(fl);
     int fstate = FL_FLY;
+    BvhTrav btrav;  // BVH && !LENS: the traversal this lane is in
+    bvh_begin(btrav, 0.0f);
+    int bstate = 0;  // 0 none, 1 traversing, 2 done
     bool latched = false;
     V3 aov_albedo, aov_normal;
     float aov_depth = inf;
@@ -297,7 +300,35 @@ BT_DEV void render_body(const RenderParams& p) {
         // segment; lanes still in flight keep their phase and resume next time.
         Traced tr;
         bool has_event = false;
-        if (alive && (!LENS || in_volume)) {
+        if (BVH && !LENS) {
+            // BVH step compaction: every lane advances its traversal one unit (descend to a leaf, test
+            // it, pop) per turn; the warp leaves to shade once enough lanes are done, the others resume.
+            // (Scenes with volumetric spheres never use the BVH, so every segment here is a full ray.)
+            if (alive && bstate == 0) {
+                bvh_begin(btrav, p.clip_max);
+                bstate = 1;
+            }
+            uint32_t waited = 0;
+#pragma unroll 1
+            for (;;) {
+                if (bstate == 1 && bvh_unit(btrav, sc.prims, sc.nodes, sc.stack, o, d, p.clip_min)) bstate = 2;
+                const unsigned m_trav = __ballot_sync(0xffffffffu, bstate == 1);
+                if (m_trav == 0) break;
+                const unsigned m_done = __ballot_sync(0xffffffffu, bstate == 2);
+                if (m_done != 0 && ((uint32_t)__popc(m_done) >= p.compact_lanes || ++waited >= p.compact_patience)) break;
+            }
+            if (bstate == 2) {
+                tr.h = btrav.h;
+                tr.o = o;
+                tr.d = d;
+                tr.t_total = btrav.h.t;
+                tr.steps = 0;
+                tr.scans = 1;
+                tr.captured = false;
+                has_event = true;
+                bstate = 0;
+            }
+        } else if (alive && (!LENS || in_volume)) {
             tr = trace_straight<BVH>(p, sc, o, d, in_volume ? 0.0f : p.clip_min, in_volume ? p.volume_step : p.clip_max, vol_obj);
             has_event = true;
         }
