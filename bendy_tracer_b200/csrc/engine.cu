@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -161,7 +162,7 @@ int build_params(bt_scene* s, uint64_t camera_ref, bool need_camera, const bt_co
     p.clip_max = m.clip_max;
     p.volume_step = m.volume_step;
     p.compact_lanes = 16;
-    p.compact_patience = 32;
+    p.compact_patience = 16;
     if (const char* e = std::getenv("BT_COMPACT_LANES")) p.compact_lanes = (uint32_t)std::atoi(e);
     if (const char* e = std::getenv("BT_COMPACT_PATIENCE")) p.compact_patience = (uint32_t)std::atoi(e);
     p.regen_lanes = 12;
@@ -169,10 +170,12 @@ int build_params(bt_scene* s, uint64_t camera_ref, bool need_camera, const bt_co
     if (const char* e = std::getenv("BT_REGEN_LANES")) p.regen_lanes = (uint32_t)std::atoi(e);
     if (const char* e = std::getenv("BT_REGEN_PATIENCE")) p.regen_patience = (uint32_t)std::atoi(e);
     p.scan_lanes = 12;
-    p.scan_patience = 4;
+    p.scan_patience = 2;
     if (const char* e = std::getenv("BT_SCAN_LANES")) p.scan_lanes = (uint32_t)std::atoi(e);
     if (const char* e = std::getenv("BT_SCAN_PATIENCE")) p.scan_patience = (uint32_t)std::atoi(e);
     if (std::getenv("BT_LENS_NO_SKIP")) p.scene.lens_skip = 0;
+    p.steps_per_turn = 2;
+    if (const char* e = std::getenv("BT_STEPS_PER_TURN")) p.steps_per_turn = (uint32_t)std::max(1, std::atoi(e));
     p.tau_scale = uniform_scale_inclusive(0.0f, 6.28318530717958647692f);
     p.one_scale = uniform_scale_inclusive(0.0f, 1.0f);
     *out = p;

@@ -219,7 +219,7 @@ BT_DEV void render_body(const RenderParams& p) {
     // block = 16x16 pixels, warp = 8x4 pixel tile (coherent first hits, 128 B framebuffer rows)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const uint32_t py = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+    const uint32_t py = blockIdx.y * (blockDim.x >> 4) + (warp >> 1) * 4 + (lane >> 3);  // 256 threads: 16 rows, 128: 8
     const bool valid = px < p.width && py < p.height;
     const uint64_t pixel = (uint64_t)py * p.width + px;
     const float inf = __int_as_float(0x7f800000);
@@ -338,7 +338,9 @@ BT_DEV void render_body(const RenderParams& p) {
             uint32_t waited = 0, scan_waited = 0;
 #pragma unroll 1
             for (;;) {
-                if (ls == FL_FLY) ls = geodesic_step<EXACT>(p, lens, o, d, fl, p.clip_max);
+#pragma unroll 1
+                for (uint32_t r = 0; r < p.steps_per_turn; ++r)  // several steps per turn amortise the ballots below
+                    if (ls == FL_FLY) ls = geodesic_step<EXACT>(p, lens, o, d, fl, p.clip_max);
                 const bool pend = ls == FL_PEND || ls == FL_PEND_FAR;
                 unsigned m_pend = __ballot_sync(0xffffffffu, pend);
                 unsigned m_fly = __ballot_sync(0xffffffffu, ls == FL_FLY);
@@ -572,8 +574,10 @@ BT_DEV void render_body(const RenderParams& p) {
     }
 }
 
+// Lensed variants carry the flight state on top of the path state: 128-thread CTAs at 5 per SM give
+// them 96 registers (20 warps / SM) instead of 80 with spills (24 warps / SM).
 template <bool LENS, bool EXACT, int NL, bool BVH>
-__global__ void __launch_bounds__(256, 3) render_kernel(const __grid_constant__ RenderParams p) {
+__global__ void __launch_bounds__(LENS ? 128 : 256, LENS ? 5 : 3) render_kernel(const __grid_constant__ RenderParams p) {
     render_body<false, LENS, EXACT, NL, BVH>(p);
 }
 // the same kernel + work counters for bench.py's roofline accounting (never timed)
@@ -737,7 +741,8 @@ size_t render_smem_bytes(const RenderParams& p) {
     } while (0)
 
 cudaError_t BT_SFX(launch_render)(const RenderParams& p, cudaStream_t stream, uint64_t* launches) {
-    dim3 grid((p.width + 15) / 16, (p.height + 15) / 16), block(256);
+    const bool small = p.scene.n_lens != 0 && !p.stats;
+    dim3 grid((p.width + 15) / 16, small ? (p.height + 7) / 8 : (p.height + 15) / 16), block(small ? 128 : 256);
     size_t smem = render_smem_bytes(p);
     if (p.stats)
         BT_DISPATCH_LENS(render_kernel_stats, grid, block, smem, stream, p);

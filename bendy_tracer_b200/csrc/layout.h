@@ -109,7 +109,8 @@ struct RenderParams {
     float tau_scale, one_scale;      // Uniform::new_inclusive(0, TAU).scale, (0, 1).scale
     uint32_t compact_lanes, compact_patience;  // per-warp step compaction thresholds (LENS kernels)
     uint32_t regen_lanes, regen_patience;      // idle lanes a warp collects before it runs the ray-generation phase
-    uint32_t scan_lanes, scan_patience;        // pending chords a warp collects before it runs the intersection phase
+    uint32_t scan_lanes, scan_patience;
+    uint32_t steps_per_turn;                   // RK4 steps a flying lane takes between two rounds of ballots        // pending chords a warp collects before it runs the intersection phase
     unsigned long long* stats;       // render_kernel_stats only: {paths, scan calls, RK4 steps, events}
 };
 
