@@ -372,7 +372,12 @@ BT_DEV bool box_test(const float4* b, V3 o, V3 d, float tmin, float tmax, float&
 // nearest primitive surface (spheres: ||o - c| - r|; rects: L-infinity distance to the world
 // AABB), minus a margin that covers the rounding of the hit tests themselves -- a ray that starts
 // at `o` cannot be reported as hitting anything within that distance (the stepper's chord skip).
-template <bool DIST>
+// C: what the scene contains -- a kernel compiled for a scene without rects carries no rect / box
+// code, one without volumetric spheres no march code, one without Glass no Fresnel / refraction.
+// The render loop's body has to stay near the 32 KB instruction cache; every shipped scene gets a
+// variant without the code it cannot reach (kernels.cu: launch_render).
+enum { CT_SPHERES = 1, CT_RECTS = 2, CT_VOLUMES = 4, CT_METAL = 8, CT_GLASS = 16, CT_ALL = 31 };
+template <bool DIST, int C = CT_ALL>
 BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, const float4* boxes, int n_prims, V3 o, V3 d, float tmin,
                         float tmax, int volume_obj, float* free_out) {
     (void)bounds;
@@ -386,11 +391,11 @@ BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, const float4*
         const float4* q = prims + i * PRIM_STRIDE;
         float4 meta = q[4];
         int type = __float_as_int(meta.x) & 3;
-        if (type == PRIM_SPHERE) {
+        if ((C & CT_SPHERES) && (!(C & CT_RECTS) || type == PRIM_SPHERE)) {
             float4 q0 = q[0];
             const float4 q1 = q[1];
             float r2 = q1.x;
-            if (!DIST && volume_obj >= 0 && __float_as_int(meta.w) == volume_obj) {
+            if ((C & CT_VOLUMES) && !DIST && volume_obj >= 0 && __float_as_int(meta.w) == volume_obj) {
                 // Sphere::hit_volumetric, sphere.rs:150-166
                 V3 e = (o + h.t * d) - v3(q0);
                 if (dot(e, e) <= r2) {
@@ -415,7 +420,7 @@ BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, const float4*
                 h.prim = i;
                 h.face = 8;  // resolved after the scan (needs the normal)
             }
-        } else {
+        } else if (C & CT_RECTS) {
             float t;
             bool front;
             if (type == PRIM_CUBOID_FACE && __float_as_int(meta.z) > 0) {
@@ -448,8 +453,9 @@ BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, const float4*
     if (DIST) *free_out = free;
     return h;
 }
+template <int C = CT_ALL>
 BT_DEV Hit scan_prims(const float4* prims, const float4* boxes, int n_prims, V3 o, V3 d, float tmin, float tmax, int volume_obj) {
-    return scan_prims_t<false>(prims, nullptr, boxes, n_prims, o, d, tmin, tmax, volume_obj, nullptr);
+    return scan_prims_t<false, C>(prims, nullptr, boxes, n_prims, o, d, tmin, tmax, volume_obj, nullptr);
 }
 
 // Closest hit through the BVH (extension; scenes above the linear-scan budget).  Records and
@@ -572,6 +578,7 @@ struct Surface {  // Manifold (ray.rs:36-47) reduced to what shading reads
     V3 center;   // sphere centre and radius (volume bbox = centre -/+ radius)
     float radius;
 };
+template <int C = CT_ALL>
 BT_DEV Surface resolve_hit(const float4* prims, const Hit& h, V3 o, V3 d) {
     Surface s;
     const float4* q = prims + h.prim * PRIM_STRIDE;
@@ -582,12 +589,12 @@ BT_DEV Surface resolve_hit(const float4* prims, const Hit& h, V3 o, V3 d) {
     s.position = o + h.t * d;
     s.center = v3(0.0f, 0.0f, 0.0f);
     s.radius = 0.0f;
-    if ((__float_as_int(meta.x) & 3) == PRIM_SPHERE) {
+    if ((C & CT_SPHERES) && (!(C & CT_RECTS) || (__float_as_int(meta.x) & 3) == PRIM_SPHERE)) {
         float4 q0 = q[0];
-        s.vol = __float_as_int(meta.z);
+        s.vol = (C & CT_VOLUMES) ? __float_as_int(meta.z) : -1;
         s.center = v3(q0);
         s.radius = q0.w;
-        if (h.face == 2) {  // generate_volume_manifold, sphere.rs:63-83
+        if ((C & CT_VOLUMES) && h.face == 2) {  // generate_volume_manifold, sphere.rs:63-83
             s.normal = v3(0.0f, 0.0f, 0.0f);
             s.face = 2;
         } else {            // generate_surface_manifold, sphere.rs:85-119
@@ -596,7 +603,7 @@ BT_DEV Surface resolve_hit(const float4* prims, const Hit& h, V3 o, V3 d) {
             s.normal = front ? normal : -normal;
             s.face = (s.vol >= 0 ? 3 : 0) + (front ? 0 : 1);
         }
-    } else {
+    } else if (C & CT_RECTS) {
         V3 n = v3(q[0]);
         s.normal = h.face == 0 ? n : -n;
         s.face = h.face;
@@ -605,15 +612,17 @@ BT_DEV Surface resolve_hit(const float4* prims, const Hit& h, V3 o, V3 d) {
 }
 
 // Object::pdf for the light's primitives (sphere.rs:44-61, rect.rs:92-108); 0 when missed.
+template <int C = CT_ALL>
 BT_DEV float light_pdf(const float4* prims, const float4* light, V3 o, V3 d, float tmin, float tmax) {
     int type = __float_as_int(light[0].x);
     if (type == LIGHT_POINT) return 0.0f;
     const float4* q = prims + __float_as_int(light[0].y) * PRIM_STRIDE;
-    if (type == LIGHT_SPHERE) {
+    if ((C & CT_SPHERES) && (!(C & CT_RECTS) || type == LIGHT_SPHERE)) {
         float t;
         if (!sphere_roots(q[0], q[1].x, o, d, tmin, tmax, t)) return 0.0f;
         return (t * t) / q[1].y;
     }
+    if (!(C & CT_RECTS)) return 0.0f;
     float t;
     bool front;
     if (!rect_test(q, o, d, tmin, tmax, false, t, front)) return 0.0f;

@@ -61,13 +61,13 @@ struct Traced {
 };
 
 // try_hit / try_hit_volume of the reference: one straight segment.
-template <bool BVH>
+template <bool BVH, int C = CT_ALL>
 BT_DEV Traced trace_straight(const RenderParams& p, const SceneView& sc, V3 o, V3 d, float tmin, float tmax, int vol_obj) {
     Traced r;
     if (BVH)
         r.h = bvh_closest(sc.prims, sc.nodes, sc.stack, o, d, tmin, tmax);
     else
-        r.h = scan_prims(sc.prims, sc.boxes, (int)p.scene.n_prims, o, d, tmin, tmax, vol_obj);
+        r.h = scan_prims<C>(sc.prims, sc.boxes, (int)p.scene.n_prims, o, d, tmin, tmax, vol_obj);
     r.steps = 0;
     r.scans = 1;
     r.captured = false;
@@ -207,7 +207,7 @@ enum { EV_TERMINAL = 0, EV_DIFFUSE = 1, EV_SPECULAR = 2 /* metallic, glass */, E
 // how its new direction is sampled: every variant consumes the same two u32 draws (r1, r2)
 enum { SK_NONE = 0, SK_COSINE = 1, SK_HEMI = 2, SK_SPHERE = 3, SK_RECT = 4 };
 
-template <bool STATS, bool LENS, bool EXACT, int NL, bool BVH>
+template <bool STATS, bool LENS, bool EXACT, int NL, bool BVH, int C>
 BT_DEV void render_body(const RenderParams& p) {
     extern __shared__ float4 smem[];
     const SceneView sc = stage_scene<BVH>(p, smem);
@@ -289,7 +289,7 @@ BT_DEV void render_body(const RenderParams& p) {
         int face = 0, hit_obj = -1;
         const float4* light = sc.lights;
         bool vol_scatter = false;
-        const bool in_volume = vol_obj >= 0;
+        const bool in_volume = (C & CT_VOLUMES) && vol_obj >= 0;
 
         // Per-warp phase compaction: a bent ray is NOT traced to its end here.  Lanes in flight are
         // in one of two phases -- STEP (an RK4 step; chords shorter than the free distance commit at
@@ -329,7 +329,7 @@ BT_DEV void render_body(const RenderParams& p) {
                 bstate = 0;
             }
         } else if (alive && (!LENS || in_volume)) {
-            tr = trace_straight<BVH>(p, sc, o, d, in_volume ? 0.0f : p.clip_min, in_volume ? p.volume_step : p.clip_max, vol_obj);
+            tr = trace_straight<BVH, C>(p, sc, o, d, in_volume ? 0.0f : p.clip_min, in_volume ? p.volume_step : p.clip_max, vol_obj);
             has_event = true;
         }
         if (LENS) {
@@ -381,12 +381,12 @@ BT_DEV void render_body(const RenderParams& p) {
                     }
                 }
             } else {
-                const Surface s = resolve_hit(sc.prims, tr.h, tr.o, tr.d);
+                const Surface s = resolve_hit<C>(sc.prims, tr.h, tr.o, tr.d);
                 pos = s.position;
                 nrm = s.normal;
                 face = s.face;
                 hit_obj = s.obj;
-                if (s.face <= 1) {
+                if (!(C & CT_VOLUMES) || s.face <= 1) {
                     // ---- sample_surface, mod.rs:454-486 + Material::shade, material.rs:81-199 ----
                     const float4 m0 = sc.mats[s.mat * MAT_STRIDE], m1 = sc.mats[s.mat * MAT_STRIDE + 1];
                     const int mk = __float_as_int(m0.w);
@@ -404,15 +404,15 @@ BT_DEV void render_body(const RenderParams& p) {
                         light = sc.lights + uniform_index(rng, p.scene.n_lights) * LIGHT_STRIDE;
                         if (gen_bool(rng, 0.5f)) {  // Pdf::Mix: true selects the light (material.rs:269-275)
                             const int lt = __float_as_int(light[0].x);
-                            sk = lt == LIGHT_SPHERE ? SK_SPHERE : (lt == LIGHT_RECT ? SK_RECT : SK_NONE);
+                            sk = ((C & CT_SPHERES) && lt == LIGHT_SPHERE) ? SK_SPHERE : (((C & CT_RECTS) && lt == LIGHT_RECT) ? SK_RECT : SK_NONE);
                         } else {
                             sk = SK_COSINE;
                         }
-                    } else {
+                    } else if (C & (CT_METAL | CT_GLASS)) {
                         ev = EV_SPECULAR;
                         sk = SK_HEMI;
                         rough = m1.x;
-                        if (mk == MAT_METALLIC) {
+                        if (!(C & CT_GLASS) || ((C & CT_METAL) && mk == MAT_METALLIC)) {
                             dir0 = reflect(din, nrm);
                         } else {  // MAT_GLASS, material.rs:231-261
                             float ior = m1.y;
@@ -449,7 +449,7 @@ BT_DEV void render_body(const RenderParams& p) {
         V3 vec = v3(0.0f, 0.0f, 0.0f);
         if (sk != SK_NONE) {
             const float4 l1 = light[1], l2 = light[2];
-            const bool rect = sk == SK_RECT;
+            const bool rect = (C & CT_RECTS) && sk == SK_RECT;
             const float r1 = uniform_f32(rng, rect ? l1.w : 0.0f, rect ? light[3].w : k.tau_scale);
             const float r2 = uniform_f32(rng, rect ? l2.w : 0.0f, rect ? light[4].w : k.one_scale);
             float cx = r1, sy = r2, z = 0.0f;
@@ -461,7 +461,7 @@ BT_DEV void render_body(const RenderParams& p) {
                 const float two = sk == SK_COSINE ? 1.0f : 2.0f;
                 cx = c * two * w;
                 sy = s * two * w;
-                z = sk == SK_COSINE ? m_sqrt(1.0f - r2) : (sk == SK_HEMI ? 1.0f - r2 : 1.0f - 2.0f * r2);
+                z = sk == SK_COSINE ? m_sqrt(1.0f - r2) : (((C & (CT_METAL | CT_GLASS)) && sk == SK_HEMI) ? 1.0f - r2 : 1.0f - 2.0f * r2);
                 X = v3(1.0f, 0.0f, 0.0f);
                 Y = v3(0.0f, 1.0f, 0.0f);
                 Z = v3(0.0f, 0.0f, 1.0f);
@@ -484,11 +484,11 @@ BT_DEV void render_body(const RenderParams& p) {
                 if (sk == SK_RECT) point = mat_vec(v3(light[3]), v3(light[4]), v3(light[5]), vec) + v3(light[6]);
                 dirvec = point - pos;
             }
-            if (ev == EV_SPECULAR) dirvec = dir0 + vec * rough;
+            if ((C & (CT_METAL | CT_GLASS)) && ev == EV_SPECULAR) dirvec = dir0 + vec * rough;
             if (ev == EV_VOLUME && !vol_scatter) dirvec = din;
             const V3 nd = normalize_a(dirvec);  // Ray::new
 
-            if (ev == EV_VOLUME) {
+            if ((C & CT_VOLUMES) && ev == EV_VOLUME) {
                 o = pos;
                 d = nd;
                 if (vol_scatter) {
@@ -513,7 +513,7 @@ BT_DEV void render_body(const RenderParams& p) {
                 float pdf = 1.0f, mpdf = 1.0f;
                 if (ev == EV_DIFFUSE) {
                     mpdf = dot(nrm, nd) * 0.318309886183790671538f;
-                    const float pb = light_pdf(sc.prims, light, pos, nd, p.clip_min, p.clip_max);
+                    const float pb = light_pdf<C>(sc.prims, light, pos, nd, p.clip_min, p.clip_max);
                     pdf = lerpf(mpdf, pb, 0.5f);
                 }
                 if (fabsf(pdf) <= 1e-5f) {
@@ -576,14 +576,14 @@ BT_DEV void render_body(const RenderParams& p) {
 
 // Lensed variants carry the flight state on top of the path state: 128-thread CTAs at 5 per SM give
 // them 96 registers (20 warps / SM) instead of 80 with spills (24 warps / SM).
-template <bool LENS, bool EXACT, int NL, bool BVH>
+template <bool LENS, bool EXACT, int NL, bool BVH, int C = CT_ALL>
 __global__ void __launch_bounds__(LENS ? 128 : 256, LENS ? 5 : 3) render_kernel(const __grid_constant__ RenderParams p) {
-    render_body<false, LENS, EXACT, NL, BVH>(p);
+    render_body<false, LENS, EXACT, NL, BVH, C>(p);
 }
 // the same kernel + work counters for bench.py's roofline accounting (never timed)
-template <bool LENS, bool EXACT, int NL, bool BVH>
+template <bool LENS, bool EXACT, int NL, bool BVH, int C = CT_ALL>
 __global__ void __launch_bounds__(256, 2) render_kernel_stats(const __grid_constant__ RenderParams p) {
-    render_body<true, LENS, EXACT, NL, BVH>(p);
+    render_body<true, LENS, EXACT, NL, BVH, C>(p);
 }
 
 template <bool LENS, bool EXACT, int NL, bool BVH>
@@ -744,10 +744,35 @@ cudaError_t BT_SFX(launch_render)(const RenderParams& p, cudaStream_t stream, ui
     const bool small = p.scene.n_lens != 0 && !p.stats;
     dim3 grid((p.width + 15) / 16, small ? (p.height + 7) / 8 : (p.height + 15) / 16), block(small ? 128 : 256);
     size_t smem = render_smem_bytes(p);
-    if (p.stats)
+    // content-specialised variants (device.cuh CT_*): the smallest compiled superset of what the scene holds
+#define BT_LAUNCH_C_(L, N, C)                                                                          \
+    do {                                                                                               \
+        cudaError_t e_ = ensure_smem(render_kernel<L, false, N, false, C>, smem);                      \
+        if (e_ != cudaSuccess) return e_;                                                              \
+        render_kernel<L, false, N, false, C><<<grid, block, smem, stream>>>(p);                        \
+    } while (0)
+    const uint32_t ct = p.scene.content;
+    const bool plain = !p.stats && p.scene.n_bvh == 0 && !(p.scene.n_lens != 0 && (p.scene.lens_exact || p.scene.n_lens != 1));
+    const bool lensed = p.scene.n_lens != 0;
+#define BT_FITS_(C) ((ct & ~(uint32_t)(C)) == 0)
+    if (plain && !lensed && BT_FITS_(CT_RECTS))
+        BT_LAUNCH_C_(false, 0, CT_RECTS);                                    // cornell.json.gz
+    else if (plain && !lensed && BT_FITS_(CT_RECTS | CT_METAL))
+        BT_LAUNCH_C_(false, 0, CT_RECTS | CT_METAL);                         // cornell2.json.gz
+    else if (plain && !lensed && BT_FITS_(CT_SPHERES | CT_VOLUMES))
+        BT_LAUNCH_C_(false, 0, CT_SPHERES | CT_VOLUMES);                     // cloud / volume.json.gz
+    else if (plain && !lensed && BT_FITS_(CT_SPHERES | CT_METAL | CT_GLASS))
+        BT_LAUNCH_C_(false, 0, CT_SPHERES | CT_METAL | CT_GLASS);            // scene.json.gz
+    else if (plain && lensed && BT_FITS_(CT_SPHERES | CT_METAL | CT_GLASS))
+        BT_LAUNCH_C_(true, 1, CT_SPHERES | CT_METAL | CT_GLASS);             // scene.json.gz + one mass (C3 / C5)
+    else if (plain && lensed && BT_FITS_(CT_SPHERES | CT_VOLUMES))
+        BT_LAUNCH_C_(true, 1, CT_SPHERES | CT_VOLUMES);                      // cloud / volume + one mass
+    else if (p.stats)
         BT_DISPATCH_LENS(render_kernel_stats, grid, block, smem, stream, p);
     else
         BT_DISPATCH_LENS(render_kernel, grid, block, smem, stream, p);
+#undef BT_FITS_
+#undef BT_LAUNCH_C_
     ++*launches;
     return cudaGetLastError();
 }

@@ -71,6 +71,7 @@ struct SceneHeader {
     uint32_t n_bvh, bvh_off;         // BVH nodes (0: linear scan over shared memory)
     uint32_t stage_off, stage_f4;    // the part of the blob every CTA stages into shared memory
     uint32_t has_volume_prims;       // any sphere with volume != None
+    uint32_t content;                // CT_SPHERES | CT_RECTS | CT_VOLUMES (device.cuh): picks a kernel without the unused code
     // root material folded to what sample_root returns (src/tracer/mod.rs:429-452)
     float root_color[3], root_albedo[3];
     uint32_t root_keeps_normal;      // 1: normal = -dir, depth = clip_max; 0: normal = 0, depth = inf

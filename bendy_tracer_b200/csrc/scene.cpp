@@ -1132,6 +1132,18 @@ FlatScene flatten(const Scene& scene, int accel) {
     h.n_vols = (uint32_t)(vols.size() / VOL_STRIDE);
     h.n_lens = (uint32_t)(lens.size() / LENS_STRIDE);
     h.prim_off = 0;
+    h.content = 0;
+    for (uint32_t i = 0; i < h.n_prims; ++i) {
+        uint32_t type;
+        std::memcpy(&type, &prims[(size_t)i * PRIM_STRIDE + 4].x, 4);
+        h.content |= (type & 3u) == PRIM_SPHERE ? 1u : 2u;
+    }
+    if (h.has_volume_prims) h.content |= 4u;
+    for (std::map<uint64_t, Data>::const_iterator it = scene.data.begin(); it != scene.data.end(); ++it) {
+        if (it->second.kind != DATA_MATERIAL) continue;
+        if (it->second.mat_kind == MAT_METALLIC) h.content |= 8u;
+        if (it->second.mat_kind == MAT_GLASS) h.content |= 16u;
+    }
     // acceleration structure: the linear scan of the reference for small scenes, a BVH beyond
     bool use_bvh = accel == ACCEL_BVH || (accel == ACCEL_AUTO && h.n_prims > (uint32_t)BVH_AUTO_PRIMS);
     if (h.has_volume_prims) use_bvh = false;  // hit_volumetric is scan-order dependent (mod.rs:414-424)
