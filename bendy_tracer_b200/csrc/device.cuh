@@ -376,7 +376,8 @@ BT_DEV bool box_test(const float4* b, V3 o, V3 d, float tmin, float tmax, float&
 // code, one without volumetric spheres no march code, one without Glass no Fresnel / refraction.
 // The render loop's body has to stay near the 32 KB instruction cache; every shipped scene gets a
 // variant without the code it cannot reach (kernels.cu: launch_render).
-enum { CT_SPHERES = 1, CT_RECTS = 2, CT_VOLUMES = 4, CT_METAL = 8, CT_GLASS = 16, CT_ALL = 31 };
+// CT_AOV: the call renders Output::Albedo / Normal / Depth (the first-hit latches of mod.rs:306-315).
+enum { CT_SPHERES = 1, CT_RECTS = 2, CT_VOLUMES = 4, CT_METAL = 8, CT_GLASS = 16, CT_AOV = 32, CT_ALL = 63 };
 template <bool DIST, int C = CT_ALL>
 BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, const float4* boxes, int n_prims, V3 o, V3 d, float tmin,
                         float tmax, int volume_obj, float* free_out) {

@@ -492,7 +492,7 @@ BT_DEV void render_body(const RenderParams& p) {
                 o = pos;
                 d = nd;
                 if (vol_scatter) {
-                    if (!latched) {
+                    if ((C & CT_AOV) && !latched) {
                         latched = true;
                         aov_albedo = v3(0.8f, 0.8f, 0.8f);
                         aov_normal = nrm;
@@ -519,7 +519,7 @@ BT_DEV void render_body(const RenderParams& p) {
                 if (fabsf(pdf) <= 1e-5f) {
                     finish = true;  // no scatter: from_emitted(BLACK)
                 } else {
-                    if (!latched) {
+                    if ((C & CT_AOV) && !latched) {
                         latched = true;
                         aov_albedo = A;
                         aov_normal = nrm;
@@ -536,12 +536,12 @@ BT_DEV void render_body(const RenderParams& p) {
         }
 
         if (finish) {
-            if (!latched) {
+            if ((C & CT_AOV) && !latched) {
                 aov_albedo = fin_albedo;
                 aov_normal = fin_normal;
                 aov_depth = fin_depth;
             }
-            switch (p.output) {  // mod.rs:306-315
+            switch ((C & CT_AOV) ? p.output : 0) {  // mod.rs:306-315
                 case 0: acc = acc + T * fin_color; break;
                 case 1: acc = acc + aov_albedo; break;
                 case 2: acc = acc + aov_normal; break;
@@ -751,7 +751,7 @@ cudaError_t BT_SFX(launch_render)(const RenderParams& p, cudaStream_t stream, ui
         if (e_ != cudaSuccess) return e_;                                                              \
         render_kernel<L, false, N, false, C><<<grid, block, smem, stream>>>(p);                        \
     } while (0)
-    const uint32_t ct = p.scene.content;
+    const uint32_t ct = p.scene.content | (p.output != 0 ? (uint32_t)CT_AOV : 0u);
     const bool plain = !p.stats && p.scene.n_bvh == 0 && !(p.scene.n_lens != 0 && (p.scene.lens_exact || p.scene.n_lens != 1));
     const bool lensed = p.scene.n_lens != 0;
 #define BT_FITS_(C) ((ct & ~(uint32_t)(C)) == 0)
