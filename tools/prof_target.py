@@ -52,9 +52,9 @@ def stepper(m, n=1 << 20, steps=512):
 if __name__ == "__main__":
     for rep in range(2):   # first round warms up (module load, clocks); profile with --launch-skip 6
         print("warm-up round" if rep == 0 else "timed round")
-        render("cornell2", 1920, 1080, 4)
-        render("scene", 1920, 1080, 1, lens=(1.362, 1.577, 6.114, 0.2))
-        render("cloud", 1920, 1080, 4)
+        render("cornell2", 1920, 1080, 16)
+        render("scene", 1920, 1080, 4, lens=(1.362, 1.577, 6.114, 0.2))
+        render("cloud", 1920, 1080, 16)
         stepper(1)
         stepper(4)
         stepper(16)
