@@ -276,6 +276,9 @@ BT_DEV float sdiv(float p, float q) { return __fdividef(p, q); }
 #endif
 
 // Sphere::hit roots (sphere.rs:121-148).  Returns true and the accepted root.
+// FLIGHT: a chord of a geodesic under the fast stepper -- positions already carry ~1e-5 of MUFU.RSQ
+// error, so the root uses the flavour's square root (MUFU.SQRT in the fast flavour).
+template <bool FLIGHT = false>
 BT_DEV bool sphere_roots_oc(V3 oc, float l2, float r2, V3 d, float tmin, float tmax, float& t_out) {
     // always the reference's rounding: |oc|^2 - r^2 cancels catastrophically for large spheres, and
     // a 1e-5 shift of a volume entry point flips Bernoulli scatter decisions at a visible rate
@@ -283,15 +286,16 @@ BT_DEV bool sphere_roots_oc(V3 oc, float l2, float r2, V3 d, float tmin, float t
     float c = l2 - r2;
     float disc = half_b * half_b - c;
     if (signbit(disc)) return false;  // most rays miss most spheres: a (mostly warp-uniform) early-out
-    float sqrtd = sqrtf(disc);
+    float sqrtd = FLIGHT ? m_sqrt(disc) : sqrtf(disc);
     float t0 = -half_b - sqrtd, t1 = -half_b + sqrtd;
     bool in0 = !(t0 < tmin || t0 > tmax), in1 = !(t1 < tmin || t1 > tmax);
     t_out = in0 ? t0 : t1;
     return in0 || in1;
 }
+template <bool FLIGHT = false>
 BT_DEV bool sphere_roots(float4 q0, float r2, V3 o, V3 d, float tmin, float tmax, float& t_out) {
     V3 oc = o - v3(q0);
-    return sphere_roots_oc(oc, dot(oc, oc), r2, d, tmin, tmax, t_out);
+    return sphere_roots_oc<FLIGHT>(oc, dot(oc, oc), r2, d, tmin, tmax, t_out);
 }
 BT_DEV float sqrt_approx(float x) {
     float r;
@@ -378,7 +382,7 @@ BT_DEV bool box_test(const float4* b, V3 o, V3 d, float tmin, float tmax, float&
 // variant without the code it cannot reach (kernels.cu: launch_render).
 // CT_AOV: the call renders Output::Albedo / Normal / Depth (the first-hit latches of mod.rs:306-315).
 enum { CT_SPHERES = 1, CT_RECTS = 2, CT_VOLUMES = 4, CT_METAL = 8, CT_GLASS = 16, CT_AOV = 32, CT_ALL = 63 };
-template <bool DIST, int C = CT_ALL>
+template <bool DIST, int C = CT_ALL, bool FLIGHT = false>
 BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, const float4* boxes, int n_prims, V3 o, V3 d, float tmin,
                         float tmax, int volume_obj, float* free_out) {
     (void)bounds;
@@ -416,7 +420,7 @@ BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, const float4*
                 const float dc = sqrt_approx(l2);
                 free = fminf(free, fabsf(dc - q0.w) - (l2 * q1.z + 2e-5f * (dc + q0.w) + 1e-6f));
             }
-            if (sphere_roots_oc(oc, l2, r2, d, tmin, h.t, t)) {
+            if (sphere_roots_oc<FLIGHT>(oc, l2, r2, d, tmin, h.t, t)) {
                 h.t = t;
                 h.prim = i;
                 h.face = 8;  // resolved after the scan (needs the normal)
@@ -495,6 +499,7 @@ BT_DEV void bvh_begin(BvhTrav& t, float tmax) {
 // One unit of "while-while" traversal: descend inner nodes until a leaf is held, test the leaf, pop.
 // Inside a warp the two phases never interleave, which keeps it converged for incoherent rays.
 // Returns true when the traversal is complete (t.h is the closest hit).
+template <bool FLIGHT = false>
 BT_DEV bool bvh_unit(BvhTrav& t, const float4* __restrict__ prims, const float4* __restrict__ nodes, uint32_t* stack, V3 o, V3 d,
                      float tmin) {
     const V3 inv = v3(m_rcp(d.x), m_rcp(d.y), m_rcp(d.z));
@@ -541,7 +546,7 @@ BT_DEV bool bvh_unit(BvhTrav& t, const float4* __restrict__ prims, const float4*
             float tt;
             bool front = true, ok;
             if (type == PRIM_SPHERE)
-                ok = sphere_roots(__ldg(q), __ldg(q + 1).x, o, d, tmin, t.h.t, tt);
+                ok = sphere_roots<FLIGHT>(__ldg(q), __ldg(q + 1).x, o, d, tmin, t.h.t, tt);
             else
                 ok = rect_test(q, o, d, tmin, t.h.t, false, tt, front);
             if (ok) {
@@ -564,11 +569,12 @@ BT_DEV bool bvh_unit(BvhTrav& t, const float4* __restrict__ prims, const float4*
     t.sp = sp;
     return cur == BVH_DONE;
 }
+template <bool FLIGHT = false>
 BT_DEV Hit bvh_closest(const float4* __restrict__ prims, const float4* __restrict__ nodes, uint32_t* stack, V3 o, V3 d,
                        float tmin, float tmax) {
     BvhTrav t;
     bvh_begin(t, tmax);
-    while (!bvh_unit(t, prims, nodes, stack, o, d, tmin)) {
+    while (!bvh_unit<FLIGHT>(t, prims, nodes, stack, o, d, tmin)) {
     }
     return t.h;
 }

@@ -129,7 +129,7 @@ BT_DEV int geodesic_step(const RenderParams& p, const L& lens, V3& x, V3& v, Fli
 }
 // INTERSECTION phase: the pending chord (or the final straight segment) against the scene; the
 // same pass refreshes the free distance.  Returns a resolved state or FL_FLY.
-template <bool EXACT, bool BVH>
+template <bool EXACT, bool BVH, int C = CT_ALL>
 BT_DEV int geodesic_scan(const RenderParams& p, const SceneView& sc, V3 x, V3 v, Flight& f, int state, float tmin, float tmax) {
     const bool far = state == FL_PEND_FAR;
     const float remaining = tmax - f.travelled;
@@ -140,11 +140,11 @@ BT_DEV int geodesic_scan(const RenderParams& p, const SceneView& sc, V3 x, V3 v,
     const float cmax = far ? remaining : fminf(len, remaining);
     float bound = 0.0f;
     if (BVH)
-        f.h = bvh_closest(sc.prims, sc.nodes, sc.stack, o, dir, cmin, cmax);
+        f.h = bvh_closest<!EXACT>(sc.prims, sc.nodes, sc.stack, o, dir, cmin, cmax);
     else if (p.scene.lens_skip)
-        f.h = scan_prims_t<true>(sc.prims, sc.bounds, sc.boxes, (int)p.scene.n_prims, o, dir, cmin, cmax, -1, &bound);
+        f.h = scan_prims_t<true, C, !EXACT>(sc.prims, sc.bounds, sc.boxes, (int)p.scene.n_prims, o, dir, cmin, cmax, -1, &bound);
     else
-        f.h = scan_prims(sc.prims, sc.boxes, (int)p.scene.n_prims, o, dir, cmin, cmax, -1);
+        f.h = scan_prims_t<false, C, !EXACT>(sc.prims, nullptr, sc.boxes, (int)p.scene.n_prims, o, dir, cmin, cmax, -1, nullptr);
     f.scans++;
     if (f.h.prim >= 0) return far ? FL_HIT_FAR : FL_HIT;
     if (far) return FL_ESCAPED;
@@ -346,7 +346,7 @@ BT_DEV void render_body(const RenderParams& p) {
                 unsigned m_fly = __ballot_sync(0xffffffffu, ls == FL_FLY);
                 if (m_pend != 0 && (m_fly == 0 || (uint32_t)__popc(m_pend) >= p.scan_lanes || ++scan_waited >= p.scan_patience)) {
                     scan_waited = 0;
-                    if (pend) ls = geodesic_scan<EXACT, BVH>(p, sc, o, d, fl, ls, p.clip_min, p.clip_max);
+                    if (pend) ls = geodesic_scan<EXACT, BVH, C>(p, sc, o, d, fl, ls, p.clip_min, p.clip_max);
                     m_pend = 0;
                     m_fly = __ballot_sync(0xffffffffu, ls == FL_FLY);
                 }
