@@ -161,12 +161,16 @@ int build_params(bt_scene* s, uint64_t camera_ref, bool need_camera, const bt_co
     p.clip_min = m.clip_min;
     p.clip_max = m.clip_max;
     p.volume_step = m.volume_step;
-    p.compact_lanes = 16;
-    p.compact_patience = 16;
+    // Scheduling thresholds of the per-warp phase machine (kernels.cu), tuned per kernel family on the
+    // shipped scenes (profiles/r1_sweep_*.log).  Long flights through a surface-only scene end a path
+    // every ~50 turns per lane: small batches keep lanes flying; a marching volume wants larger ones.
+    const bool long_flights = p.scene.n_lens != 0 && !p.scene.has_volume_prims;
+    p.compact_lanes = long_flights ? 12 : 16;
+    p.compact_patience = long_flights ? 8 : 16;
     if (const char* e = std::getenv("BT_COMPACT_LANES")) p.compact_lanes = (uint32_t)std::atoi(e);
     if (const char* e = std::getenv("BT_COMPACT_PATIENCE")) p.compact_patience = (uint32_t)std::atoi(e);
-    p.regen_lanes = 12;
-    p.regen_patience = 16;
+    p.regen_lanes = long_flights ? 4 : 12;
+    p.regen_patience = long_flights ? 8 : 16;
     if (const char* e = std::getenv("BT_REGEN_LANES")) p.regen_lanes = (uint32_t)std::atoi(e);
     if (const char* e = std::getenv("BT_REGEN_PATIENCE")) p.regen_patience = (uint32_t)std::atoi(e);
     p.scan_lanes = 12;
