@@ -1,8 +1,9 @@
 // device.cuh -- device-side math of the render loop: RNG + distributions, vector helpers,
 // primitive intersection over the shared-memory SoA blob, shading, volume shading and the
-// geodesic (RK4) stepper.  Compiled with -fmad=false: a*b+c is never contracted (the Rust
-// reference never contracts either), FMAs appear only where written as fmaf() -- i.e. in the
-// geodesic stepper, whose arithmetic is this project's own definition.
+// geodesic (RK4) stepper.  The exact flavour is compiled with -fmad=false: a*b+c is never
+// contracted (the Rust reference never contracts either), FMAs appear only where written as fmaf()
+// -- i.e. in the geodesic stepper, whose arithmetic is this project's own definition.
+// The fast flavour lets the compiler contract everything except the x*() helpers below.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -30,6 +31,12 @@ BT_DEV V3 operator*(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
 BT_DEV V3 operator/(V3 a, float s) { return v3(a.x / s, a.y / s, a.z / s); }
 BT_DEV V3 operator/(V3 a, V3 b) { return v3(a.x / b.x, a.y / b.y, a.z / b.z); }
 BT_DEV float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+// The same operations with every product and sum rounded separately whatever the compiler's FMA
+// contraction setting (the fast flavour is built -fmad=true): used where a contraction would matter --
+// the sphere quadratic (|oc|^2 - r^2 cancels catastrophically for large spheres) and the hit point,
+// which the scan, the BVH and the oracle must all round the same way.
+BT_DEV float xdot(V3 a, V3 b) { return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z)); }
+BT_DEV V3 xat(V3 o, float t, V3 d) { return v3(__fadd_rn(o.x, __fmul_rn(t, d.x)), __fadd_rn(o.y, __fmul_rn(t, d.y)), __fadd_rn(o.z, __fmul_rn(t, d.z))); }
 BT_DEV V3 cross(V3 a, V3 b) { return v3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
 // Two arithmetic flavours (compile time).  BT_EXACT_SCAN: every division / square root is the IEEE
 // operation the Rust reference performs, so values are bit-identical to the CPU oracle.  Default:
@@ -282,12 +289,12 @@ template <bool FLIGHT = false>
 BT_DEV bool sphere_roots_oc(V3 oc, float l2, float r2, V3 d, float tmin, float tmax, float& t_out) {
     // always the reference's rounding: |oc|^2 - r^2 cancels catastrophically for large spheres, and
     // a 1e-5 shift of a volume entry point flips Bernoulli scatter decisions at a visible rate
-    float half_b = dot(oc, d);
-    float c = l2 - r2;
-    float disc = half_b * half_b - c;
+    float half_b = xdot(oc, d);
+    float c = __fsub_rn(l2, r2);
+    float disc = __fsub_rn(__fmul_rn(half_b, half_b), c);
     if (signbit(disc)) return false;  // most rays miss most spheres: a (mostly warp-uniform) early-out
     float sqrtd = FLIGHT ? m_sqrt(disc) : sqrtf(disc);
-    float t0 = -half_b - sqrtd, t1 = -half_b + sqrtd;
+    float t0 = __fsub_rn(-half_b, sqrtd), t1 = __fadd_rn(-half_b, sqrtd);
     bool in0 = !(t0 < tmin || t0 > tmax), in1 = !(t1 < tmin || t1 > tmax);
     t_out = in0 ? t0 : t1;
     return in0 || in1;
@@ -295,7 +302,7 @@ BT_DEV bool sphere_roots_oc(V3 oc, float l2, float r2, V3 d, float tmin, float t
 template <bool FLIGHT = false>
 BT_DEV bool sphere_roots(float4 q0, float r2, V3 o, V3 d, float tmin, float tmax, float& t_out) {
     V3 oc = o - v3(q0);
-    return sphere_roots_oc<FLIGHT>(oc, dot(oc, oc), r2, d, tmin, tmax, t_out);
+    return sphere_roots_oc<FLIGHT>(oc, xdot(oc, oc), r2, d, tmin, tmax, t_out);
 }
 BT_DEV float sqrt_approx(float x) {
     float r;
@@ -402,8 +409,8 @@ BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, const float4*
             float r2 = q1.x;
             if ((C & CT_VOLUMES) && !DIST && volume_obj >= 0 && __float_as_int(meta.w) == volume_obj) {
                 // Sphere::hit_volumetric, sphere.rs:150-166
-                V3 e = (o + h.t * d) - v3(q0);
-                if (dot(e, e) <= r2) {
+                V3 e = xat(o, h.t, d) - v3(q0);
+                if (xdot(e, e) <= r2) {
                     h.prim = i;
                     h.face = 2;  // Face::Volume at t = clip.max
                     continue;
@@ -411,7 +418,7 @@ BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, const float4*
             }
             float t;
             const V3 oc = o - v3(q0);
-            const float l2 = dot(oc, oc);
+            const float l2 = xdot(oc, oc);
             if (DIST) {
                 // A reported root t puts the point o + t d within ~1e-6 |oc|^2 / r of the true surface
                 // (the residual of the quadratic, however ill-conditioned t itself is for a grazing
@@ -593,7 +600,7 @@ BT_DEV Surface resolve_hit(const float4* prims, const Hit& h, V3 o, V3 d) {
     s.mat = __float_as_int(meta.y);
     s.obj = __float_as_int(meta.w);
     s.vol = -1;
-    s.position = o + h.t * d;
+    s.position = xat(o, h.t, d);
     s.center = v3(0.0f, 0.0f, 0.0f);
     s.radius = 0.0f;
     if ((C & CT_SPHERES) && (!(C & CT_RECTS) || (__float_as_int(meta.x) & 3) == PRIM_SPHERE)) {

@@ -386,16 +386,25 @@ def test_full_size_properties():
 # ---- BVH (scenes above the linear-scan budget) -------------------------------------------------
 @pytest.mark.parametrize("name,lens", [("cornell", None), ("scene", None), ("scene", LENS_SCENE)])
 def test_bvh_equals_linear_scan_on_shipped_scenes(name, lens):
-    """forcing the BVH on a shipped scene must not change a single bit of the image (against the scan
-    with the same per-face rect tests; the box slab test of the default scan has its own test)"""
+    """Forcing the BVH on a shipped scene must not change a single bit of the image in the exact
+    flavour (against the scan with the same per-face rect tests; the box slab test of the default scan
+    has its own test).  The fast flavour is built with FMA contraction, and the BVH kernel and the
+    content-specialised scan kernel are separate compilations of the shading code: there the two
+    images agree to rounding (1e-4 of the bar) rather than bit for bit."""
     w, h = _res(name)
     _, esc, cam = load_pair(name, w, h, lenses=lens)
-    esc.set_accel("linear_faces")
-    a, _, _ = engine_render(esc, cam, w, h, 2, 2, 0, seed=4)
-    esc.set_accel("bvh")
-    assert esc.info()["n_bvh_nodes"] > 0
-    b, _, _ = engine_render(esc, cam, w, h, 2, 2, 0, seed=4)
-    assert np.array_equal(a, b)
+    for precision in ("exact", "fast"):
+        esc.set_precision(precision)
+        esc.set_accel("linear_faces")
+        a = engine_render(esc, cam, w, h, 2, 2, 0, seed=4)[0].copy()
+        esc.set_accel("bvh")
+        assert esc.info()["n_bvh_nodes"] > 0
+        b = engine_render(esc, cam, w, h, 2, 2, 0, seed=4)[0].copy()
+        if precision == "exact":
+            assert np.array_equal(a, b)
+        else:
+            d = np.abs(a[..., :3] - b[..., :3]).sum(-1) / 8
+            assert (d > 1e-3).mean() < 5e-3 and np.median(d) <= 1e-6, ((d > 1e-3).mean(), np.median(d))
 
 
 def test_bvh_synthetic_scene_vs_oracle(oracle):
@@ -416,9 +425,13 @@ def test_bvh_synthetic_scene_vs_oracle(oracle):
     got, _, _ = engine_render(esc, cam, w, h, 2, 2, 0, seed=6)
     mae = mae_per_channel(got, ref, n)
     assert (mae <= IMAGE_MAE).all(), mae
+    esc.set_precision("exact")                             # bit equality across structures: the exact flavour
+    bvh_exact = engine_render(esc, cam, w, h, 2, 2, 0, seed=6)[0].copy()
     esc.set_accel("linear_faces")
     lin, _, _ = engine_render(esc, cam, w, h, 2, 2, 0, seed=6)
-    assert np.array_equal(lin, got)
+    assert np.array_equal(lin, bvh_exact)
+    assert (mae_per_channel(bvh_exact, ref, n) <= 1e-5).all()
+    esc.set_precision("auto")
     # first hits agree with the oracle's scan
     ys, xs = np.mgrid[0:h, 0:w]
     cfg = O.make_config(samples=1)
