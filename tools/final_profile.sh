@@ -3,7 +3,7 @@
 # capture per dominant kernel (each only after the plain command has exited 0).
 set -x
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/final_pytest.log
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/final_pytest.log; python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/final_smoke.log 2>&1
 python bench.py > gpurun_out/final_bench_C2.json 2> gpurun_out/final_bench_C2.err || exit 1
 python bench.py --workload C3 --steps 2 --warmup 3 > gpurun_out/final_bench_C3.json 2> gpurun_out/final_bench_C3.err
 python bench.py --workload C4-cloud --steps 3 --warmup 3 --no-extras > gpurun_out/final_bench_C4.json 2> gpurun_out/final_bench_C4.err
