@@ -388,7 +388,8 @@ BT_DEV bool box_test(const float4* b, V3 o, V3 d, float tmin, float tmax, float&
 // The render loop's body has to stay near the 32 KB instruction cache; every shipped scene gets a
 // variant without the code it cannot reach (kernels.cu: launch_render).
 // CT_AOV: the call renders Output::Albedo / Normal / Depth (the first-hit latches of mod.rs:306-315).
-enum { CT_SPHERES = 1, CT_RECTS = 2, CT_VOLUMES = 4, CT_METAL = 8, CT_GLASS = 16, CT_AOV = 32, CT_ALL = 63 };
+// CT_CUBOID_LIGHT: a Cuboid carries ObjectFlags::LIGHT (WeightedIndex face pick, cuboid.rs:48-81; generic kernels only).
+enum { CT_SPHERES = 1, CT_RECTS = 2, CT_VOLUMES = 4, CT_METAL = 8, CT_GLASS = 16, CT_AOV = 32, CT_CUBOID_LIGHT = 64, CT_ALL = 127 };
 template <bool DIST, int C = CT_ALL, bool FLIGHT = false>
 BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, const float4* boxes, int n_prims, V3 o, V3 d, float tmin,
                         float tmax, int volume_obj, float* free_out) {
@@ -626,10 +627,30 @@ BT_DEV Surface resolve_hit(const float4* prims, const Hit& h, V3 o, V3 d) {
 }
 
 // Object::pdf for the light's primitives (sphere.rs:44-61, rect.rs:92-108); 0 when missed.
+// `lights`: the light table (a LIGHT_CUBOID record points at its six face sub-records in it).
 template <int C = CT_ALL>
-BT_DEV float light_pdf(const float4* prims, const float4* light, V3 o, V3 d, float tmin, float tmax) {
+BT_DEV float light_pdf(const float4* prims, const float4* lights, const float4* light, V3 o, V3 d, float tmin, float tmax) {
     int type = __float_as_int(light[0].x);
     if (type == LIGHT_POINT) return 0.0f;
+    if ((C & CT_CUBOID_LIGHT) && (C & CT_RECTS) && type == LIGHT_CUBOID) {
+        // Cuboid::pdf, cuboid.rs:56-81: the face with the strictly smallest t below clip.max, then
+        // Rect::pdf of that face (its re-hit returns the same t and +-n)
+        const float4* face = lights + __float_as_int(light[2].z) * LIGHT_STRIDE;
+        float best = tmax, shadow = 0.0f;
+        bool any = false;
+        for (int f = 0; f < 6; ++f, face += LIGHT_STRIDE) {
+            const float4* q = prims + __float_as_int(face[0].y) * PRIM_STRIDE;
+            float t;
+            bool front;
+            if (rect_test(q, o, d, tmin, best, true, t, front)) {
+                const V3 n = v3(q[0]);
+                best = t;
+                shadow = face[5].w * fabsf(dot(d, front ? n : -n));
+                any = true;
+            }
+        }
+        return any ? (best * best) / shadow : 0.0f;
+    }
     const float4* q = prims + __float_as_int(light[0].y) * PRIM_STRIDE;
     if ((C & CT_SPHERES) && (!(C & CT_RECTS) || type == LIGHT_SPHERE)) {
         float t;

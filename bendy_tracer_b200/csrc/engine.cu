@@ -189,7 +189,8 @@ int build_params(bt_scene* s, uint64_t camera_ref, bool need_camera, const bt_co
 int check_renderable(const bt_scene* s) {
     if (s->flat.diffuse_without_light)
         return fail(BT_ERR_SCENE, "Uniform::new called with `low >= high` (a Diffuse surface needs at least one LIGHT object)");
-    if (s->flat.unsupported_light) return fail(BT_ERR_UNSUPPORTED, "a Cuboid with ObjectFlags::LIGHT is not supported by the device path yet");
+    if (s->flat.cuboid_light_without_area)
+        return fail(BT_ERR_SCENE, "called `Result::unwrap()` on an `Err` value: AllWeightsZero (a LIGHT Cuboid without face area)");
     if (render_smem_bytes(RenderParams{s->flat.header}) > 200 * 1024)
         return fail(BT_ERR_UNSUPPORTED, "scene does not fit the shared-memory staging buffer (use BT_ACCEL_BVH / BT_ACCEL_AUTO)");
     return BT_OK;

@@ -287,7 +287,8 @@ BT_DEV void render_body(const RenderParams& p) {
         V3 pos = o, nrm = d, din = d, A = T, dir0 = d;  // event geometry (defaults are placeholders)
         float rough = 0.0f, hit_t = 0.0f;
         int face = 0, hit_obj = -1;
-        const float4* light = sc.lights;
+        const float4* light = sc.lights;   // the light object picked by a Diffuse event (its pdf)
+        const float4* lsamp = sc.lights;   // the record its point is sampled from (a cuboid's face)
         bool vol_scatter = false;
         const bool in_volume = (C & CT_VOLUMES) && vol_obj >= 0;
 
@@ -402,8 +403,17 @@ BT_DEV void render_body(const RenderParams& p) {
                     } else if (mk == MAT_DIFFUSE) {
                         ev = EV_DIFFUSE;
                         light = sc.lights + uniform_index(rng, p.scene.n_lights) * LIGHT_STRIDE;
+                        lsamp = light;
                         if (gen_bool(rng, 0.5f)) {  // Pdf::Mix: true selects the light (material.rs:269-275)
-                            const int lt = __float_as_int(light[0].x);
+                            if ((C & CT_CUBOID_LIGHT) && (C & CT_RECTS) && __float_as_int(light[0].x) == LIGHT_CUBOID) {
+                                // Cuboid::random_point, cuboid.rs:48-54: WeightedIndex (one Uniform::new(0, total)
+                                // draw, partition_point(w <= chosen)), then that face's Rect::random_point
+                                const float4 c1 = light[1], c2 = light[2];
+                                const float chosen = uniform_f32(rng, 0.0f, c2.y);
+                                const int idx = (c1.x <= chosen) + (c1.y <= chosen) + (c1.z <= chosen) + (c1.w <= chosen) + (c2.x <= chosen);
+                                lsamp = sc.lights + (__float_as_int(c2.z) + idx) * LIGHT_STRIDE;
+                            }
+                            const int lt = __float_as_int(lsamp[0].x);
                             sk = ((C & CT_SPHERES) && lt == LIGHT_SPHERE) ? SK_SPHERE : (((C & CT_RECTS) && lt == LIGHT_RECT) ? SK_RECT : SK_NONE);
                         } else {
                             sk = SK_COSINE;
@@ -448,10 +458,10 @@ BT_DEV void render_body(const RenderParams& p) {
         // (rect.rs:82-86) all draw (r1, r2) in this order; only the combination differs.
         V3 vec = v3(0.0f, 0.0f, 0.0f);
         if (sk != SK_NONE) {
-            const float4 l1 = light[1], l2 = light[2];
+            const float4 l1 = lsamp[1], l2 = lsamp[2];
             const bool rect = (C & CT_RECTS) && sk == SK_RECT;
-            const float r1 = uniform_f32(rng, rect ? l1.w : 0.0f, rect ? light[3].w : k.tau_scale);
-            const float r2 = uniform_f32(rng, rect ? l2.w : 0.0f, rect ? light[4].w : k.one_scale);
+            const float r1 = uniform_f32(rng, rect ? l1.w : 0.0f, rect ? lsamp[3].w : k.tau_scale);
+            const float r2 = uniform_f32(rng, rect ? l2.w : 0.0f, rect ? lsamp[4].w : k.one_scale);
             float cx = r1, sy = r2, z = 0.0f;
             V3 X = v3(l1), Y = v3(l2), Z = v3(0.0f, 0.0f, 0.0f);
             if (!rect) {
@@ -479,9 +489,9 @@ BT_DEV void render_body(const RenderParams& p) {
             fstate = FL_FLY;
             V3 dirvec = vec;  // Cosine, volume scatter
             if (ev == EV_DIFFUSE && sk != SK_COSINE) {  // Pdf::Light: random_point(light) - origin
-                V3 point = v3(light[1]);                                        // POINT: the translation
-                if (sk == SK_SPHERE) point = v3(light[1]) + vec * light[1].w;   // sphere.rs:40-42
-                if (sk == SK_RECT) point = mat_vec(v3(light[3]), v3(light[4]), v3(light[5]), vec) + v3(light[6]);
+                V3 point = v3(lsamp[1]);                                        // POINT: the translation
+                if (sk == SK_SPHERE) point = v3(lsamp[1]) + vec * lsamp[1].w;   // sphere.rs:40-42
+                if (sk == SK_RECT) point = mat_vec(v3(lsamp[3]), v3(lsamp[4]), v3(lsamp[5]), vec) + v3(lsamp[6]);
                 dirvec = point - pos;
             }
             if ((C & (CT_METAL | CT_GLASS)) && ev == EV_SPECULAR) dirvec = dir0 + vec * rough;
@@ -513,7 +523,7 @@ BT_DEV void render_body(const RenderParams& p) {
                 float pdf = 1.0f, mpdf = 1.0f;
                 if (ev == EV_DIFFUSE) {
                     mpdf = dot(nrm, nd) * 0.318309886183790671538f;
-                    const float pb = light_pdf<C>(sc.prims, light, pos, nd, p.clip_min, p.clip_max);
+                    const float pb = light_pdf<C>(sc.prims, sc.lights, light, pos, nd, p.clip_min, p.clip_max);
                     pdf = lerpf(mpdf, pb, 0.5f);
                 }
                 if (fabsf(pdf) <= 1e-5f) {
@@ -722,22 +732,24 @@ size_t render_smem_bytes(const RenderParams& p) {
 
 #endif
 
-// picks <LENS, EXACT, NL, BVH> from the scene header
-#define BT_LAUNCH_(KERNEL, L, E, N, B, GRID, BLOCK, SMEM, STREAM, ...)                                 \
+// picks <LENS, EXACT, NL, BVH> from the scene header (TAIL: name of a function-like macro giving further template arguments)
+#define BT_LAUNCH_(KERNEL, L, E, N, B, TAIL, GRID, BLOCK, SMEM, STREAM, ...)                           \
     do {                                                                                              \
-        cudaError_t e_ = ensure_smem(KERNEL<L, E, N, B>, SMEM);                                        \
+        cudaError_t e_ = ensure_smem(KERNEL<L, E, N, B TAIL()>, SMEM);                                   \
         if (e_ != cudaSuccess) return e_;                                                              \
-        KERNEL<L, E, N, B><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);                                \
+        KERNEL<L, E, N, B TAIL()><<<GRID, BLOCK, SMEM, STREAM>>>(__VA_ARGS__);                           \
     } while (0)
-#define BT_DISPATCH_LENS(KERNEL, GRID, BLOCK, SMEM, STREAM, ...)                                       \
+#define BT_TAIL_NONE()
+#define BT_TAIL_NO_CUBOID_LIGHT() , (CT_ALL & ~CT_CUBOID_LIGHT)
+#define BT_DISPATCH_LENS(KERNEL, TAIL, GRID, BLOCK, SMEM, STREAM, ...)                                 \
     do {                                                                                              \
         const bool exact_ = p.scene.lens_exact != 0, bvh_ = p.scene.n_bvh != 0;                        \
-        if (p.scene.n_lens == 0 && !bvh_) BT_LAUNCH_(KERNEL, false, false, 0, false, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);      \
-        else if (p.scene.n_lens == 0) BT_LAUNCH_(KERNEL, false, false, 0, true, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);           \
-        else if (bvh_) BT_LAUNCH_(KERNEL, true, false, 0, true, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);                            \
-        else if (p.scene.n_lens == 1 && !exact_) BT_LAUNCH_(KERNEL, true, false, 1, false, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__); \
-        else if (!exact_) BT_LAUNCH_(KERNEL, true, false, 0, false, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);                        \
-        else BT_LAUNCH_(KERNEL, true, true, 0, false, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);                                      \
+        if (p.scene.n_lens == 0 && !bvh_) BT_LAUNCH_(KERNEL, false, false, 0, false, TAIL, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);      \
+        else if (p.scene.n_lens == 0) BT_LAUNCH_(KERNEL, false, false, 0, true, TAIL, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);           \
+        else if (bvh_) BT_LAUNCH_(KERNEL, true, false, 0, true, TAIL, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);                            \
+        else if (p.scene.n_lens == 1 && !exact_) BT_LAUNCH_(KERNEL, true, false, 1, false, TAIL, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__); \
+        else if (!exact_) BT_LAUNCH_(KERNEL, true, false, 0, false, TAIL, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);                        \
+        else BT_LAUNCH_(KERNEL, true, true, 0, false, TAIL, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);                                      \
     } while (0)
 
 cudaError_t BT_SFX(launch_render)(const RenderParams& p, cudaStream_t stream, uint64_t* launches) {
@@ -768,9 +780,11 @@ cudaError_t BT_SFX(launch_render)(const RenderParams& p, cudaStream_t stream, ui
     else if (plain && lensed && BT_FITS_(CT_SPHERES | CT_VOLUMES))
         BT_LAUNCH_C_(true, 1, CT_SPHERES | CT_VOLUMES);                      // cloud / volume + one mass
     else if (p.stats)
-        BT_DISPATCH_LENS(render_kernel_stats, grid, block, smem, stream, p);
+        BT_DISPATCH_LENS(render_kernel_stats, BT_TAIL_NONE, grid, block, smem, stream, p);
+    else if (ct & CT_CUBOID_LIGHT)  // a LIGHT Cuboid: the only content that needs the WeightedIndex / Cuboid::pdf code
+        BT_DISPATCH_LENS(render_kernel, BT_TAIL_NONE, grid, block, smem, stream, p);
     else
-        BT_DISPATCH_LENS(render_kernel, grid, block, smem, stream, p);
+        BT_DISPATCH_LENS(render_kernel, BT_TAIL_NO_CUBOID_LIGHT, grid, block, smem, stream, p);
 #undef BT_FITS_
 #undef BT_LAUNCH_C_
     ++*launches;
@@ -781,7 +795,7 @@ cudaError_t BT_SFX(launch_trace)(const RenderParams& p, uint32_t n, const float*
                          DeviceSegment* out, cudaStream_t stream, uint64_t* launches) {
     if (n == 0) return cudaSuccess;
     size_t smem = render_smem_bytes(p);
-    BT_DISPATCH_LENS(trace_kernel, (n + 255) / 256, 256, smem, stream, p, n, origins, dirs, out);
+    BT_DISPATCH_LENS(trace_kernel, BT_TAIL_NONE, (n + 255) / 256, 256, smem, stream, p, n, origins, dirs, out);
     ++*launches;
     return cudaGetLastError();
 }

@@ -37,7 +37,11 @@ enum { MAT_STRIDE = 2 };
 //   RECT:   l1 = (x.xyz, -hw) l2 = (y.xyz, -hh) l3 = (Mx.xyz, scale_x) l4 = (My.xyz, scale_y)
 //           l5 = (Mz.xyz, -) l6 = (T.xyz, -)       (rect.rs:82-86: Uniform::new_inclusive(-h, h))
 //   POINT:  l1 = (T.xyz, -)                        (object/mod.rs:150)
-enum { LIGHT_SPHERE = 0, LIGHT_RECT = 1, LIGHT_POINT = 2 };
+//   CUBOID: l1 = (cum0..cum3) l2 = (cum4, Uniform::new(0, total).scale, first face sub-record, -)
+//           WeightedIndex over the face areas (cuboid.rs:48-54).  The six faces follow the n_lights
+//           object records as LIGHT_RECT sub-records (never picked by the light index) with the
+//           face transform and l5.w = Rect::area; Cuboid::pdf (cuboid.rs:56-81) walks them.
+enum { LIGHT_SPHERE = 0, LIGHT_RECT = 1, LIGHT_POINT = 2, LIGHT_CUBOID = 3 };
 enum { LIGHT_STRIDE = 7 };
 
 // ---- volume record: VOL_STRIDE float4 (reference src/scene/data/volume.rs:75-82) -----------
@@ -71,7 +75,7 @@ struct SceneHeader {
     uint32_t n_bvh, bvh_off;         // BVH nodes (0: linear scan over shared memory)
     uint32_t stage_off, stage_f4;    // the part of the blob every CTA stages into shared memory
     uint32_t has_volume_prims;       // any sphere with volume != None
-    uint32_t content;                // CT_SPHERES | CT_RECTS | CT_VOLUMES (device.cuh): picks a kernel without the unused code
+    uint32_t content;                // CT_* bits (device.cuh): picks a kernel without the unused code
     // root material folded to what sample_root returns (src/tracer/mod.rs:429-452)
     float root_color[3], root_albedo[3];
     uint32_t root_keeps_normal;      // 1: normal = -dir, depth = clip_max; 0: normal = 0, depth = inf

@@ -758,6 +758,15 @@ namespace {
 struct Bounds {
     float lo[3], hi[3];
 };
+// LIGHT_RECT fields l1..l6 of a light record (layout.h): Rect::random_point, rect.rs:82-86
+void fill_rect_light(float4* l, const Rect& r, const Affine& tf) {
+    l[1] = f4(r.x[0], r.x[1], r.x[2], -r.half_width);
+    l[2] = f4(r.y[0], r.y[1], r.y[2], -r.half_height);
+    l[3] = f4(tf.f[0], tf.f[1], tf.f[2], uniform_scale_inclusive(-r.half_width, r.half_width));
+    l[4] = f4(tf.f[3], tf.f[4], tf.f[5], uniform_scale_inclusive(-r.half_height, r.half_height));
+    l[5] = f4(tf.f[6], tf.f[7], tf.f[8], 0.0f);
+    l[6] = f4(tf.f[9], tf.f[10], tf.f[11], 0.0f);
+}
 void push_rect(std::vector<float4>& blob, std::vector<Bounds>& bounds, const Rect& r, const Affine& tf, int type, uint32_t mat, uint32_t obj) {
     {   // world-space AABB of the four corners (rect.rs:38-56)
         Bounds b;
@@ -986,7 +995,7 @@ FlatScene flatten(const Scene& scene, int accel) {
     FlatScene fs;
     std::memset(&fs.header, 0, sizeof fs.header);
     fs.diffuse_without_light = false;
-    fs.unsupported_light = false;
+    fs.cuboid_light_without_area = false;
 
     // data tables
     std::map<uint64_t, uint32_t> mat_index, vol_index;
@@ -1037,7 +1046,8 @@ FlatScene flatten(const Scene& scene, int accel) {
         h.root_keeps_normal = d.mat_kind == MAT_EMISSIVE ? 0u : 1u;
     }
 
-    std::vector<float4> prims, lights, boxes;
+    std::vector<float4> prims, lights, face_lights, boxes;
+    std::vector<size_t> cuboid_lights;  // offsets of the LIGHT_CUBOID records in `lights`
     std::vector<std::pair<uint32_t, uint32_t> > box_of_prim;  // (first face record, box index)
     std::vector<Bounds> bounds;
     bool any_diffuse = false;
@@ -1092,30 +1102,57 @@ FlatScene flatten(const Scene& scene, int accel) {
             n_prims = 6;
         }
         if (o.flags & 1u) {  // ObjectFlags::LIGHT
-            if (o.kind == OBJ_CUBOID) {
-                fs.unsupported_light = true;
-                continue;
-            }
             size_t base = lights.size();
             lights.resize(base + LIGHT_STRIDE, f4(0, 0, 0, 0));
             if (o.kind == OBJ_SPHERE) {
                 lights[base] = f4(as_f(LIGHT_SPHERE), as_f(first_prim), as_f(n_prims), as_f(obj));
                 lights[base + 1] = f4(tf.f[9], tf.f[10], tf.f[11], o.radius);
             } else if (o.kind == OBJ_RECT) {
-                const Rect& r = o.rect;
                 lights[base] = f4(as_f(LIGHT_RECT), as_f(first_prim), as_f(n_prims), as_f(obj));
-                lights[base + 1] = f4(r.x[0], r.x[1], r.x[2], -r.half_width);
-                lights[base + 2] = f4(r.y[0], r.y[1], r.y[2], -r.half_height);
-                lights[base + 3] = f4(tf.f[0], tf.f[1], tf.f[2], uniform_scale_inclusive(-r.half_width, r.half_width));
-                lights[base + 4] = f4(tf.f[3], tf.f[4], tf.f[5], uniform_scale_inclusive(-r.half_height, r.half_height));
-                lights[base + 5] = f4(tf.f[6], tf.f[7], tf.f[8], 0.0f);
-                lights[base + 6] = f4(tf.f[9], tf.f[10], tf.f[11], 0.0f);
+                fill_rect_light(&lights[base], o.rect, tf);
+            } else if (o.kind == OBJ_CUBOID) {
+                // Cuboid::random_point, cuboid.rs:48-54: WeightedIndex over the face areas (rand 0.8.5:
+                // cumulative sums without the last weight, Uniform::new(0, total)), then the face's
+                // Rect::random_point.  The six faces become LIGHT_RECT sub-records behind the object
+                // lights (face_lights, appended below); l2.z holds the first one's index.
+                float cumulative[5];
+                float total = 4.0f * o.faces[0].half_width * o.faces[0].half_height;
+                for (int i = 1; i < 6; ++i) {
+                    cumulative[i - 1] = total;
+                    total += 4.0f * o.faces[i].half_width * o.faces[i].half_height;
+                }
+                if (!(total > 0.0f)) fs.cuboid_light_without_area = true;  // WeightedIndex::new(..).unwrap() panics
+                lights[base] = f4(as_f(LIGHT_CUBOID), as_f(first_prim), as_f(n_prims), as_f(obj));
+                lights[base + 1] = f4(cumulative[0], cumulative[1], cumulative[2], cumulative[3]);
+                lights[base + 2] = f4(cumulative[4], total > 0.0f ? uniform_scale(0.0f, total) : 0.0f,
+                                      as_f((uint32_t)(face_lights.size() / LIGHT_STRIDE)), 0.0f);
+                cuboid_lights.push_back(base);
+                for (int i = 0; i < 6; ++i) {
+                    Affine ftf = tf;
+                    float t[3];
+                    mat_vec(tf, o.face_offset[i], t);
+                    for (int k = 0; k < 3; ++k) ftf.f[9 + k] = t[k] + tf.f[9 + k];
+                    size_t fb = face_lights.size();
+                    face_lights.resize(fb + LIGHT_STRIDE, f4(0, 0, 0, 0));
+                    face_lights[fb] = f4(as_f(LIGHT_RECT), as_f(first_prim + (uint32_t)i), as_f(1u), as_f(obj));
+                    fill_rect_light(&face_lights[fb], o.faces[i], ftf);
+                    face_lights[fb + 5].w = 4.0f * o.faces[i].half_width * o.faces[i].half_height;  // Rect::area (rect.rs:98)
+                }
+                fs.header.content |= 64u;  // CT_CUBOID_LIGHT
             } else {
                 lights[base] = f4(as_f(LIGHT_POINT), as_f(0), as_f(0), as_f(obj));
                 lights[base + 1] = f4(tf.f[9], tf.f[10], tf.f[11], 0.0f);
             }
         }
     }
+    // object lights first (Uniform::new(0, count) indexes them), the cuboid face sub-records behind
+    const uint32_t n_object_lights = (uint32_t)(lights.size() / LIGHT_STRIDE);
+    for (size_t i = 0; i < cuboid_lights.size(); ++i) {
+        uint32_t rel;
+        std::memcpy(&rel, &lights[cuboid_lights[i] + 2].z, 4);
+        lights[cuboid_lights[i] + 2].z = as_f(n_object_lights + rel);
+    }
+    lights.insert(lights.end(), face_lights.begin(), face_lights.end());
 
     std::vector<float4> lens;
     for (size_t i = 0; i < scene.lenses.size(); ++i) {
@@ -1128,11 +1165,11 @@ FlatScene flatten(const Scene& scene, int accel) {
     SceneHeader& h = fs.header;
     h.n_prims = (uint32_t)(prims.size() / PRIM_STRIDE);
     h.n_mats = (uint32_t)(mats.size() / MAT_STRIDE);
-    h.n_lights = (uint32_t)(lights.size() / LIGHT_STRIDE);
+    h.n_lights = n_object_lights;
     h.n_vols = (uint32_t)(vols.size() / VOL_STRIDE);
     h.n_lens = (uint32_t)(lens.size() / LENS_STRIDE);
     h.prim_off = 0;
-    h.content = 0;
+    h.content &= 64u;  // (CT_CUBOID_LIGHT was set while flattening the lights)
     for (uint32_t i = 0; i < h.n_prims; ++i) {
         uint32_t type;
         std::memcpy(&type, &prims[(size_t)i * PRIM_STRIDE + 4].x, 4);

@@ -116,7 +116,7 @@ struct FlatScene {
     std::vector<uint64_t> object_refs;  // object index -> ObjectRef
     std::vector<uint32_t> prim_order;   // record position -> canonical primitive index (identity without a BVH)
     bool diffuse_without_light;         // a Diffuse material is reachable but no LIGHT exists
-    bool unsupported_light;             // a Cuboid carries ObjectFlags::LIGHT (not flattened yet)
+    bool cuboid_light_without_area;     // a LIGHT Cuboid whose face areas sum to 0: WeightedIndex::new(..).unwrap() panics (cuboid.rs:49)
 };
 // accel: 0 = automatic (BVH above BVH_AUTO_PRIMS primitives), 1 = linear scan, 2 = BVH
 enum { ACCEL_AUTO = 0, ACCEL_LINEAR = 1, ACCEL_BVH = 2, ACCEL_LINEAR_FACES = 3, BVH_AUTO_PRIMS = 64 };

@@ -122,3 +122,24 @@ def synthetic_scene(n_spheres=200, n_rects=100, n_cuboids=20, seed=0, extent=6.0
     scene = {"roots": [], "root_material": 1, "objects": {"collection": objs, "next_key": key},
              "data": {"collection": data, "next_key": 4 + n_mats}}
     return json.loads(json.dumps(scene))
+
+
+def cornell_with_cuboid_light(extra_rect_light=True):
+    """cornell.json.gz with the short box (object 8) turned into an emissive LIGHT Cuboid
+    (Cuboid::random_point / Cuboid::pdf, cuboid.rs:48-81); the ceiling rect light stays (two LIGHT
+    objects: Uniform::new(0, 2) picks between them) unless extra_rect_light is False."""
+    import copy
+    doc = copy.deepcopy(O.read_scene_json(O.scene_path("cornell")))
+    objs = doc["objects"]["collection"]
+    data = doc["data"]["collection"]
+    key = doc["data"]["next_key"]
+    data[str(key)] = {"inner": {"Material": {"Emissive": {"albedo": {"r": 0.9, "g": 0.6, "b": 0.3}, "intensity": 4.0}}}}
+    doc["data"]["next_key"] = key + 1
+    box = objs["8"]
+    assert "Cuboid" in box["inner"]
+    box["flags"]["bits"] = 1
+    for _, rect in box["inner"]["Cuboid"]["faces"]:
+        rect["material"] = key
+    if not extra_rect_light:
+        objs["6"]["flags"]["bits"] = 0
+    return doc

@@ -442,6 +442,49 @@ def test_bvh_synthetic_scene_vs_oracle(oracle):
     assert ((g["face"] == r["face"]) & (g["object_ref"] == r["object_ref"])).mean() >= 0.9995
 
 
+@pytest.mark.parametrize("two_lights", [True, False])
+def test_cuboid_light(oracle, two_lights):
+    """A Cuboid with ObjectFlags::LIGHT: WeightedIndex face pick by area + Rect::random_point
+    (cuboid.rs:48-54) and Cuboid::pdf (cuboid.rs:56-81), alone and beside the ceiling rect light
+    (Uniform::new(0, 2) light index).  The exact flavour equals the oracle to libm rounding under the
+    box slab test, the six literal rect tests and the BVH; the fast flavour meets the image bar."""
+    import json
+    import bendy_tracer_b200 as bt
+    from common import cornell_with_cuboid_light
+    doc = cornell_with_cuboid_light(two_lights)
+    w, h = 96, 96
+    osc = O.OracleScene(doc)
+    esc = bt.Scene.from_json(json.dumps(doc))
+    cam = esc.find_by_tag("camera")
+    for s in (osc, esc):
+        s.set_camera_aspect(cam, 1.0)
+    assert esc.info()["n_lights"] == (2 if two_lights else 1)
+    ref, n, _ = oracle_render(osc, cam, w, h, 4, 2, 0, seed=21)
+    plain = oracle_render(load_pair("cornell", w, h)[0], cam, w, h, 4, 2, 0, seed=21)[0]
+    assert mae_per_channel(ref, plain, n).max() > 1e-2            # the box light really changes the image
+    fast = engine_render(esc, cam, w, h, 4, 2, 0, seed=21)[0].copy()
+    assert (mae_per_channel(fast, ref, n) <= IMAGE_MAE).all(), mae_per_channel(fast, ref, n)
+    esc.set_precision("exact")
+    images = {}
+    for accel in ("auto", "linear_faces", "bvh"):
+        esc.set_accel(accel)
+        images[accel] = engine_render(esc, cam, w, h, 4, 2, 0, seed=21)[0].copy()
+        mae = mae_per_channel(images[accel], ref, n)
+        assert (mae <= 1e-6).all(), (accel, mae)
+    assert np.array_equal(images["linear_faces"], images["bvh"])   # same per-face tests, same tie rule
+    for output in (1, 2, 3):                                       # AOVs through the generic kernel
+        esc.set_accel("auto")
+        r = oracle_render(osc, cam, w, h, 2, 2, output, seed=22)[0]
+        g = engine_render(esc, cam, w, h, 2, 2, output, seed=22)[0]
+        assert (mae_per_channel(g, r, 8) <= 1e-6).all()
+    # WeightedIndex::new(all-zero areas).unwrap() panics (cuboid.rs:49)
+    for _, rect in doc["objects"]["collection"]["8"]["inner"]["Cuboid"]["faces"]:
+        rect["half_width"] = 0.0
+    bad = bt.Scene.from_json(json.dumps(doc))
+    with pytest.raises(bt.ScenePanic):
+        bt.Tracer().render(bad, cam, bt.RenderConfig.with_samples(1), bt.Buffer(8, 8))
+
+
 def test_cli_progressive_render_and_png(tmp_path):
     """csrc/bendy_b200_cli: 1 pass per iteration until --samples, PNG screenshot == Buffer::preview of the
     same progressive sequence through the Python mirror"""

@@ -157,6 +157,21 @@ def test_box_shaped_cuboids_are_recognised():
     assert bt.Scene.from_json(json.dumps(doc)).info()["n_boxes"] == 0
 
 
+def test_cuboid_light_flattens():
+    """A LIGHT Cuboid is one light object (its six faces become sub-records behind the object lights)
+    and the oracle samples it (Cuboid::random_point / pdf, cuboid.rs:48-81)."""
+    from common import cornell_with_cuboid_light, oracle_render
+    doc = cornell_with_cuboid_light(True)
+    sc = bt.Scene.from_json(json.dumps(doc))
+    info = sc.info()
+    assert info["n_lights"] == 2 and info["n_primitives"] == 18 and info["n_boxes"] == 2
+    assert json.loads(sc.to_json())["objects"]["collection"]["8"]["flags"]["bits"] == 1
+    osc = O.OracleScene(doc)
+    img, n, _ = oracle_render(osc, 0, 32, 32, 2, 0, 0, seed=1)
+    base, _, _ = oracle_render(O.OracleScene.load(O.scene_path("cornell")), 0, 32, 32, 2, 0, 0, seed=1)
+    assert np.isfinite(img).all() and img[..., :3].sum() > 1.5 * base[..., :3].sum()
+
+
 def test_precision_and_accel_arguments():
     s = bt.Scene.load(O.scene_path("cloud"))
     for mode in ("auto", "fast", "exact"):
