@@ -183,11 +183,16 @@ BT_DEV bool gen_bool(Rng& rng, float p) {
     uint64_t p_int = shift >= 0 ? (mant << shift) : (shift > -64 ? (mant >> (-shift)) : 0ULL);
     return rng.next_u64() < p_int;
 }
-// UniformInt<usize>::new(0, n).sample
-BT_DEV uint32_t uniform_index(Rng& rng, uint32_t n) {
-    uint64_t range = n;
-    uint64_t ints_to_reject = (0xffffffffffffffffULL - range + 1) % range;
-    uint64_t zone = 0xffffffffffffffffULL - ints_to_reject;
+// UniformInt<usize>::new(0, n).sample (rand 0.8.5: widening multiply, rejection above `zone`).
+// zone = MAX - (MAX - n + 1) % n depends on n only: the host computes it once per call
+// (RenderParams::light_zone) -- in the kernel the 64-bit modulo was a 70-instruction subroutine
+// per Diffuse event.  n == 1: every draw is accepted and the index is 0 (the draw is still consumed).
+BT_DEV uint32_t uniform_index(Rng& rng, uint32_t n, uint64_t zone) {
+    if (n == 1) {
+        (void)rng.next_u64();
+        return 0;
+    }
+    const uint64_t range = n;
     for (;;) {
         uint64_t v = rng.next_u64();
         uint64_t lo = v * range;
@@ -331,6 +336,35 @@ BT_DEV bool rect_test(const float4* q, V3 o, V3 d, float tmin, float tmax, bool 
     return ok;
 }
 
+// Rect::hit for a PRIM_RECT_AA record (layout.h): normal on axis K, q2 on axis (K+1)%3, q3 on (K+2)%3,
+// all exact +-1.  Every dot product of rect_test then has one non-zero term (the products with the
+// zero components are +-0 and the sums with them exact), so picking the components gives the same
+// bits in both flavours with 5 multiply-adds instead of 15.  K is uniform across the warp.
+template <int K> BT_DEV float comp(float4 v) { return K == 0 ? v.x : (K == 1 ? v.y : v.z); }
+template <int K> BT_DEV float comp(V3 v) { return K == 0 ? v.x : (K == 1 ? v.y : v.z); }
+#ifdef BT_EXACT_SCAN
+BT_DEV float sat1(float o, float t, float d) { return o + t * d; }
+#else
+BT_DEV float sat1(float o, float t, float d) { return fmaf(t, d, o); }
+#endif
+template <int K>
+BT_DEV bool rect_test_aa(const float4* q, V3 o, V3 d, float tmin, float tmax, float& t_out, bool& front) {
+    const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+    const float nk = comp<K>(q0);
+    const float qq = comp<K>(d) * nk;
+    const float p = (comp<K>(q1) - comp<K>(o)) * nk;
+    const float t = sdiv(p, qq);
+    bool ok = fabsf(qq) > 1e-5f && !(t < tmin || t > tmax);
+    const float pu = sat1(comp<(K + 1) % 3>(o), t, comp<(K + 1) % 3>(d));
+    const float pw = sat1(comp<(K + 2) % 3>(o), t, comp<(K + 2) % 3>(d));
+    const float lx = fmaf(pu, comp<(K + 1) % 3>(q2), q2.w);
+    const float ly = fmaf(pw, comp<(K + 2) % 3>(q3), q3.w);
+    ok = ok && (lx * lx <= q0.w) && (ly * ly <= q1.w);
+    t_out = t;
+    front = p < 0.0f;
+    return ok;
+}
+
 // Cuboid::hit (cuboid.rs:83-105) for a cuboid whose six faces form one box: the smallest face
 // distance in [tmin, tmax) from one slab test.  The per-face t equals Rect::hit's p / q for that
 // face up to rounding; the rect's inside test becomes the slab-interval test.  Returns the face
@@ -456,7 +490,15 @@ BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, const float4*
                 const float m = 1e-4f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + fabsf(hi.x - lo.x) + fabsf(hi.y - lo.y) + fabsf(hi.z - lo.z)) + 1e-4f;
                 free = fminf(free, fmaxf(fmaxf(dx, dy), dz) - m);
             }
-            if (rect_test(q, o, d, tmin, h.t, type == PRIM_CUBOID_FACE, t, front)) {
+            bool hit;
+            if (type == PRIM_RECT_AA) {  // (uniform across the warp)
+                const int k = (__float_as_int(meta.x) >> 2) & 3;
+                hit = k == 0 ? rect_test_aa<0>(q, o, d, tmin, h.t, t, front)
+                             : (k == 1 ? rect_test_aa<1>(q, o, d, tmin, h.t, t, front) : rect_test_aa<2>(q, o, d, tmin, h.t, t, front));
+            } else {
+                hit = rect_test(q, o, d, tmin, h.t, type == PRIM_CUBOID_FACE, t, front);
+            }
+            if (hit) {
                 h.t = t;
                 h.prim = i;
                 h.face = front ? 0 : 1;
@@ -549,7 +591,7 @@ BT_DEV bool bvh_unit(BvhTrav& t, const float4* __restrict__ prims, const float4*
         for (uint32_t i = first; i < first + count; ++i) {
             const float4* q = prims + i * PRIM_STRIDE;
             const int meta = __float_as_int(__ldg(q + 4).x);
-            const int type = meta & 3, canon = meta >> 2;
+            const int type = meta & 3, canon = meta >> PRIM_CANON_SHIFT;
             const bool strict = type == PRIM_CUBOID_FACE;
             float tt;
             bool front = true, ok;

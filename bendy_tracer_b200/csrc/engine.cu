@@ -37,6 +37,8 @@ int cuda_fail(cudaError_t e, const char* what) {
 struct bt_engine {
     int device;
     cudaStream_t stream;
+    cudaStream_t stream2;   // second lane of the host-buffer pipeline (bt_render, BT_MEM_HOST)
+    cudaEvent_t ev_fork, ev_join;
     uint64_t launches;
     // scratch for host-memory calls
     void* d_scratch;
@@ -155,6 +157,12 @@ int build_params(bt_scene* s, uint64_t camera_ref, bool need_camera, const bt_co
     p.paths_per_pixel = (uint32_t)(m.samples * p.sub_count);
     p.seed = seed;
     p.path_base = sample_base * p.sub_count;
+    p.row0 = 0;
+    p.row_end = height;
+    {   // UniformInt<usize>::new(0, n).sample: zone = MAX - (MAX - n + 1) % n, hoisted out of the kernel
+        const uint64_t range = p.scene.n_lights;
+        p.light_zone = range ? 0xffffffffffffffffULL - (0xffffffffffffffffULL - range + 1) % range : 0;
+    }
     p.output = m.output;
     p.max_bounces = clamp_u32(m.max_bounces);
     p.max_volume_bounces = clamp_u32(m.max_volume_bounces);
@@ -229,9 +237,14 @@ int bt_engine_create(int device, bt_engine** out) {
     int khz = 0;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
     en->clock_khz = khz;
+    en->stream = en->stream2 = 0;
+    en->ev_fork = en->ev_join = 0;
     e = cudaStreamCreateWithFlags(&en->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&en->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&en->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&en->ev_join, cudaEventDisableTiming);
     if (e != cudaSuccess) {
-        delete en;
+        bt_engine_destroy(en);
         return cuda_fail(e, "cudaStreamCreate");
     }
     *out = en;
@@ -242,7 +255,10 @@ void bt_engine_destroy(bt_engine* engine) {
     if (!engine) return;
     cudaSetDevice(engine->device);
     if (engine->d_scratch) cudaFree(engine->d_scratch);
-    cudaStreamDestroy(engine->stream);
+    if (engine->ev_fork) cudaEventDestroy(engine->ev_fork);
+    if (engine->ev_join) cudaEventDestroy(engine->ev_join);
+    if (engine->stream2) cudaStreamDestroy(engine->stream2);
+    if (engine->stream) cudaStreamDestroy(engine->stream);
     delete engine;
 }
 
@@ -413,30 +429,54 @@ void bt_render_config_default(bt_render_config* c) {
     c->samples = 64;
 }
 
-int bt_render_async(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_config* config,
-                    const bt_render_config* rc, uint64_t seed, uint64_t sample_base, float* rgba32f_device,
-                    uint32_t width, uint32_t height, uint64_t* samples_inout, int32_t* status, void* cuda_stream) {
-    if (!engine || !scene || !config || !rc || !status) return fail(BT_ERR_INVALID_ARG, "NULL argument");
-    if (!scene->engine) scene->engine = engine;  // a scene created without an engine binds on first use
-    if (scene->engine != engine) return fail(BT_ERR_INVALID_ARG, "scene belongs to another engine");
-    GUARD_BEGIN
-    if (rc->samples == 0) {  // mod.rs:186-188
-        *status = BT_STATUS_DONE;
-        return BT_OK;
-    }
-    if (!rgba32f_device || width == 0 || height == 0) return fail(BT_ERR_INVALID_ARG, "empty buffer");
-    if (config->output < 0 || config->output > 3 || (rc->has_output && (rc->output < 0 || rc->output > 3)))
-        return fail(BT_ERR_INVALID_ARG, "invalid Output");
-    CK(cudaSetDevice(engine->device));
-    cudaStream_t stream = (cudaStream_t)cuda_stream;  // NULL is the CUDA default stream, taken literally
+namespace {
+// The body of Tracer::render for pixel rows [row0, row_end) of the frame at `fb` (device memory):
+// checks, per-call constants, ONE kernel launch on `stream`.  bt_render_async renders the whole
+// frame with it; bt_render pipelines a host frame through it in bands.
+int render_rows(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_config* config, const bt_render_config* rc,
+                uint64_t seed, uint64_t sample_base, float* fb, uint32_t width, uint32_t height, uint32_t row0, uint32_t row_end,
+                cudaStream_t stream, uint32_t* sub_count_out) {
     int rcode = refresh_scene(scene, stream);
     if (rcode != BT_OK) return rcode;
     if ((rcode = check_renderable(scene)) != BT_OK) return rcode;
     RenderParams p;
     if ((rcode = build_params(scene, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return rcode;
-    p.fb = (float4*)rgba32f_device;
+    p.fb = (float4*)fb;
+    p.row0 = row0;
+    p.row_end = row_end;
     CK(use_exact(engine, scene) ? launch_render_exact(p, stream, &engine->launches) : launch_render_fast(p, stream, &engine->launches));
-    if (samples_inout) *samples_inout += rc->samples * p.sub_count;  // mod.rs:199
+    if (sub_count_out) *sub_count_out = p.sub_count;
+    return BT_OK;
+}
+int check_render_args(bt_engine* engine, bt_scene* scene, const bt_config* config, const bt_render_config* rc, const float* fb,
+                      uint32_t width, uint32_t height) {
+    if (!scene->engine) scene->engine = engine;  // a scene created without an engine binds on first use
+    if (scene->engine != engine) return fail(BT_ERR_INVALID_ARG, "scene belongs to another engine");
+    if (!fb || width == 0 || height == 0) return fail(BT_ERR_INVALID_ARG, "empty buffer");
+    if (config->output < 0 || config->output > 3 || (rc->has_output && (rc->output < 0 || rc->output > 3)))
+        return fail(BT_ERR_INVALID_ARG, "invalid Output");
+    return BT_OK;
+}
+}  // namespace
+
+int bt_render_async(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_config* config,
+                    const bt_render_config* rc, uint64_t seed, uint64_t sample_base, float* rgba32f_device,
+                    uint32_t width, uint32_t height, uint64_t* samples_inout, int32_t* status, void* cuda_stream) {
+    if (!engine || !scene || !config || !rc || !status) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    GUARD_BEGIN
+    if (rc->samples == 0) {  // mod.rs:186-188
+        *status = BT_STATUS_DONE;
+        return BT_OK;
+    }
+    int rcode = check_render_args(engine, scene, config, rc, rgba32f_device, width, height);
+    if (rcode != BT_OK) return rcode;
+    CK(cudaSetDevice(engine->device));
+    cudaStream_t stream = (cudaStream_t)cuda_stream;  // NULL is the CUDA default stream, taken literally
+    uint32_t sub_count = 1;
+    if ((rcode = render_rows(engine, scene, camera_ref, config, rc, seed, sample_base, rgba32f_device, width, height, 0, height,
+                             stream, &sub_count)) != BT_OK)
+        return rcode;
+    if (samples_inout) *samples_inout += rc->samples * sub_count;  // mod.rs:199
     *status = BT_STATUS_IN_PROGRESS;
     return BT_OK;
     GUARD_END
@@ -488,19 +528,51 @@ int bt_render(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_
         CK(cudaStreamSynchronize(engine->stream));
         return BT_OK;
     }
-    size_t bytes = (size_t)width * height * 4 * sizeof(float);
-    int r = ensure_scratch(engine, bytes);
+    // Host buffer: the frame goes through the GPU in horizontal bands, each band's upload, kernel and
+    // download queued on one of two streams, so that band i+1's upload and band i-1's download run
+    // under band i's kernel; only the first upload and the last download are exposed.  Pixels are
+    // independent and the RNG is keyed by pixel, so the image does not depend on the banding
+    // (BT_HOST_BANDS=1 renders the frame in one piece; tests compare the two bit for bit).
+    if (!scene || !config) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    GUARD_BEGIN
+    int r = check_render_args(engine, scene, config, rc, rgba32f, width, height);
     if (r != BT_OK) return r;
-    CK(cudaMemcpyAsync(engine->d_scratch, rgba32f, bytes, cudaMemcpyHostToDevice, engine->stream));
-    r = bt_render_async(engine, scene, camera_ref, config, rc, seed, sample_base, (float*)engine->d_scratch, width,
-                        height, samples_inout, status, engine->stream);
-    if (r != BT_OK) {
-        cudaStreamSynchronize(engine->stream);
-        return r;
+    const size_t row_bytes = (size_t)width * 4 * sizeof(float), bytes = row_bytes * height;
+    if ((r = ensure_scratch(engine, bytes)) != BT_OK) return r;
+    uint32_t bands = (uint32_t)std::min<size_t>(8, std::max<size_t>(1, bytes / (8u << 20)));
+    if (const char* e = std::getenv("BT_HOST_BANDS")) bands = (uint32_t)std::max(1, std::atoi(e));
+    uint32_t band_rows = ((height + bands - 1) / bands + 15u) & ~15u;  // whole 16-row CTAs
+    // the scene's device copy is refreshed on the first stream; the second one waits for it
+    if ((r = refresh_scene(scene, engine->stream)) != BT_OK) return r;
+    CK(cudaEventRecord(engine->ev_fork, engine->stream));
+    CK(cudaStreamWaitEvent(engine->stream2, engine->ev_fork, 0));
+    uint32_t sub_count = 1;
+    int band = 0;
+    for (uint32_t row0 = 0; row0 < height; row0 += band_rows, ++band) {
+        const uint32_t row_end = std::min(height, row0 + band_rows);
+        cudaStream_t st = (band & 1) ? engine->stream2 : engine->stream;
+        char* dev = (char*)engine->d_scratch + (size_t)row0 * row_bytes;
+        char* host = (char*)rgba32f + (size_t)row0 * row_bytes;
+        const size_t n = (size_t)(row_end - row0) * row_bytes;
+        cudaError_t ce = cudaMemcpyAsync(dev, host, n, cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess) {
+            r = render_rows(engine, scene, camera_ref, config, rc, seed, sample_base, (float*)engine->d_scratch, width, height, row0,
+                            row_end, st, &sub_count);
+            if (r == BT_OK) ce = cudaMemcpyAsync(host, dev, n, cudaMemcpyDeviceToHost, st);
+        }
+        if (ce != cudaSuccess || r != BT_OK) {  // drain both lanes before reporting
+            cudaStreamSynchronize(engine->stream);
+            cudaStreamSynchronize(engine->stream2);
+            return ce != cudaSuccess ? cuda_fail(ce, "bt_render: band copy") : r;
+        }
     }
-    CK(cudaMemcpyAsync(rgba32f, engine->d_scratch, bytes, cudaMemcpyDeviceToHost, engine->stream));
+    CK(cudaEventRecord(engine->ev_join, engine->stream2));
+    CK(cudaStreamWaitEvent(engine->stream, engine->ev_join, 0));
     CK(cudaStreamSynchronize(engine->stream));
+    if (samples_inout) *samples_inout += rc->samples * sub_count;  // mod.rs:199
+    *status = BT_STATUS_IN_PROGRESS;
     return BT_OK;
+    GUARD_END
 }
 
 int bt_resolve_u8(bt_engine* engine, const float* rgba32f, int mem, uint32_t width, uint32_t height,

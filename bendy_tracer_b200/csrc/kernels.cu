@@ -219,8 +219,8 @@ BT_DEV void render_body(const RenderParams& p) {
     // block = 16x16 pixels, warp = 8x4 pixel tile (coherent first hits, 128 B framebuffer rows)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-    const uint32_t py = blockIdx.y * (blockDim.x >> 4) + (warp >> 1) * 4 + (lane >> 3);  // 256 threads: 16 rows, 128: 8
-    const bool valid = px < p.width && py < p.height;
+    const uint32_t py = p.row0 + blockIdx.y * (blockDim.x >> 4) + (warp >> 1) * 4 + (lane >> 3);  // 256 threads: 16 rows, 128: 8
+    const bool valid = px < p.width && py < p.row_end;
     const uint64_t pixel = (uint64_t)py * p.width + px;
     const float inf = __int_as_float(0x7f800000);
     // path_seed(seed, pixel, index) with its pixel-dependent prefix hoisted out of the path loop
@@ -402,7 +402,7 @@ BT_DEV void render_body(const RenderParams& p) {
                         fin_albedo = fin_color;
                     } else if (mk == MAT_DIFFUSE) {
                         ev = EV_DIFFUSE;
-                        light = sc.lights + uniform_index(rng, p.scene.n_lights) * LIGHT_STRIDE;
+                        light = sc.lights + uniform_index(rng, p.scene.n_lights, p.light_zone) * LIGHT_STRIDE;
                         lsamp = light;
                         if (gen_bool(rng, 0.5f)) {  // Pdf::Mix: true selects the light (material.rs:269-275)
                             if ((C & CT_CUBOID_LIGHT) && (C & CT_RECTS) && __float_as_int(light[0].x) == LIGHT_CUBOID) {
@@ -754,7 +754,8 @@ size_t render_smem_bytes(const RenderParams& p) {
 
 cudaError_t BT_SFX(launch_render)(const RenderParams& p, cudaStream_t stream, uint64_t* launches) {
     const bool small = p.scene.n_lens != 0 && !p.stats;
-    dim3 grid((p.width + 15) / 16, small ? (p.height + 7) / 8 : (p.height + 15) / 16), block(small ? 128 : 256);
+    const uint32_t rows = p.row_end - p.row0;
+    dim3 grid((p.width + 15) / 16, small ? (rows + 7) / 8 : (rows + 15) / 16), block(small ? 128 : 256);
     size_t smem = render_smem_bytes(p);
     // content-specialised variants (device.cuh CT_*): the smallest compiled superset of what the scene holds
 #define BT_LAUNCH_C_(L, N, C)                                                                          \

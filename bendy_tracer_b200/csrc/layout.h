@@ -15,10 +15,16 @@ namespace bt {
 //   n = M*z, the full affine inverse and the local axes folded into two plane equations)
 //   q0 = (n.xyz, hw^2/|x|^2)  q1 = (T.xyz, hh^2/|y|^2)
 //   q2 = (ax.xyz, cx)  q3 = (ay.xyz, cy)   with local.x = dot(pos, ax) + cx
-enum { PRIM_SPHERE = 0, PRIM_RECT = 1, PRIM_CUBOID_FACE = 2 };
+// RECT_AA: a Rect whose world normal and both plane-equation axes are exact +-unit coordinate axes
+//   (every wall of the Cornell box).  Same record, with the in-plane axes ordered so that q2 lies on
+//   axis (k+1)%3 and q3 on (k+2)%3, k = the normal's axis; the scan then runs rect_test_aa<k>, which
+//   picks components instead of forming dot products and rounds exactly like the general test.
+enum { PRIM_SPHERE = 0, PRIM_RECT = 1, PRIM_CUBOID_FACE = 2, PRIM_RECT_AA = 3 };
 enum { PRIM_STRIDE = 5 };
-// q4.x = type | (canonical primitive index << 2): under a BVH the records are stored in tree order
-// and the canonical index decides exact-distance ties the way the reference's scan order does.
+// q4.x = type | (k << 2) | (canonical primitive index << PRIM_CANON_SHIFT): under a BVH the records are
+// stored in tree order and the canonical index decides exact-distance ties the way the reference's
+// scan order does.
+enum { PRIM_CANON_SHIFT = 4 };
 
 // ---- BVH node: BVH_STRIDE float4 (extension: built when a scene exceeds the linear-scan budget)
 //   an inner node holds BOTH child boxes (so a child is only visited when its box is hit):
@@ -108,6 +114,8 @@ struct RenderParams {
     uint32_t paths_per_pixel;        // samples * subpixel_count of this call
     uint32_t sub_count;
     uint64_t seed, path_base;        // path index of the first path of this call
+    uint64_t light_zone;             // UniformInt<usize>::new(0, n_lights): the acceptance zone (rand 0.8.5), hoisted per call
+    uint32_t row0, row_end;          // this launch renders pixel rows [row0, row_end) (bt_render pipelines a host frame in bands)
     int32_t output;
     uint32_t max_bounces, max_volume_bounces;
     float clip_min, clip_max, volume_step;

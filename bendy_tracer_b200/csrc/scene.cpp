@@ -767,7 +767,18 @@ void fill_rect_light(float4* l, const Rect& r, const Affine& tf) {
     l[5] = f4(tf.f[6], tf.f[7], tf.f[8], 0.0f);
     l[6] = f4(tf.f[9], tf.f[10], tf.f[11], 0.0f);
 }
-void push_rect(std::vector<float4>& blob, std::vector<Bounds>& bounds, const Rect& r, const Affine& tf, int type, uint32_t mat, uint32_t obj) {
+// 0 / 1 / 2 when v is exactly +-1 on that axis and (+-)0 on the others, else -1
+int unit_axis(const float v[3]) {
+    int k = -1;
+    for (int i = 0; i < 3; ++i) {
+        if (v[i] == 0.0f) continue;
+        if (std::fabs(v[i]) != 1.0f || k >= 0) return -1;
+        k = i;
+    }
+    return k;
+}
+void push_rect(std::vector<float4>& blob, std::vector<Bounds>& bounds, const Rect& r, const Affine& tf, int type, uint32_t mat, uint32_t obj,
+               bool allow_aa = false) {
     {   // world-space AABB of the four corners (rect.rs:38-56)
         Bounds b;
         for (int k = 0; k < 3; ++k) { b.lo[k] = 3.0e38f; b.hi[k] = -3.0e38f; }
@@ -813,11 +824,27 @@ void push_rect(std::vector<float4>& blob, std::vector<Bounds>& bounds, const Rec
     float hw2 = (float)((double)(r.half_width * r.half_width) / x2);
     float hh2 = (float)((double)(r.half_height * r.half_height) / y2);
     float area = 4.0f * r.half_width * r.half_height;  // rect.rs:88-90
+    float4 q2 = f4((float)ax[0], (float)ax[1], (float)ax[2], (float)cx), q3 = f4((float)ay[0], (float)ay[1], (float)ay[2], (float)cy);
+    // axis-aligned? (normal and both plane axes exact +-unit coordinate axes, on three different axes)
+    uint32_t aa_axis = 0;
+    if (type == PRIM_RECT && allow_aa) {
+        const float fn[3] = {n[0], n[1], n[2]}, fx[3] = {q2.x, q2.y, q2.z}, fy[3] = {q3.x, q3.y, q3.z};
+        int kn = unit_axis(fn), kx = unit_axis(fx), ky = unit_axis(fy);
+        if (kn >= 0 && kx >= 0 && ky >= 0 && kn != kx && kn != ky && kx != ky) {
+            if (kx != (kn + 1) % 3) {  // the inside test is symmetric in (q2, hw2) and (q3, hh2)
+                std::swap(q2, q3);
+                std::swap(hw2, hh2);
+            }
+            type = PRIM_RECT_AA;
+            aa_axis = (uint32_t)kn;
+        }
+    }
     blob.push_back(f4(n[0], n[1], n[2], hw2));
     blob.push_back(f4(tf.f[9], tf.f[10], tf.f[11], hh2));
-    blob.push_back(f4((float)ax[0], (float)ax[1], (float)ax[2], (float)cx));
-    blob.push_back(f4((float)ay[0], (float)ay[1], (float)ay[2], (float)cy));
-    blob.push_back(f4(as_f((uint32_t)type | ((uint32_t)(blob.size() / PRIM_STRIDE) << 2)), as_f(mat), type == PRIM_RECT ? area : as_f(0u), as_f(obj)));
+    blob.push_back(q2);
+    blob.push_back(q3);
+    blob.push_back(f4(as_f((uint32_t)type | (aa_axis << 2) | ((uint32_t)(blob.size() / PRIM_STRIDE) << PRIM_CANON_SHIFT)), as_f(mat),
+                      type != PRIM_CUBOID_FACE ? area : as_f(0u), as_f(obj)));
 }
 
 // A Cuboid whose six faces really are the faces of one rectangular box (Cuboid::new, cuboid.rs:19-30,
@@ -1046,6 +1073,8 @@ FlatScene flatten(const Scene& scene, int accel) {
         h.root_keeps_normal = d.mat_kind == MAT_EMISSIVE ? 0u : 1u;
     }
 
+    // BT_ACCEL_LINEAR_FACES keeps the literal tests: six Rect::hit per cuboid, the general rect test everywhere
+    const bool aa_rects = accel != ACCEL_LINEAR_FACES && !std::getenv("BT_NO_AA_RECTS");
     std::vector<float4> prims, lights, face_lights, boxes;
     std::vector<size_t> cuboid_lights;  // offsets of the LIGHT_CUBOID records in `lights`
     std::vector<std::pair<uint32_t, uint32_t> > box_of_prim;  // (first face record, box index)
@@ -1072,7 +1101,7 @@ FlatScene flatten(const Scene& scene, int accel) {
             prims.push_back(f4(r * r, 3.14159265358979323846f * r * r, r > 0.0f ? 2e-5f / r : 3.0e38f, 0.0f));
             prims.push_back(f4(0, 0, 0, 0));
             prims.push_back(f4(0, 0, 0, 0));
-            prims.push_back(f4(as_f(PRIM_SPHERE | ((uint32_t)(prims.size() / PRIM_STRIDE) << 2)), as_f(mat), as_f(vol), as_f(obj)));
+            prims.push_back(f4(as_f(PRIM_SPHERE | ((uint32_t)(prims.size() / PRIM_STRIDE) << PRIM_CANON_SHIFT)), as_f(mat), as_f(vol), as_f(obj)));
             {
                 Bounds b;
                 for (int k = 0; k < 3; ++k) { b.lo[k] = tf.f[9 + k] - r; b.hi[k] = tf.f[9 + k] + r; }
@@ -1081,7 +1110,7 @@ FlatScene flatten(const Scene& scene, int accel) {
             n_prims = 1;
             any_diffuse |= scene.get_data(o.material).mat_kind == MAT_DIFFUSE;
         } else if (o.kind == OBJ_RECT) {
-            push_rect(prims, bounds, o.rect, tf, PRIM_RECT, resolve.material(o.rect.material), obj);
+            push_rect(prims, bounds, o.rect, tf, PRIM_RECT, resolve.material(o.rect.material), obj, aa_rects);
             n_prims = 1;
             any_diffuse |= scene.get_data(o.rect.material).mat_kind == MAT_DIFFUSE;
         } else if (o.kind == OBJ_CUBOID) {

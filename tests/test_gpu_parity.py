@@ -140,6 +140,36 @@ def test_render_contract(oracle):
     assert (mae_per_channel(one.data, ref, 8) <= IMAGE_MAE).all()
 
 
+@pytest.mark.parametrize("name,lens", [("cornell2", None), ("scene", LENS_SCENE)])
+def test_host_buffer_bands(oracle, name, lens, monkeypatch):
+    """bt_render with a host buffer pipelines the frame in row bands over two streams (upload and
+    download under the neighbouring band's kernel).  The image must not depend on the banding: one
+    band, three ragged bands, many bands and a device-resident buffer agree bit for bit, and the
+    running sums accumulate into a non-zero host buffer."""
+    import bendy_tracer_b200 as bt
+    w, h = 100, 70                                                  # ragged against 16-row CTAs and 8x4 tiles
+    _, esc, cam = load_pair(name, w, h, lenses=lens)
+    start = np.random.default_rng(3).random((h, w, 4), dtype=np.float32)
+    images = {}
+    for bands in ("1", "3", "64", None):
+        if bands is None:
+            monkeypatch.delenv("BT_HOST_BANDS", raising=False)
+        else:
+            monkeypatch.setenv("BT_HOST_BANDS", bands)
+        buf = bt.Buffer(w, h)
+        buf.data[...] = start
+        images[bands] = engine_render(esc, cam, w, h, 3, 2, 0, seed=9, buffer=buf)[0].copy()
+        assert buf.samples() == 12
+    for bands in ("3", "64", None):
+        assert np.array_equal(images[bands], images["1"]), bands
+    dev = bt.Buffer(w, h, device="cuda:0")
+    dev.data.copy_(__import__("torch").from_numpy(start))
+    got = engine_render(esc, cam, w, h, 3, 2, 0, seed=9, buffer=dev)[0]
+    assert np.array_equal(got, images["1"])
+    assert np.array_equal(images["1"][..., 3], start[..., 3])       # alpha untouched
+    assert (images["1"][..., :3] >= start[..., :3]).all() and (images["1"][..., :3] > start[..., :3]).mean() > 0.5
+
+
 def test_render_errors(oracle):
     import json
     import bendy_tracer_b200 as bt
@@ -208,6 +238,38 @@ def test_box_slab_test_equals_six_rect_tests(oracle, name):
     assert (mae_per_channel(img_box, img_faces, 8) <= 1e-4).all()
     ref, nref, _ = oracle_render(load_pair(name, w, h)[0], cam, w, h, 2, 2, 0, seed=4)
     assert (mae_per_channel(img_box, ref, nref) <= IMAGE_MAE).all()
+
+
+@pytest.mark.parametrize("name", ["cornell", "cornell2"])
+def test_axis_aligned_rect_test_is_bit_identical(name, monkeypatch):
+    """Rects whose normal and plane axes are exact coordinate axes (the Cornell walls) run
+    rect_test_aa, which picks components instead of forming dot products.  It must round exactly like
+    the general Rect::hit restatement: same images (both flavours) and same probe segments with the
+    specialisation switched off at flatten time (BT_NO_AA_RECTS)."""
+    import bendy_tracer_b200 as bt
+    w, h = 160, 120
+    rng = np.random.default_rng(5)
+    n = 100000
+    origins = rng.uniform([-2.4, 0.1, -4.9], [2.4, 4.9, -0.1], (n, 3)).astype(np.float32)
+    dirs = rng.normal(size=(n, 3))
+    dirs = (dirs / np.linalg.norm(dirs, axis=1, keepdims=True)).astype(np.float32)
+    out = {}
+    for aa in (True, False):
+        if aa:
+            monkeypatch.delenv("BT_NO_AA_RECTS", raising=False)
+        else:
+            monkeypatch.setenv("BT_NO_AA_RECTS", "1")
+        _, esc, cam = load_pair(name, w, h)                      # (flattened on first use, under this setting)
+        for prec in ("fast", "exact"):
+            esc.set_precision(prec)
+            out[aa, prec] = engine_render(esc, cam, w, h, 2, 2, 0, seed=13)[0].copy()
+            out[aa, prec, "seg"] = bt.Tracer(bt.Config(), seed=1).trace_segments(esc, origins, dirs)
+    for prec in ("fast", "exact"):
+        assert np.array_equal(out[True, prec], out[False, prec]), prec
+        a, b = out[True, prec, "seg"], out[False, prec, "seg"]
+        for field in ("t", "face", "object_ref", "position", "normal"):
+            assert np.array_equal(a[field], b[field]), (prec, field)
+        assert ((a["object_ref"] >= 1) & (a["object_ref"] <= 6)).mean() > 0.5                  # mostly walls
 
 
 # ---- lens field -----------------------------------------------------------------------------
