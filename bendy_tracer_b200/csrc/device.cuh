@@ -765,15 +765,15 @@ BT_DEV V3 with_frustum_dir(float yfov, float xfov, float u, float v) {
     float s3 = qw * 2.0f;
     return (vv * s1 + b * s2) + cross(b, vv) * s3;
 }
-BT_DEV void camera_ray(const CameraBlock& cam, const Consts& k, Rng& rng, uint32_t x, uint32_t y, uint32_t sub_index,
+// (sub_i, sub_j): the sub-pixel of this path, i fastest (mod.rs:70-106)
+BT_DEV void camera_ray(const CameraBlock& cam, const Consts& k, Rng& rng, uint32_t x, uint32_t y, uint32_t sub_i, uint32_t sub_j,
                        V3& origin, V3& direction) {
     float v = (float)y * cam.pixel_height - 1.0f;
     float u = (float)x * cam.pixel_width - 1.0f;
     float u_sub = 0.0f, v_sub = 0.0f;
     if (cam.sub_width != 0.0f) {
-        uint32_t i = sub_index % cam.sub_n, j = sub_index / cam.sub_n;
-        u_sub = (float)i * cam.sub_width;
-        v_sub = (float)j * cam.sub_width;
+        u_sub = (float)sub_i * cam.sub_width;
+        v_sub = (float)sub_j * cam.sub_width;
     }
     float u_offset = u_sub * cam.pixel_width + uniform_f32(rng, cam.su_low, cam.su_scale);
     float v_offset = v_sub * cam.pixel_height + uniform_f32(rng, cam.sv_low, cam.sv_scale);

@@ -228,6 +228,7 @@ BT_DEV void render_body(const RenderParams& p) {
 
     V3 acc = v3(0.0f, 0.0f, 0.0f);
     uint32_t path = 0;
+    uint32_t sub_i = 0, sub_j = 0;  // sub-pixel of the next path: path_base is a multiple of sub_count, so a call starts at (0, 0)
     bool alive = false, done = !valid;
     uint32_t st_scans = 0, st_steps = 0, st_events = 0;  // STATS only
 
@@ -260,7 +261,11 @@ BT_DEV void render_body(const RenderParams& p) {
         if (regen && !alive && !done) {
             if (path < p.paths_per_pixel) {
                 rng.seed_from_u64(splitmix_mix(pixel_key + 0xd1342543de82ef95ULL * (p.path_base + path + 1)));
-                camera_ray(p.cam, k, rng, px, py, path % p.sub_count, o, d);
+                camera_ray(p.cam, k, rng, px, py, sub_i, sub_j, o, d);
+                if (++sub_i == p.cam.sub_n) {  // the next path's sub-pixel, counted instead of divided out
+                    sub_i = 0;
+                    if (++sub_j == p.cam.sub_n) sub_j = 0;
+                }
                 T = v3(1.0f, 1.0f, 1.0f);
                 bounce = 0;
                 vb = 0;
@@ -641,7 +646,8 @@ __global__ void camera_rays_kernel(const __grid_constant__ RenderParams p, uint3
     const uint64_t pixel = (uint64_t)ys[i] * p.width + xs[i];
     rng.seed_from_u64(path_seed(p.seed, pixel, p.path_base + path_index[i]));
     V3 o, d;
-    camera_ray(p.cam, k, rng, xs[i], ys[i], (uint32_t)(path_index[i] % p.sub_count), o, d);
+    const uint32_t sub = (uint32_t)(path_index[i] % p.sub_count);
+    camera_ray(p.cam, k, rng, xs[i], ys[i], sub % p.cam.sub_n, sub / p.cam.sub_n, o, d);
     out[6 * i] = o.x; out[6 * i + 1] = o.y; out[6 * i + 2] = o.z;
     out[6 * i + 3] = d.x; out[6 * i + 4] = d.y; out[6 * i + 5] = d.z;
 }
