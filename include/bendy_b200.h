@@ -168,7 +168,10 @@ void bt_render_config_default(bt_render_config* cfg);  /* RenderConfig::DEFAULT,
  * seed / sample_base key the per-path RNG stream (replaces SmallRng::from_entropy, mod.rs:240):
  * pass s of this call uses global pass index sample_base + s, so disjoint [sample_base,
  * sample_base + samples) ranges on different GPUs render disjoint sample sets of one image.
- * Blocking.  mem = BT_MEM_HOST copies the buffer to the device and back inside the call. */
+ * Blocking.  mem = BT_MEM_HOST copies the buffer to the device and back inside the call: the frame
+ * is pipelined through the GPU in row bands over two streams (upload and download of a band run
+ * under its neighbours' kernels; pin the buffer -- cudaHostAlloc / cudaHostRegister -- for the
+ * overlap to be real).  The image does not depend on the banding (BT_HOST_BANDS=n overrides it). */
 int bt_render(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_config* config,
               const bt_render_config* render_config, uint64_t seed, uint64_t sample_base,
               float* rgba32f, int mem, uint32_t width, uint32_t height, uint64_t* samples_inout,

@@ -14,3 +14,5 @@ python tools/prof_target.py > gpurun_out/final_plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k 'regex:render_kernel|integrate_kernel' --launch-skip 6 --launch-count 6 -o gpurun_out/final_prof -f python tools/prof_target.py > gpurun_out/final_ncu_full.log 2>&1
 tail -3 gpurun_out/final_ncu_full.log
 cat gpurun_out/final_pytest.log
+python tools/prof_one.py cloud 16 > gpurun_out/final_plain_cloud.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k 'regex:render_kernel' --launch-skip 1 --launch-count 1 -o gpurun_out/final_prof_cloud -f python tools/prof_one.py cloud 16 > gpurun_out/final_ncu_cloud.log 2>&1

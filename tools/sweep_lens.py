@@ -48,19 +48,27 @@ def main():
     if "--one" in sys.argv:
         return one()
     configs = [
-        {"BT_LENS_NO_SKIP": "1", "BT_SCAN_LANES": "1", "BT_SCAN_PATIENCE": "1"},   # the previous behaviour: scan with every step
-        {"BT_LENS_NO_SKIP": "1"},
-        {"BT_SCAN_LANES": "1", "BT_SCAN_PATIENCE": "1"},
         {},
+        {"BT_SCAN_LANES": "1", "BT_SCAN_PATIENCE": "1"},
+        {"BT_SCAN_LANES": "4", "BT_SCAN_PATIENCE": "1"},
+        {"BT_SCAN_LANES": "6", "BT_SCAN_PATIENCE": "1"},
+        {"BT_SCAN_LANES": "6", "BT_SCAN_PATIENCE": "2"},
         {"BT_SCAN_LANES": "8", "BT_SCAN_PATIENCE": "2"},
-        {"BT_SCAN_LANES": "8", "BT_SCAN_PATIENCE": "4"},
+        {"BT_SCAN_LANES": "12", "BT_SCAN_PATIENCE": "4"},
         {"BT_SCAN_LANES": "16", "BT_SCAN_PATIENCE": "4"},
-        {"BT_SCAN_LANES": "16", "BT_SCAN_PATIENCE": "8"},
-        {"BT_SCAN_LANES": "24", "BT_SCAN_PATIENCE": "8"},
-        {"BT_SCAN_LANES": "24", "BT_SCAN_PATIENCE": "16"},
-        {"BT_COMPACT_LANES": "16", "BT_COMPACT_PATIENCE": "32"},
-        {"BT_COMPACT_LANES": "4", "BT_COMPACT_PATIENCE": "8"},
+        {"BT_SCAN_LANES": "6", "BT_SCAN_PATIENCE": "1", "BT_STEPS_PER_TURN": "1"},
+        {"BT_SCAN_LANES": "6", "BT_SCAN_PATIENCE": "2", "BT_STEPS_PER_TURN": "3"},
+        {"BT_SCAN_LANES": "6", "BT_SCAN_PATIENCE": "1", "BT_COMPACT_LANES": "8", "BT_COMPACT_PATIENCE": "8"},
+        {"BT_SCAN_LANES": "6", "BT_SCAN_PATIENCE": "1", "BT_COMPACT_LANES": "16", "BT_COMPACT_PATIENCE": "16"},
     ]
+    if "--old" in sys.argv:
+        configs = [
+            {"BT_LENS_NO_SKIP": "1", "BT_SCAN_LANES": "1", "BT_SCAN_PATIENCE": "1"},   # scan with every step
+            {"BT_LENS_NO_SKIP": "1"},
+            {"BT_SCAN_LANES": "24", "BT_SCAN_PATIENCE": "8"},
+            {"BT_COMPACT_LANES": "16", "BT_COMPACT_PATIENCE": "32"},
+            {"BT_COMPACT_LANES": "4", "BT_COMPACT_PATIENCE": "8"},
+        ]
     for c in configs:
         env = dict(os.environ)
         env.update(c)
