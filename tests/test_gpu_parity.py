@@ -170,6 +170,78 @@ def test_host_buffer_bands(oracle, name, lens, monkeypatch):
     assert (images["1"][..., :3] != start[..., :3]).mean() > 0.5      # (a Diffuse pdf may be negative: sums can shrink)
 
 
+def test_render_config_overrides(oracle):
+    """RenderConfig overrides merged onto the tracer's Config (ChunkConfig::with_configs, mod.rs:218-229):
+    max_bounces (which also overrides max_volume_bounces -- the :224 quirk), volume_step, output."""
+    import bendy_tracer_b200 as bt
+    w, h = 96, 64
+    for name, kw, okw in (("cornell2", dict(max_bounces=2), dict(r_max_bounces=2)),
+                          ("cloud", dict(max_bounces=3), dict(r_max_bounces=3)),          # march cut to 3 steps
+                          ("cloud", dict(volume_step=0.05, max_volume_bounces=7), dict(r_volume_step=0.05, r_max_volume_bounces=7)),
+                          ("scene", dict(output=bt.Output.Normal, max_bounces=0), dict(r_output=2, r_max_bounces=0))):
+        osc, esc, cam = load_pair(name, w, h)
+        cfg = O.make_config(samples=2, subsample=2, **okw)
+        ref, n, _ = osc.render(cam, cfg, w, h, seed=31, sample_base=0)
+        default, _, _ = oracle_render(osc, cam, w, h, 2, 2, 0, seed=31)
+        assert not np.array_equal(ref, default)                   # the override changes the image
+        esc.set_precision("exact")
+        buf = bt.Buffer(w, h)
+        rc = bt.RenderConfig(samples=2, subsample=bt.Subsample(2), **kw)
+        bt.Tracer(bt.Config(chunks_x=8, chunks_y=4), seed=31).render(esc, cam, rc, buf)
+        assert buf.samples() == n == 8
+        assert (mae_per_channel(buf.data, ref, n) <= 1e-6).all(), (name, kw, mae_per_channel(buf.data, ref, n))
+
+
+def test_many_lights(oracle):
+    """Three LIGHT objects of different kinds (rect, sphere, and a flagged camera -> Object::random_point's
+    `_ => translation` arm with pdf None): Uniform::new(0, 3) goes through the rejection zone
+    (RenderParams::light_zone), every light kind is sampled and its pdf evaluated."""
+    import copy
+    import json
+    import bendy_tracer_b200 as bt
+    doc = copy.deepcopy(O.read_scene_json(O.scene_path("cornell")))
+    objs = doc["objects"]["collection"]
+    key = doc["objects"]["next_key"]
+    tf = [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0, -1.0, 3.0, -1.5]
+    objs[str(key)] = {"object_ref": key, "tag": None, "flags": {"bits": 1},
+                      "transform": {"transform_world": tf, "transform_local": tf, "transform_parent": None},
+                      "inner": {"Sphere": {"material": 1, "volume": None, "radius": 0.3}}, "children": None}
+    doc["objects"]["next_key"] = key + 1
+    objs["0"]["flags"]["bits"] = 1                                # the camera as a (point) light: never hit, pdf 0
+    w, h = 96, 96
+    osc = O.OracleScene(doc)
+    esc = bt.Scene.from_json(json.dumps(doc))
+    cam = esc.find_by_tag("camera")
+    for s_ in (osc, esc):
+        s_.set_camera_aspect(cam, 1.0)
+    assert esc.info()["n_lights"] == 3
+    ref, n, _ = oracle_render(osc, cam, w, h, 4, 2, 0, seed=41)
+    esc.set_precision("exact")
+    exact = engine_render(esc, cam, w, h, 4, 2, 0, seed=41)[0].copy()
+    # a small, intense sphere light sampled without a cosine: single paths carry sums of 10..100, so one
+    # path that libm's and CUDA's sincos round differently (~1e-4 of arguments) moves the mean by 1e-5 --
+    # all but a handful of pixels agree to f32 rounding
+    assert (mae_per_channel(exact, ref, n) <= 1e-4).all(), mae_per_channel(exact, ref, n)
+    rel = np.abs(exact[..., :3] - ref[..., :3]) / (np.abs(ref[..., :3]) + 1.0)
+    assert (rel > 1e-4).mean() < 2e-3, [(t, float((rel > t).mean())) for t in (1e-6, 1e-5, 1e-4, 1e-3, 1e-2)]
+    esc.set_precision("fast")
+    fast = engine_render(esc, cam, w, h, 4, 2, 0, seed=41)[0]
+    assert (mae_per_channel(fast, ref, n) <= IMAGE_MAE).all()
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (7, 3), (17, 33)])
+def test_tiny_and_ragged_frames(oracle, w, h):
+    """frames smaller than one 8x4 warp tile / one 16x16 CTA, and ragged against both"""
+    for name in ("cornell", "scene"):
+        osc, esc, cam = load_pair(name, w, h)
+        ref, n, _ = oracle_render(osc, cam, w, h, 3, 2, 0, seed=8)
+        esc.set_precision("exact")
+        got, n2, _ = engine_render(esc, cam, w, h, 3, 2, 0, seed=8)
+        assert n == n2 == 12 and got.shape == (h, w, 4)
+        assert (mae_per_channel(got, ref, n) <= 1e-6).all()
+        assert np.array_equal(got[..., 3], ref[..., 3])
+
+
 def test_render_errors(oracle):
     import json
     import bendy_tracer_b200 as bt
