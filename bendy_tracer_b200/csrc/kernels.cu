@@ -9,6 +9,8 @@
 #include "device.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
+
 #ifdef BT_EXACT_SCAN
 #define BT_SFX(name) name##_exact
 #else
@@ -590,7 +592,8 @@ BT_DEV void render_body(const RenderParams& p) {
 }
 
 // Lensed variants carry the flight state on top of the path state: 128-thread CTAs at 5 per SM give
-// them 96 registers (20 warps / SM) instead of 80 with spills (24 warps / SM).
+// them 96 registers (20 warps / SM) instead of 80 with spills (24 warps / SM).  The flat variants keep
+// the 85-register cap of (256, 3) and are launched with 128 threads as well (launch_render).
 template <bool LENS, bool EXACT, int NL, bool BVH, int C = CT_ALL>
 __global__ void __launch_bounds__(LENS ? 128 : 256, LENS ? 5 : 3) render_kernel(const __grid_constant__ RenderParams p) {
     render_body<false, LENS, EXACT, NL, BVH, C>(p);
@@ -732,8 +735,8 @@ cudaError_t ensure_smem(K kernel, size_t bytes) {
 }  // namespace
 
 #ifndef BT_EXACT_SCAN
-size_t render_smem_bytes(const RenderParams& p) {
-    return (size_t)p.scene.stage_f4 * sizeof(float4) + (p.scene.n_bvh ? (size_t)BVH_STACK * 256 * 2 * sizeof(uint32_t) : 0);
+size_t render_smem_bytes(const RenderParams& p, unsigned threads) {
+    return (size_t)p.scene.stage_f4 * sizeof(float4) + (p.scene.n_bvh ? (size_t)BVH_STACK * threads * 2 * sizeof(uint32_t) : 0);
 }
 
 #endif
@@ -759,10 +762,12 @@ size_t render_smem_bytes(const RenderParams& p) {
     } while (0)
 
 cudaError_t BT_SFX(launch_render)(const RenderParams& p, cudaStream_t stream, uint64_t* launches) {
-    const bool small = p.scene.n_lens != 0 && !p.stats;
+    // 128-thread CTAs (16 x 8 pixels): at 72..78 registers seven of them fit an SM (28 warps) where three
+    // 256-thread CTAs gave 24 -- cornell2 +3.7 %; BT_WIDE_CTAS=1 keeps 256 threads for the flat kernels (A/B)
+    const bool small = !p.stats && (p.scene.n_lens != 0 || !std::getenv("BT_WIDE_CTAS"));
     const uint32_t rows = p.row_end - p.row0;
     dim3 grid((p.width + 15) / 16, small ? (rows + 7) / 8 : (rows + 15) / 16), block(small ? 128 : 256);
-    size_t smem = render_smem_bytes(p);
+    size_t smem = render_smem_bytes(p, block.x);
     // content-specialised variants (device.cuh CT_*): the smallest compiled superset of what the scene holds
 #define BT_LAUNCH_C_(L, N, C)                                                                          \
     do {                                                                                               \

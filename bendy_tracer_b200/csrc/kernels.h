@@ -42,7 +42,7 @@ cudaError_t launch_resolve(const float4* fb, uint32_t n_pixels, uint64_t samples
                            cudaStream_t stream, uint64_t* launches);
 cudaError_t launch_fp32_peak(float* out, uint32_t iters, int blocks, cudaStream_t stream, uint64_t* launches);
 
-size_t render_smem_bytes(const RenderParams& p);
+size_t render_smem_bytes(const RenderParams& p, unsigned threads = 256);
 enum { FP32_PEAK_THREADS = 256, FP32_PEAK_CHAINS = 8, FP32_PEAK_UNROLL = 16 };
 
 }  // namespace bt
