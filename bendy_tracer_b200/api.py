@@ -322,6 +322,28 @@ class Buffer:
         self._preview = None
         self._samples = 0
 
+    def chunks(self, chunks_x, chunks_y):
+        """Buffer::chunks + Chunks::next (buffer.rs:102-115, 293-326): ceil-div tile size, row-major
+        enumeration, last row / column clipped.  Yields (min_x, min_y, max_x, max_y).  The engine does not
+        schedule by these tiles (Config.chunks_* only ever affected scheduling); the iterator is kept
+        for callers that walk the reference's tiles."""
+        w, h = self.width(), self.height()
+        if chunks_x <= 0 or chunks_y <= 0:
+            raise ZeroDivisionError("attempt to calculate the remainder with a divisor of zero")   # the reference panics
+        cw = w // chunks_x if w % chunks_x == 0 else w // chunks_x + 1
+        ch = h // chunks_y if h % chunks_y == 0 else h // chunks_y + 1
+        ox = oy = 0
+        done = False
+        while not done:
+            tw, th = min(cw, w - ox), min(ch, h - oy)
+            yield (ox, oy, ox + tw, oy + th)
+            ox += tw
+            if ox == w:
+                ox = 0
+                oy += th
+            if oy == h:
+                done = True
+
     def _ptr_mem(self):
         if isinstance(self.data, np.ndarray):
             return self.data.ctypes.data, _ffi.MEM_HOST

@@ -721,9 +721,7 @@ BT_DEV V3 light_point(Rng& rng, const Consts& k, const float4* light) {
 }
 
 // DensityMap::sample(Trilinear), volume.rs:140-167
-BT_DEV float density_at(const float* g, int w, int h, float x, float y, float z) {
-    return __ldg(g + ((int)z * h + (int)y) * w + (int)x);
-}
+BT_DEV float density_at(const float* g, int w, int h, int x, int y, int z) { return __ldg(g + (z * h + y) * w + x); }
 BT_DEV float density_trilinear(const float4* vol, const float* grids, V3 coord) {
     float4 v0 = vol[0], v1 = vol[1];
     int w = __float_as_int(v0.x), h = __float_as_int(v0.y), dd = __float_as_int(v0.z);
@@ -732,19 +730,23 @@ BT_DEV float density_trilinear(const float4* vol, const float* grids, V3 coord) 
     float cx = fminf(fmaxf(coord.x, 0.0f), 1.0f) * v1.x;
     float cy = fminf(fmaxf(coord.y, 0.0f), 1.0f) * v1.y;
     float cz = fminf(fmaxf(coord.z, 0.0f), 1.0f) * v1.z;
-    float fx = floorf(cx), ux = ceilf(cx), fy = floorf(cy), uy = ceilf(cy), fz = floorf(cz), uz = ceilf(cz);
-    float tx = cx - truncf(cx), ty = cy - truncf(cy), tz = cz - truncf(cz);
-    float x0 = density_at(g, w, h, fx, fy, fz), x1 = density_at(g, w, h, ux, fy, fz);
-    float y0 = lerpf(x0, x1, tx);
-    x0 = density_at(g, w, h, fx, uy, fz); x1 = density_at(g, w, h, ux, uy, fz);
-    float y1 = lerpf(x0, x1, tx);
-    float z0 = lerpf(y0, y1, ty);
-    x0 = density_at(g, w, h, fx, fy, uz); x1 = density_at(g, w, h, ux, fy, uz);
-    y0 = lerpf(x0, x1, tx);
-    x0 = density_at(g, w, h, fx, uy, uz); x1 = density_at(g, w, h, ux, uy, uz);
-    y1 = lerpf(x0, x1, tx);
-    float z1 = lerpf(y0, y1, ty);
-    return lerpf(z0, z1, tz);
+    // floor / ceil / fract of the reference (volume.rs:143-166) for c >= 0: one conversion each way per axis
+    // (floor = trunc, ceil = floor + (c != floor), fract = c - trunc) instead of three roundings and two casts
+    const int x0 = __float2int_rz(cx), y0 = __float2int_rz(cy), z0 = __float2int_rz(cz);
+    const float fx = (float)x0, fy = (float)y0, fz = (float)z0;
+    const int x1 = x0 + (cx > fx ? 1 : 0), y1 = y0 + (cy > fy ? 1 : 0), z1 = z0 + (cz > fz ? 1 : 0);
+    const float tx = cx - fx, ty = cy - fy, tz = cz - fz;
+    float a = density_at(g, w, h, x0, y0, z0), b = density_at(g, w, h, x1, y0, z0);
+    float r0 = lerpf(a, b, tx);
+    a = density_at(g, w, h, x0, y1, z0); b = density_at(g, w, h, x1, y1, z0);
+    float r1 = lerpf(a, b, tx);
+    float s0 = lerpf(r0, r1, ty);
+    a = density_at(g, w, h, x0, y0, z1); b = density_at(g, w, h, x1, y0, z1);
+    r0 = lerpf(a, b, tx);
+    a = density_at(g, w, h, x0, y1, z1); b = density_at(g, w, h, x1, y1, z1);
+    r1 = lerpf(a, b, tx);
+    float s1 = lerpf(r0, r1, ty);
+    return lerpf(s0, s1, tz);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -228,6 +228,25 @@ def test_buffer_mirror():
     assert b.dimensions() == (3, 2) and b.maybe_preview() is None and b.take_preview() is None
 
 
+@pytest.mark.parametrize("w,h,cx,cy", [(512, 512, 8, 4), (1920, 1080, 8, 4), (100, 70, 8, 4), (7, 3, 4, 2), (5, 5, 8, 8)])
+def test_buffer_chunks(w, h, cx, cy):
+    """Buffer::chunks / Chunks::next (buffer.rs:102-115, 293-326): the tiles partition the image, in
+    row-major order, ceil-div sized with the last row / column clipped"""
+    buf = bt.Buffer(w, h)
+    tiles = list(buf.chunks(cx, cy))
+    cover = np.zeros((h, w), np.int32)
+    cw, ch = -(-w // cx), -(-h // cy)
+    for i, (x0, y0, x1, y1) in enumerate(tiles):
+        assert 0 <= x0 < x1 <= w and 0 <= y0 < y1 <= h and x1 - x0 <= cw and y1 - y0 <= ch
+        assert x0 % cw == 0 and y0 % ch == 0
+        cover[y0:y1, x0:x1] += 1
+    assert (cover == 1).all()
+    assert tiles == sorted(tiles, key=lambda t: (t[1], t[0]))
+    assert len(tiles) == -(-w // cw) * -(-h // ch)
+    if (w, h, cx, cy) == (512, 512, 8, 4):
+        assert tiles[0] == (0, 0, 64, 128) and len(tiles) == 32           # SURVEY 8a row 1: C1 tiles are 64 x 128
+
+
 def test_shard_passes_partition():
     for samples in (1, 7, 64, 1024):
         for world in (1, 2, 3, 4, 8):
