@@ -142,7 +142,8 @@ void bt_lens_config_default(bt_lens_config* cfg);
  * volumetric spheres always use the scan (hit_volumetric depends on the scan order, :414-424). */
 enum { BT_ACCEL_AUTO = 0, BT_ACCEL_LINEAR = 1, BT_ACCEL_BVH = 2,
        BT_ACCEL_LINEAR_FACES = 3 /* the scan with every Cuboid as its six Rect::hit tests (cuboid.rs:83-105, literally);
-                                    the other modes test a box-shaped cuboid with one slab test */ };
+                                    the other modes test a box-shaped cuboid with one slab test and an
+                                    axis-aligned Rect with a component-picking test that rounds identically) */ };
 int bt_scene_set_accel(bt_scene* scene, int accel);
 /* Arithmetic flavour of the render / trace / camera-ray kernels for this scene.  EXACT: every
  * division, square root and dot product is the IEEE operation sequence of the reference (values
