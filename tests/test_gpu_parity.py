@@ -517,6 +517,46 @@ def test_full_size_properties():
     assert (m > 0.05).all() and (m < 1.0).all()                      # a lit Cornell box
 
 
+def test_full_size_properties_c3_c4():
+    """BASELINE configs C3 (scene + lens, 3840x2160) and C4 (cloud, 1920x1080) at full frame size and
+    reduced spp: determinism, pass-range additivity, the r_s = 0 control (bit-identical to the unlensed
+    frame), a host frame through the band pipeline == the device-resident frame, finite sums."""
+    import torch
+    import bendy_tracer_b200 as bt
+    for name, w, h, lens in (("scene", 3840, 2160, LENS_SCENE), ("cloud", 1920, 1080, None)):
+        esc = bt.Scene.load(O.scene_path(name))
+        cam = esc.find_by_tag("camera")
+        esc.set_camera_aspect(cam, w / h)
+        tracer = bt.Tracer(bt.Config(), seed=2)
+        rc = bt.RenderConfig.with_samples_subsample(2, bt.Subsample(2))
+        one = bt.RenderConfig.with_samples_subsample(1, bt.Subsample(2))
+        flat = bt.Buffer(w, h, device="cuda:0")
+        tracer.render(esc, cam, rc, flat)
+        if lens is not None:
+            esc.set_lenses(np.array([[1.0, 1.0, 5.0, 0.0]], np.float32))   # a mass without mass
+            ctrl = bt.Buffer(w, h, device="cuda:0")
+            tracer.render(esc, cam, rc, ctrl)
+            assert bool((ctrl.data == flat.data).all())
+            esc.set_lenses(lens)
+        a = bt.Buffer(w, h, device="cuda:0")
+        b = bt.Buffer(w, h, device="cuda:0")
+        tracer.render(esc, cam, rc, a)
+        tracer.render(esc, cam, rc, b)
+        assert bool((a.data == b.data).all()) and bool(a.data.isfinite().all()) and bool((a.data[..., 3] == 1.0).all())
+        if lens is not None:
+            assert float((a.data - flat.data).abs().mean()) > 1e-3       # the lens really bends the image
+        c = bt.Buffer(w, h, device="cuda:0")
+        tracer.render(esc, cam, one, c, sample_base=0)
+        tracer.render(esc, cam, one, c, sample_base=1)
+        assert c.samples() == a.samples() == 8
+        assert float((a.data - c.data).abs().max()) <= 1e-3 * float(a.data[..., :3].abs().max())
+        host = bt.Buffer(w, h)                                           # 133 MB at 4K: 8 bands over two streams
+        tracer.render(esc, cam, rc, host)
+        assert np.array_equal(host.data, a.data.cpu().numpy())
+        del a, b, c, flat
+        torch.cuda.empty_cache()
+
+
 # ---- BVH (scenes above the linear-scan budget) -------------------------------------------------
 @pytest.mark.parametrize("name,lens", [("cornell", None), ("scene", None), ("scene", LENS_SCENE)])
 def test_bvh_equals_linear_scan_on_shipped_scenes(name, lens):
