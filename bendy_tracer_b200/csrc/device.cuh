@@ -424,16 +424,41 @@ BT_DEV bool box_test(const float4* b, V3 o, V3 d, float tmin, float tmax, float&
 // CT_AOV: the call renders Output::Albedo / Normal / Depth (the first-hit latches of mod.rs:306-315).
 // CT_CUBOID_LIGHT: a Cuboid carries ObjectFlags::LIGHT (WeightedIndex face pick, cuboid.rs:48-81; generic kernels only).
 enum { CT_SPHERES = 1, CT_RECTS = 2, CT_VOLUMES = 4, CT_METAL = 8, CT_GLASS = 16, CT_AOV = 32, CT_CUBOID_LIGHT = 64, CT_ALL = 127 };
+// What a DIST scan learns about the surroundings of the ray's origin: the smallest per-primitive
+// bound, the primitive it belongs to when that is a sphere (-1 otherwise) and the smallest bound among
+// all the other primitives.  The stepper re-evaluates the nearest sphere's distance exactly at every
+// step (sphere_free_bound) and lets only `rest` decay with the distance flown.
+struct FreeInfo {
+    float nearest, rest;
+    int sphere;
+};
+BT_DEV void free_update(FreeInfo& fi, float b, int sphere) {
+    if (b < fi.nearest) {
+        fi.rest = fi.nearest;
+        fi.nearest = b;
+        fi.sphere = sphere;
+    } else {
+        fi.rest = fminf(fi.rest, b);
+    }
+}
+// lower bound on the distance from o to the surface of the sphere record q, minus the margin that
+// covers the rounding of Sphere::hit itself (see scan_prims_t<DIST>); l2 = |o - c|^2
+BT_DEV float sphere_free_bound(float4 q0, float4 q1, float l2) {
+    const float dc = sqrt_approx(l2);
+    return fabsf(dc - q0.w) - (l2 * q1.z + 2e-5f * (dc + q0.w) + 1e-6f);
+}
 template <bool DIST, int C = CT_ALL, bool FLIGHT = false>
 BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, const float4* boxes, int n_prims, V3 o, V3 d, float tmin,
-                        float tmax, int volume_obj, float* free_out) {
+                        float tmax, int volume_obj, FreeInfo* free_out) {
     (void)bounds;
     (void)boxes;
     Hit h;
     h.t = tmax;
     h.prim = -1;
     h.face = 0;
-    float free = __int_as_float(0x7f800000);
+    FreeInfo fi;
+    fi.nearest = fi.rest = __int_as_float(0x7f800000);
+    fi.sphere = -1;
     for (int i = 0; i < n_prims; ++i) {
         const float4* q = prims + i * PRIM_STRIDE;
         float4 meta = q[4];
@@ -459,8 +484,7 @@ BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, const float4*
                 // (the residual of the quadratic, however ill-conditioned t itself is for a grazing
                 // ray), so dist(o, surface) <= t + that: the margin below is 20x it, plus the rounding
                 // of this bound.  q1.z = 2e-5 / r.
-                const float dc = sqrt_approx(l2);
-                free = fminf(free, fabsf(dc - q0.w) - (l2 * q1.z + 2e-5f * (dc + q0.w) + 1e-6f));
+                free_update(fi, sphere_free_bound(q0, q1, l2), i);
             }
             if (sphere_roots_oc<FLIGHT>(oc, l2, r2, d, tmin, h.t, t)) {
                 h.t = t;
@@ -475,7 +499,7 @@ BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, const float4*
                 int face;
                 float bd;
                 const bool hit = box_test(boxes + (__float_as_int(meta.z) - 1) * BOX_STRIDE, o, d, tmin, h.t, t, face, front, DIST ? &bd : nullptr);
-                if (DIST) free = fminf(free, bd - (1e-4f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + bd) + 1e-4f));
+                if (DIST) free_update(fi, bd - (1e-4f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + bd) + 1e-4f), -1);
                 if (hit) {
                     h.t = t;
                     h.prim = i + face;
@@ -488,7 +512,7 @@ BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, const float4*
                 const float4 lo = bounds[i * BOUND_STRIDE], hi = bounds[i * BOUND_STRIDE + 1];
                 const float dx = fmaxf(lo.x - o.x, o.x - hi.x), dy = fmaxf(lo.y - o.y, o.y - hi.y), dz = fmaxf(lo.z - o.z, o.z - hi.z);
                 const float m = 1e-4f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + fabsf(hi.x - lo.x) + fabsf(hi.y - lo.y) + fabsf(hi.z - lo.z)) + 1e-4f;
-                free = fminf(free, fmaxf(fmaxf(dx, dy), dz) - m);
+                free_update(fi, fmaxf(fmaxf(dx, dy), dz) - m, -1);
             }
             bool hit;
             if (type == PRIM_RECT_AA) {  // (uniform across the warp)
@@ -505,7 +529,7 @@ BT_DEV Hit scan_prims_t(const float4* prims, const float4* bounds, const float4*
             }
         }
     }
-    if (DIST) *free_out = free;
+    if (DIST) *free_out = fi;
     return h;
 }
 template <int C = CT_ALL>

@@ -184,12 +184,12 @@ int build_params(bt_scene* s, uint64_t camera_ref, bool need_camera, const bt_co
     p.regen_patience = long_flights ? 8 : (cheap_scans ? 32 : 16);
     if (const char* e = std::getenv("BT_REGEN_LANES")) p.regen_lanes = (uint32_t)std::atoi(e);
     if (const char* e = std::getenv("BT_REGEN_PATIENCE")) p.regen_patience = (uint32_t)std::atoi(e);
-    p.scan_lanes = 12;
-    p.scan_patience = 2;
+    p.scan_lanes = 8;      // (profiles/r1_sweep_nearest_sphere_bound.log: flat within 1 % from 6/2 to 8/4)
+    p.scan_patience = 3;
     if (const char* e = std::getenv("BT_SCAN_LANES")) p.scan_lanes = (uint32_t)std::atoi(e);
     if (const char* e = std::getenv("BT_SCAN_PATIENCE")) p.scan_patience = (uint32_t)std::atoi(e);
     if (std::getenv("BT_LENS_NO_SKIP")) p.scene.lens_skip = 0;
-    p.steps_per_turn = 2;
+    p.steps_per_turn = long_flights ? 3 : 2;
     if (const char* e = std::getenv("BT_STEPS_PER_TURN")) p.steps_per_turn = (uint32_t)std::max(1, std::atoi(e));
     p.tau_scale = uniform_scale_inclusive(0.0f, 6.28318530717958647692f);
     p.one_scale = uniform_scale_inclusive(0.0f, 1.0f);

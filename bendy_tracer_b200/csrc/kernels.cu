@@ -86,6 +86,8 @@ struct Flight {
     float travelled;
     uint32_t steps, scans;
     float free;  // no primitive surface lies within this distance of x (<= 0: unknown)
+    float rest;  // the same for every primitive but `near`, whose distance is re-evaluated at each step
+    int near;    // the sphere that bounded `free` at the last intersection pass (-1: none / not a sphere)
     V3 xp;       // start of the last chord xp -> x that needed / needs an intersection test
     Hit h;       // FL_HIT / FL_HIT_FAR: the hit on that chord (t relative to its start)
 };
@@ -100,7 +102,8 @@ enum { FL_FLY = 0, FL_PEND = 1, FL_PEND_FAR = 2, FL_HIT = 4, FL_HIT_FAR = 5, FL_
 BT_DEV void flight_reset(Flight& f) {
     f.travelled = 0.0f;
     f.steps = f.scans = 0;
-    f.free = 0.0f;
+    f.free = f.rest = 0.0f;
+    f.near = -1;
     f.xp = v3(0.0f, 0.0f, 0.0f);
     f.h.t = 0.0f;
     f.h.prim = -1;
@@ -108,8 +111,12 @@ BT_DEV void flight_reset(Flight& f) {
 }
 // STEP phase: one RK4 step of a bent ray.  A chord shorter than the free distance cannot touch
 // anything and is committed at once; otherwise it is left pending for the intersection phase.
-template <bool EXACT, class L>
-BT_DEV int geodesic_step(const RenderParams& p, const L& lens, V3& x, V3& v, Flight& f, float tmax) {
+// The free distance decays with the distance flown, except for the sphere that bounded it at the
+// last intersection pass: its distance is evaluated afresh at the chord's start, so a ray that flies
+// along a large surface (the r = 100 ground sphere, a unit or three below most of every path) keeps its
+// free distance instead of spending it after a few steps (C3: 23.7 -> 12.8 intersection passes per path, cloud + lens 28.6 -> 18.8).
+template <bool EXACT, int C, class L>
+BT_DEV int geodesic_step(const RenderParams& p, const L& lens, const float4* prims, V3& x, V3& v, Flight& f, float tmax) {
     float rmin;
     bool captured, far;
     D0Cache<L> cache;
@@ -117,11 +124,19 @@ BT_DEV int geodesic_step(const RenderParams& p, const L& lens, V3& x, V3& v, Fli
     if (captured) return FL_CAPTURED;
     if (far) return FL_PEND_FAR;
     const V3 x0 = x;
+    float free = f.free;
+    if ((C & CT_SPHERES) && f.near >= 0) {
+        const float4* q = prims + f.near * PRIM_STRIDE;
+        const float4 q0 = q[0], q1 = q[1];
+        const V3 oc = x0 - v3(q0);
+        free = fminf(sphere_free_bound(q0, q1, fmaf(oc.z, oc.z, fmaf(oc.y, oc.y, oc.x * oc.x))), f.rest);
+    }
     rk4_from_k1<EXACT>(lens, cache, x, v, k1, step_size(p.scene.kappa, p.scene.h_min, p.scene.h_max, rmin));
     float len;
     (void)normalize_fma<EXACT>(x - x0, &len);
-    if (len * 1.02f < f.free) {  // nothing within reach: the chord needs no intersection test
-        f.free -= len;
+    if (len * 1.02f < free) {  // nothing within reach: the chord needs no intersection test
+        f.free = free - len;
+        f.rest -= len;
         f.travelled += len;
         f.steps++;
         return (f.travelled >= tmax || f.steps >= p.scene.max_steps) ? FL_ESCAPED : FL_FLY;
@@ -140,7 +155,9 @@ BT_DEV int geodesic_scan(const RenderParams& p, const SceneView& sc, V3 x, V3 v,
     float len;
     const V3 dir = normalize_fma<EXACT>(far ? v : x - f.xp, &len);
     const float cmax = far ? remaining : fminf(len, remaining);
-    float bound = 0.0f;
+    FreeInfo bound;
+    bound.nearest = bound.rest = 0.0f;
+    bound.sphere = -1;
     if (BVH)
         f.h = bvh_closest<!EXACT>(sc.prims, sc.nodes, sc.stack, o, dir, cmin, cmax);
     else if (p.scene.lens_skip)
@@ -152,7 +169,9 @@ BT_DEV int geodesic_scan(const RenderParams& p, const SceneView& sc, V3 x, V3 v,
     if (far) return FL_ESCAPED;
     f.travelled += len;
     f.steps++;
-    f.free = bound - len;  // the bound was taken at the chord's start
+    f.free = bound.nearest - len;  // the bounds were taken at the chord's start
+    f.rest = bound.rest - len;
+    f.near = bound.sphere;
     return (f.travelled >= tmax || f.steps >= p.scene.max_steps) ? FL_ESCAPED : FL_FLY;
 }
 // the event of a resolved flight
@@ -181,7 +200,7 @@ BT_DEV Traced trace_ray(const RenderParams& p, const SceneView& sc, const L& len
     int st = FL_FLY;
 #pragma unroll 1
     while (st < FL_HIT) {
-        st = geodesic_step<EXACT>(p, lens, o, d, f, tmax);
+        st = geodesic_step<EXACT, CT_ALL>(p, lens, sc.prims, o, d, f, tmax);
         if (st == FL_PEND || st == FL_PEND_FAR) st = geodesic_scan<EXACT, BVH>(p, sc, o, d, f, st, tmin, tmax);
     }
     return flight_result<EXACT>(st, o, d, f);
@@ -348,7 +367,7 @@ BT_DEV void render_body(const RenderParams& p) {
             for (;;) {
 #pragma unroll 1
                 for (uint32_t r = 0; r < p.steps_per_turn; ++r)  // several steps per turn amortise the ballots below
-                    if (ls == FL_FLY) ls = geodesic_step<EXACT>(p, lens, o, d, fl, p.clip_max);
+                    if (ls == FL_FLY) ls = geodesic_step<EXACT, C>(p, lens, sc.prims, o, d, fl, p.clip_max);
                 const bool pend = ls == FL_PEND || ls == FL_PEND_FAR;
                 unsigned m_pend = __ballot_sync(0xffffffffu, pend);
                 unsigned m_fly = __ballot_sync(0xffffffffu, ls == FL_FLY);

@@ -49,17 +49,14 @@ def main():
         return one()
     configs = [
         {},
-        {"BT_SCAN_LANES": "1", "BT_SCAN_PATIENCE": "1"},
         {"BT_SCAN_LANES": "4", "BT_SCAN_PATIENCE": "1"},
-        {"BT_SCAN_LANES": "6", "BT_SCAN_PATIENCE": "1"},
         {"BT_SCAN_LANES": "6", "BT_SCAN_PATIENCE": "2"},
-        {"BT_SCAN_LANES": "8", "BT_SCAN_PATIENCE": "2"},
+        {"BT_SCAN_LANES": "8", "BT_SCAN_PATIENCE": "3"},
+        {"BT_SCAN_LANES": "8", "BT_SCAN_PATIENCE": "4"},
         {"BT_SCAN_LANES": "12", "BT_SCAN_PATIENCE": "4"},
-        {"BT_SCAN_LANES": "16", "BT_SCAN_PATIENCE": "4"},
-        {"BT_SCAN_LANES": "6", "BT_SCAN_PATIENCE": "1", "BT_STEPS_PER_TURN": "1"},
-        {"BT_SCAN_LANES": "6", "BT_SCAN_PATIENCE": "2", "BT_STEPS_PER_TURN": "3"},
-        {"BT_SCAN_LANES": "6", "BT_SCAN_PATIENCE": "1", "BT_COMPACT_LANES": "8", "BT_COMPACT_PATIENCE": "8"},
-        {"BT_SCAN_LANES": "6", "BT_SCAN_PATIENCE": "1", "BT_COMPACT_LANES": "16", "BT_COMPACT_PATIENCE": "16"},
+        {"BT_SCAN_LANES": "16", "BT_SCAN_PATIENCE": "6"},
+        {"BT_SCAN_LANES": "8", "BT_SCAN_PATIENCE": "3", "BT_STEPS_PER_TURN": "3"},
+        {"BT_SCAN_LANES": "8", "BT_SCAN_PATIENCE": "2", "BT_STEPS_PER_TURN": "4"},
     ]
     if "--old" in sys.argv:
         configs = [
