@@ -268,8 +268,8 @@ BT_DEV void render_body(const RenderParams& p) {
     V3 aov_albedo, aov_normal;
     float aov_depth = inf;
 
-#pragma unroll 1
     uint32_t regen_waited = 0;
+#pragma unroll 1
     for (;;) {
         // Regeneration phase (ray generation is ~400 instructions): run it for all idle lanes at once,
         // and only when enough of them are idle -- in a warp that marches through a volume or flies
