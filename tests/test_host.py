@@ -273,3 +273,24 @@ def test_cli_builtin_scene_and_flags(tmp_path):
                         "--scene", O.scene_path("scene"), "--save-scene", str(out)], capture_output=True, text=True)
     assert r.returncode == 0 and "loaded scene" in r.stderr
     assert json.load(open(out))["objects"]["collection"]["0"]["inner"]["Camera"]["aspect_ratio"] == 1.5   # w / h
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference algorithm on the host cores): one JSON line with the
+    contract's keys; under torchrun only rank 0 prints, the other ranks exit 0 without work."""
+    import subprocess
+    import sys
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--workload", "C1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, check=True, env={**os.environ, "RANK": "0"}).stdout
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == d["unit"] == "Msamples/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "C1" in d["config"]["workload"]
+    other = subprocess.run(cmd, capture_output=True, text=True, check=True, env={**os.environ, "RANK": "1"})
+    assert other.stdout.strip() == ""
