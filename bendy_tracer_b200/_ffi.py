@@ -50,6 +50,7 @@ SIGNATURES = {
     "bt_engine_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "bt_engine_destroy": (None, [_P]),
     "bt_engine_launch_count": (C.c_uint64, [_P]),
+    "bt_engine_set_tuning": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "bt_scene_create_json": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(_P)]),
     "bt_scene_to_json": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "bt_free": (None, [_P]),
@@ -72,6 +73,8 @@ SIGNATURES = {
                                   C.POINTER(C.c_int32), _P]),
     "bt_render_stats": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(BtConfig), C.POINTER(BtRenderConfig), C.c_uint64,
                                   C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "bt_render_pool_stats": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(BtConfig), C.POINTER(BtRenderConfig), C.c_uint64,
+                                       C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
     "bt_resolve_u8": (C.c_int, [_P, _P, C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, _P]),
     "bt_trace_segments": (C.c_int, [_P, _P, C.POINTER(BtConfig), C.c_uint32, _P, _P, C.POINTER(BtSegment)]),
     "bt_camera_rays": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(BtConfig), C.POINTER(BtRenderConfig), C.c_uint64,

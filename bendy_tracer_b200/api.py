@@ -157,6 +157,11 @@ class Engine:
     def launch_count(self):
         return int(lib.bt_engine_launch_count(self.handle))
 
+    def set_tuning(self, **knobs):
+        """scheduling knobs of the kernels (bt_engine_set_tuning): never change an image; None restores the default"""
+        for name, value in knobs.items():
+            check(lib.bt_engine_set_tuning(self.handle, name.encode(), -1 if value is None else int(value)))
+
     def fp32_peak_tflops(self, iters=4096):
         t = C.c_double()
         check(lib.bt_fp32_peak(self.handle, iters, C.byref(t)))
@@ -434,6 +439,22 @@ class Tracer:
         check(lib.bt_render_stats(engine.handle, scene.handle, camera, C.byref(cfg), C.byref(rc), self.seed, sample_base,
                                   width, height, out))
         return dict(paths=out[0], scans=out[1], rk4_steps=out[2], events=out[3])
+
+    def render_pool_stats(self, scene: Scene, camera: int, config: RenderConfig, width, height, sample_base=0):
+        """scheduling counters of the pooled kernel for the render call with these arguments (bt_render_pool_stats)"""
+        engine = self.engine or Engine.default(0)
+        cfg, rc = self.config._c(), config._c()
+        out = (C.c_uint64 * 12)()
+        check(lib.bt_render_pool_stats(engine.handle, scene.handle, camera, C.byref(cfg), C.byref(rc), self.seed, sample_base,
+                                       width, height, out))
+        keys = ("step_iterations", "step_lanes", "refill_rounds", "step_entries", "scan_passes", "scan_slots", "shade_passes",
+                "shade_slots", "regen_passes", "paths_issued", "paths_retired", "turns")
+        d = dict(zip(keys, [int(v) for v in out]))
+        d["lanes_per_step"] = d["step_lanes"] / max(d["step_iterations"], 1)
+        d["lanes_per_scan"] = d["scan_slots"] / max(d["scan_passes"], 1)
+        d["lanes_per_shade"] = d["shade_slots"] / max(d["shade_passes"], 1)
+        d["lanes_per_regen"] = d["paths_issued"] / max(d["regen_passes"], 1)
+        return d
 
     def trace_segments(self, scene: Scene, origins, dirs):
         """ChunkState::try_hit (mod.rs:389-402) / the geodesic segment for each ray; dict of numpy arrays"""

@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <filesystem>
 #include <fstream>
 #include <sstream>
 #include <string>
@@ -244,9 +245,10 @@ int main(int argc, char** argv) {
     ck(bt_resolve_u8(engine, buffer.data(), BT_MEM_HOST, width, height, have, cs, rgba.data()), "resolve");
     if (screenshot.find('.') == std::string::npos) screenshot += "/render.png";  // DEFAULT_SCREENSHOT, main.rs:21,277-281
     size_t slash = screenshot.find_last_of('/');
-    if (slash != std::string::npos) {
-        std::string cmd = "mkdir -p '" + screenshot.substr(0, slash) + "'";
-        if (std::system(cmd.c_str()) != 0) die("cannot create " + screenshot.substr(0, slash));
+    if (slash != std::string::npos && slash > 0) {  // fs::create_dir_all(parent), main.rs:283-285
+        std::error_code ec;
+        std::filesystem::create_directories(screenshot.substr(0, slash), ec);
+        if (ec) die("cannot create " + screenshot.substr(0, slash) + ": " + ec.message());
     }
     if (!write_png(screenshot, rgba, width, height)) die("cannot write " + screenshot);
     std::fprintf(stderr, "saved screenshot to %s\n", screenshot.c_str());

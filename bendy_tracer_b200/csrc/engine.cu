@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -34,8 +35,30 @@ int cuda_fail(cudaError_t e, const char* what) {
     } while (0)
 }  // namespace
 
+// Scheduling knobs of the kernels: none of them changes an image.  Read from the environment ONCE, when the
+// engine is created (BT_<NAME>), and settable per engine with bt_engine_set_tuning; -1 = the built-in default.
+struct Tuning {
+    int64_t compact_lanes = -1, compact_patience = -1, regen_lanes = -1, regen_patience = -1, scan_lanes = -1, scan_patience = -1;
+    int64_t steps_per_turn = -1, lens_no_skip = -1, host_bands = -1, wide_ctas = -1;
+    int64_t pool_w = -1, pool_refill = -1, pool_step_min = -1, pool_threads = -1;
+};
+struct TuningName {
+    const char* name;
+    int64_t Tuning::*field;
+};
+static const TuningName kTuning[] = {
+    {"compact_lanes", &Tuning::compact_lanes}, {"compact_patience", &Tuning::compact_patience},
+    {"regen_lanes", &Tuning::regen_lanes},     {"regen_patience", &Tuning::regen_patience},
+    {"scan_lanes", &Tuning::scan_lanes},       {"scan_patience", &Tuning::scan_patience},
+    {"steps_per_turn", &Tuning::steps_per_turn}, {"lens_no_skip", &Tuning::lens_no_skip},
+    {"host_bands", &Tuning::host_bands},       {"wide_ctas", &Tuning::wide_ctas},
+    {"pool_w", &Tuning::pool_w},               {"pool_refill", &Tuning::pool_refill},
+    {"pool_step_min", &Tuning::pool_step_min}, {"pool_threads", &Tuning::pool_threads},
+};
+
 struct bt_engine {
     int device;
+    Tuning tune;
     cudaStream_t stream;
     cudaStream_t stream2;   // second lane of the host-buffer pipeline (bt_render, BT_MEM_HOST)
     cudaEvent_t ev_fork, ev_join;
@@ -138,8 +161,11 @@ Merged merge(const bt_config& c, const bt_render_config& r) {
 
 uint32_t clamp_u32(uint64_t v) { return v > 0xfffffffeULL ? 0xfffffffeu : (uint32_t)v; }
 
-int build_params(bt_scene* s, uint64_t camera_ref, bool need_camera, const bt_config* config, const bt_render_config* rc,
-                 uint64_t seed, uint64_t sample_base, uint32_t width, uint32_t height, RenderParams* out) {
+uint32_t knob(int64_t v, uint32_t dflt) { return v < 0 ? dflt : (uint32_t)v; }
+
+int build_params(const bt_engine* en, bt_scene* s, uint64_t camera_ref, bool need_camera, const bt_config* config,
+                 const bt_render_config* rc, uint64_t seed, uint64_t sample_base, uint32_t width, uint32_t height, RenderParams* out) {
+    const Tuning& tn = en->tune;
     Merged m = merge(*config, *rc);
     RenderParams p;
     std::memset(&p, 0, sizeof p);
@@ -173,24 +199,23 @@ int build_params(bt_scene* s, uint64_t camera_ref, bool need_camera, const bt_co
     // shipped scenes (profiles/r1_sweep_*.log).  Long flights through a surface-only scene end a path
     // every ~50 turns per lane: small batches keep lanes flying; a marching volume wants larger ones.
     const bool long_flights = p.scene.n_lens != 0 && !p.scene.has_volume_prims;
-    p.compact_lanes = long_flights ? 12 : 16;
-    p.compact_patience = long_flights ? 8 : 16;
-    if (const char* e = std::getenv("BT_COMPACT_LANES")) p.compact_lanes = (uint32_t)std::atoi(e);
-    if (const char* e = std::getenv("BT_COMPACT_PATIENCE")) p.compact_patience = (uint32_t)std::atoi(e);
+    p.compact_lanes = knob(tn.compact_lanes, long_flights ? 12 : 16);
+    p.compact_patience = knob(tn.compact_patience, long_flights ? 8 : 16);
     // A scan over a handful of surface primitives costs less than half a ray generation: such a warp
     // is better off collecting more idle lanes first (scene.json.gz: +4.6 %, profiles/r1_sweep_regen2.log).
     const bool cheap_scans = p.scene.n_lens == 0 && !p.scene.has_volume_prims && p.scene.n_bvh == 0 && p.scene.n_prims <= 8;
-    p.regen_lanes = long_flights ? 4 : (cheap_scans ? 24 : 12);
-    p.regen_patience = long_flights ? 8 : (cheap_scans ? 32 : 16);
-    if (const char* e = std::getenv("BT_REGEN_LANES")) p.regen_lanes = (uint32_t)std::atoi(e);
-    if (const char* e = std::getenv("BT_REGEN_PATIENCE")) p.regen_patience = (uint32_t)std::atoi(e);
-    p.scan_lanes = 8;      // (profiles/r1_sweep_nearest_sphere_bound.log: flat within 1 % from 6/2 to 8/4)
-    p.scan_patience = 3;
-    if (const char* e = std::getenv("BT_SCAN_LANES")) p.scan_lanes = (uint32_t)std::atoi(e);
-    if (const char* e = std::getenv("BT_SCAN_PATIENCE")) p.scan_patience = (uint32_t)std::atoi(e);
-    if (std::getenv("BT_LENS_NO_SKIP")) p.scene.lens_skip = 0;
-    p.steps_per_turn = long_flights ? 3 : 2;
-    if (const char* e = std::getenv("BT_STEPS_PER_TURN")) p.steps_per_turn = (uint32_t)std::max(1, std::atoi(e));
+    p.regen_lanes = knob(tn.regen_lanes, long_flights ? 4 : (cheap_scans ? 24 : 12));
+    p.regen_patience = knob(tn.regen_patience, long_flights ? 8 : (cheap_scans ? 32 : 16));
+    p.scan_lanes = knob(tn.scan_lanes, 8);      // (profiles/r1_sweep_nearest_sphere_bound.log: flat within 1 % from 6/2 to 8/4)
+    p.scan_patience = knob(tn.scan_patience, 3);
+    if (tn.lens_no_skip > 0) p.scene.lens_skip = 0;
+    p.steps_per_turn = std::max(1u, knob(tn.steps_per_turn, long_flights ? 3 : 2));
+    p.wide_ctas = knob(tn.wide_ctas, 0);
+    // the pooled kernel (render_pool.cuh): 32 W path slots per warp; 0 = one path per lane (render_body)
+    p.pool_w = std::min(knob(tn.pool_w, 0), 8u);
+    p.pool_refill = std::max(1u, knob(tn.pool_refill, 6));
+    p.pool_step_min = knob(tn.pool_step_min, 24);
+    p.pool_threads = knob(tn.pool_threads, 0) & ~31u;  // 0: the kernel's own CTA size (launch_pool)
     p.tau_scale = uniform_scale_inclusive(0.0f, 6.28318530717958647692f);
     p.one_scale = uniform_scale_inclusive(0.0f, 1.0f);
     *out = p;
@@ -233,6 +258,11 @@ int bt_engine_create(int device, bt_engine** out) {
     if (prop.major < 10) return fail(BT_ERR_CUDA, std::string("device is not sm_100 class: ") + prop.name);
     bt_engine* en = new bt_engine();
     en->device = device;
+    for (const TuningName& t : kTuning) {  // BT_COMPACT_LANES, BT_POOL_W, ...: read once, here
+        std::string env = "BT_";
+        for (const char* c = t.name; *c; ++c) env += (char)std::toupper((unsigned char)*c);
+        if (const char* v = std::getenv(env.c_str())) en->tune.*(t.field) = std::atoll(v);
+    }
     en->launches = 0;
     en->d_scratch = 0;
     en->scratch_bytes = 0;
@@ -266,6 +296,16 @@ void bt_engine_destroy(bt_engine* engine) {
 }
 
 uint64_t bt_engine_launch_count(const bt_engine* engine) { return engine ? engine->launches : 0; }
+
+int bt_engine_set_tuning(bt_engine* engine, const char* name, int64_t value) {
+    if (!engine || !name) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    for (const TuningName& t : kTuning)
+        if (!std::strcmp(t.name, name)) {
+            engine->tune.*(t.field) = value;
+            return BT_OK;
+        }
+    return fail(BT_ERR_INVALID_ARG, std::string("unknown tuning knob `") + name + "`");
+}
 
 int bt_scene_create_json(bt_engine* engine, const void* bytes, size_t n, bt_scene** out) {
     if (!bytes || !out) return fail(BT_ERR_INVALID_ARG, "NULL argument");
@@ -443,7 +483,7 @@ int render_rows(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const b
     if (rcode != BT_OK) return rcode;
     if ((rcode = check_renderable(scene)) != BT_OK) return rcode;
     RenderParams p;
-    if ((rcode = build_params(scene, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return rcode;
+    if ((rcode = build_params(engine, scene, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return rcode;
     p.fb = (float4*)fb;
     p.row0 = row0;
     p.row_end = row_end;
@@ -499,7 +539,7 @@ int bt_render_stats(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, con
     if (rcode != BT_OK) return rcode;
     if ((rcode = check_renderable(scene)) != BT_OK) return rcode;
     RenderParams p;
-    if ((rcode = build_params(scene, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return rcode;
+    if ((rcode = build_params(engine, scene, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return rcode;
     size_t fb_bytes = (size_t)width * height * 16;
     if ((rcode = ensure_scratch(engine, fb_bytes + 64)) != BT_OK) return rcode;
     CK(cudaMemsetAsync(engine->d_scratch, 0, fb_bytes + 64, engine->stream));
@@ -510,6 +550,39 @@ int bt_render_stats(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, con
     CK(cudaMemcpyAsync(host, p.stats, sizeof host, cudaMemcpyDeviceToHost, engine->stream));
     CK(cudaStreamSynchronize(engine->stream));
     for (int i = 0; i < 4; ++i) stats_out[i] = host[i];
+    return BT_OK;
+    GUARD_END
+}
+
+int bt_render_pool_stats(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_config* config,
+                         const bt_render_config* rc, uint64_t seed, uint64_t sample_base, uint32_t width, uint32_t height,
+                         uint64_t stats_out[12]) {
+    if (!engine || !scene || !config || !rc || !stats_out) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    GUARD_BEGIN
+    if (!scene->engine) scene->engine = engine;
+    if (scene->engine != engine) return fail(BT_ERR_INVALID_ARG, "scene belongs to another engine");
+    for (int i = 0; i < 12; ++i) stats_out[i] = 0;
+    if (rc->samples == 0) return BT_OK;
+    CK(cudaSetDevice(engine->device));
+    int rcode = refresh_scene(scene, engine->stream);
+    if (rcode != BT_OK) return rcode;
+    if ((rcode = check_renderable(scene)) != BT_OK) return rcode;
+    RenderParams p;
+    if ((rcode = build_params(engine, scene, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return rcode;
+    if (p.pool_w == 0) return fail(BT_ERR_UNSUPPORTED, "the pooled kernel is switched off (tuning knob pool_w = 0)");
+    size_t fb_bytes = (size_t)width * height * 16;
+    if ((rcode = ensure_scratch(engine, fb_bytes + 128)) != BT_OK) return rcode;
+    CK(cudaMemsetAsync(engine->d_scratch, 0, fb_bytes + 128, engine->stream));
+    p.fb = (float4*)engine->d_scratch;
+    p.stats = (unsigned long long*)((char*)engine->d_scratch + fb_bytes);
+    p.pool_stats = 1;
+    cudaError_t ce = use_exact(engine, scene) ? launch_render_exact(p, engine->stream, &engine->launches) : launch_render_fast(p, engine->stream, &engine->launches);
+    if (ce == cudaErrorNotSupported) return fail(BT_ERR_UNSUPPORTED, "scheduling counters exist for the content-specialised pooled kernels only");
+    CK(ce);
+    unsigned long long host[12];
+    CK(cudaMemcpyAsync(host, p.stats, sizeof host, cudaMemcpyDeviceToHost, engine->stream));
+    CK(cudaStreamSynchronize(engine->stream));
+    for (int i = 0; i < 12; ++i) stats_out[i] = host[i];
     return BT_OK;
     GUARD_END
 }
@@ -543,7 +616,7 @@ int bt_render(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_
     const size_t row_bytes = (size_t)width * 4 * sizeof(float), bytes = row_bytes * height;
     if ((r = ensure_scratch(engine, bytes)) != BT_OK) return r;
     uint32_t bands = (uint32_t)std::min<size_t>(8, std::max<size_t>(1, bytes / (8u << 20)));
-    if (const char* e = std::getenv("BT_HOST_BANDS")) bands = (uint32_t)std::max(1, std::atoi(e));
+    if (engine->tune.host_bands > 0) bands = (uint32_t)engine->tune.host_bands;
     uint32_t band_rows = ((height + bands - 1) / bands + 15u) & ~15u;  // whole 16-row CTAs
     // the scene's device copy is refreshed on the first stream; the second one waits for it
     if ((r = refresh_scene(scene, engine->stream)) != BT_OK) return r;
@@ -614,7 +687,7 @@ int bt_trace_segments(bt_engine* engine, bt_scene* scene, const bt_config* confi
     bt_render_config_default(&rc);
     rc.samples = 1;
     RenderParams p;
-    if ((r = build_params(scene, 0, false, config, &rc, 0, 0, 1, 1, &p)) != BT_OK) return r;
+    if ((r = build_params(engine, scene, 0, false, config, &rc, 0, 0, 1, 1, &p)) != BT_OK) return r;
     size_t in_bytes = (size_t)n * 3 * sizeof(float), out_bytes = (size_t)n * sizeof(DeviceSegment);
     size_t off_d = (in_bytes + 255) & ~(size_t)255, off_o = 2 * off_d;
     if ((r = ensure_scratch(engine, off_o + out_bytes + 256)) != BT_OK) return r;
@@ -651,7 +724,7 @@ int bt_camera_rays(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, cons
     int r = refresh_scene(scene, engine->stream);
     if (r != BT_OK) return r;
     RenderParams p;
-    if ((r = build_params(scene, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return r;
+    if ((r = build_params(engine, scene, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return r;
     size_t b32 = ((size_t)n * 4 + 255) & ~(size_t)255, b64 = ((size_t)n * 8 + 255) & ~(size_t)255, bo = (size_t)n * 24;
     if ((r = ensure_scratch(engine, 2 * b32 + b64 + bo + 256)) != BT_OK) return r;
     char* base = (char*)engine->d_scratch;

@@ -9,6 +9,7 @@
 #include "device.cuh"
 #include "kernels.h"
 
+#include <algorithm>
 #include <cstdlib>
 
 #ifdef BT_EXACT_SCAN
@@ -228,6 +229,247 @@ enum { EV_TERMINAL = 0, EV_DIFFUSE = 1, EV_SPECULAR = 2 /* metallic, glass */, E
 // how its new direction is sampled: every variant consumes the same two u32 draws (r1, r2)
 enum { SK_NONE = 0, SK_COSINE = 1, SK_HEMI = 2, SK_SPHERE = 3, SK_RECT = 4 };
 
+// The state a path carries from event to event (the recursion of ChunkState::sample, mod.rs:322-342, unrolled):
+// its RNG stream, the throughput T, the bounce / volume-bounce counters, the volume being marched and the
+// first-hit AOV latches (mod.rs:306-315).
+struct PathQ {
+    Rng rng;
+    V3 T;
+    uint32_t bounce, vb;
+    int vol_obj;
+    bool latched;
+    V3 aov_albedo, aov_normal;
+    float aov_depth;
+};
+BT_DEV void path_reset(PathQ& q) {
+    q.T = v3(1.0f, 1.0f, 1.0f);
+    q.bounce = 0;
+    q.vb = 0;
+    q.vol_obj = -1;
+    q.latched = false;
+    q.aov_albedo = v3(0.0f, 0.0f, 0.0f);
+    q.aov_normal = v3(0.0f, 0.0f, 0.0f);
+    q.aov_depth = __int_as_float(0x7f800000);
+}
+
+// One event of a path: classify the traced segment (sample_root / sample_surface / sample_volume), draw the
+// new direction with the shared sampler and update the path state.  Returns true when the path ends --
+// `contrib` is then what Chunk::write_* adds to the pixel for this path (buffer.rs:222-260); otherwise
+// (o, d) is the scattered ray.  Called by every lane that holds an event; the three stages below are
+// laid out so that the lanes of a warp meet again at the sampler and at the scattered-ray code.
+template <int C>
+BT_DEV bool shade_event(const RenderParams& p, const SceneView& sc, const Consts& k, const Traced& tr, PathQ& q, V3& o, V3& d,
+                        V3& contrib) {
+    const float inf = __int_as_float(0x7f800000);
+    Rng& rng = q.rng;
+    int ev = EV_TERMINAL, sk = SK_NONE;
+    bool finish = false;
+    V3 fin_color = v3(0.0f, 0.0f, 0.0f), fin_albedo = v3(0.0f, 0.0f, 0.0f), fin_normal = v3(0.0f, 0.0f, 0.0f);
+    float fin_depth = inf;
+    V3 pos = tr.o, nrm = tr.d, A = q.T, dir0 = tr.d;  // event geometry (defaults are placeholders)
+    const V3 din = tr.d;
+    float rough = 0.0f;
+    const float hit_t = tr.t_total;
+    int face = 0, hit_obj = -1;
+    const float4* light = sc.lights;   // the light object picked by a Diffuse event (its pdf)
+    const float4* lsamp = sc.lights;   // the record its point is sampled from (a cuboid's face)
+    bool vol_scatter = false;
+    const bool in_volume = (C & CT_VOLUMES) && q.vol_obj >= 0;
+
+    // ---- 1. classify the event ----------------------------------------------------------------
+    if (tr.h.prim < 0) {
+        finish = true;
+        if (!tr.captured) {  // sample_root, mod.rs:429-452
+            fin_color = v3(p.scene.root_color[0], p.scene.root_color[1], p.scene.root_color[2]);
+            fin_albedo = v3(p.scene.root_albedo[0], p.scene.root_albedo[1], p.scene.root_albedo[2]);
+            if (p.scene.root_keeps_normal) {
+                fin_normal = -tr.d;
+                fin_depth = p.clip_max;
+            }
+        }
+    } else {
+        const Surface s = resolve_hit<C>(sc.prims, tr.h, tr.o, tr.d);
+        pos = s.position;
+        nrm = s.normal;
+        face = s.face;
+        hit_obj = s.obj;
+        if (!(C & CT_VOLUMES) || s.face <= 1) {
+            // ---- sample_surface, mod.rs:454-486 + Material::shade, material.rs:81-199 ----
+            const float4 m0 = sc.mats[s.mat * MAT_STRIDE], m1 = sc.mats[s.mat * MAT_STRIDE + 1];
+            const int mk = __float_as_int(m0.w);
+            A = v3(m0);
+            if (mk == MAT_FLAT) {
+                finish = true;  // ColorData::from_emitted(albedo)
+                fin_color = A;
+                fin_albedo = A;
+            } else if (mk == MAT_EMISSIVE) {
+                finish = true;
+                fin_color = A * m1.z;
+                fin_albedo = fin_color;
+            } else if (mk == MAT_DIFFUSE) {
+                ev = EV_DIFFUSE;
+                light = sc.lights + uniform_index(rng, p.scene.n_lights, p.light_zone) * LIGHT_STRIDE;
+                lsamp = light;
+                if (gen_bool(rng, 0.5f)) {  // Pdf::Mix: true selects the light (material.rs:269-275)
+                    if ((C & CT_CUBOID_LIGHT) && (C & CT_RECTS) && __float_as_int(light[0].x) == LIGHT_CUBOID) {
+                        // Cuboid::random_point, cuboid.rs:48-54: WeightedIndex (one Uniform::new(0, total)
+                        // draw, partition_point(w <= chosen)), then that face's Rect::random_point
+                        const float4 c1 = light[1], c2 = light[2];
+                        const float chosen = uniform_f32(rng, 0.0f, c2.y);
+                        const int idx = (c1.x <= chosen) + (c1.y <= chosen) + (c1.z <= chosen) + (c1.w <= chosen) + (c2.x <= chosen);
+                        lsamp = sc.lights + (__float_as_int(c2.z) + idx) * LIGHT_STRIDE;
+                    }
+                    const int lt = __float_as_int(lsamp[0].x);
+                    sk = ((C & CT_SPHERES) && lt == LIGHT_SPHERE) ? SK_SPHERE : (((C & CT_RECTS) && lt == LIGHT_RECT) ? SK_RECT : SK_NONE);
+                } else {
+                    sk = SK_COSINE;
+                }
+            } else if (C & (CT_METAL | CT_GLASS)) {
+                ev = EV_SPECULAR;
+                sk = SK_HEMI;
+                rough = m1.x;
+                if (!(C & CT_GLASS) || ((C & CT_METAL) && mk == MAT_METALLIC)) {
+                    dir0 = reflect(din, nrm);
+                } else {  // MAT_GLASS, material.rs:231-261
+                    float ior = m1.y;
+                    if (s.face == 0) ior = m_rcp(ior);
+                    const float cos_theta = fminf(dot(-din, nrm), 1.0f);
+                    const float sin_theta = m_sqrt(1.0f - cos_theta * cos_theta);
+                    const float fr = fresnel(din, nrm, ior);
+                    if (ior * sin_theta > 1.0f || gen_bool(rng, fr))
+                        dir0 = reflect(din, nrm);
+                    else
+                        dir0 = refract(din, nrm, ior);
+                }
+            }
+        } else {
+            // ---- sample_volume, mod.rs:488-523 + Volume::shade, volume.rs:26-60 ----
+            ev = EV_VOLUME;
+            if (!in_volume) q.vb = 0;  // entered from sample(): volume_bounce = 0
+            const V3 bmin = v3(s.center.x - s.radius, s.center.y - s.radius, s.center.z - s.radius);
+            const V3 bmax = v3(s.center.x + s.radius, s.center.y + s.radius, s.center.z + s.radius);
+            const V3 coord = m_div(s.position - bmin, bmax - bmin);
+            const float density = p.volume_step * density_trilinear(sc.vols + s.vol * VOL_STRIDE, sc.grids, coord);
+            if (density >= 1.0f || gen_bool(rng, density)) {
+                vol_scatter = true;
+                sk = SK_SPHERE;
+                if (s.face == 2) pos = pos - din * p.volume_step * standard_f32(rng);
+            }
+        }
+    }
+
+    // ---- 2. the shared direction sampler: two u32 draws, one sincos, one basis --------------
+    // UnitSphere / UnitHemisphere / Cosine (math/distr.rs:7-103) and Rect::random_point
+    // (rect.rs:82-86) all draw (r1, r2) in this order; only the combination differs.
+    V3 vec = v3(0.0f, 0.0f, 0.0f);
+    if (sk != SK_NONE) {
+        const float4 l1 = lsamp[1], l2 = lsamp[2];
+        const bool rect = (C & CT_RECTS) && sk == SK_RECT;
+        const float r1 = uniform_f32(rng, rect ? l1.w : 0.0f, rect ? lsamp[3].w : k.tau_scale);
+        const float r2 = uniform_f32(rng, rect ? l2.w : 0.0f, rect ? lsamp[4].w : k.one_scale);
+        float cx = r1, sy = r2, z = 0.0f;
+        V3 X = v3(l1), Y = v3(l2), Z = v3(0.0f, 0.0f, 0.0f);
+        if (!rect) {
+            float sn, cs;
+            bt_sincos(r1, &sn, &cs);
+            const float w = m_sqrt(sk == SK_COSINE ? r2 : r2 * (1.0f - r2));
+            const float two = sk == SK_COSINE ? 1.0f : 2.0f;
+            cx = cs * two * w;
+            sy = sn * two * w;
+            z = sk == SK_COSINE ? m_sqrt(1.0f - r2) : (((C & (CT_METAL | CT_GLASS)) && sk == SK_HEMI) ? 1.0f - r2 : 1.0f - 2.0f * r2);
+            X = v3(1.0f, 0.0f, 0.0f);
+            Y = v3(0.0f, 1.0f, 0.0f);
+            Z = v3(0.0f, 0.0f, 1.0f);
+            if (sk != SK_SPHERE) {
+                Z = normalize_s(nrm);
+                any_orthonormal_pair(Z, X, Y);
+            }
+        }
+        vec = (X * cx + Y * sy) + Z * z;
+    }
+
+    // ---- 3. the scattered ray ------------------------------------------------------------
+    if (ev != EV_TERMINAL) {
+        V3 dirvec = vec;  // Cosine, volume scatter
+        if (ev == EV_DIFFUSE && sk != SK_COSINE) {  // Pdf::Light: random_point(light) - origin
+            V3 point = v3(lsamp[1]);                                        // POINT: the translation
+            if (sk == SK_SPHERE) point = v3(lsamp[1]) + vec * lsamp[1].w;   // sphere.rs:40-42
+            if (sk == SK_RECT) point = mat_vec(v3(lsamp[3]), v3(lsamp[4]), v3(lsamp[5]), vec) + v3(lsamp[6]);
+            dirvec = point - pos;
+        }
+        if ((C & (CT_METAL | CT_GLASS)) && ev == EV_SPECULAR) dirvec = dir0 + vec * rough;
+        if (ev == EV_VOLUME && !vol_scatter) dirvec = din;
+        const V3 nd = normalize_a(dirvec);  // Ray::new
+
+        if ((C & CT_VOLUMES) && ev == EV_VOLUME) {
+            o = pos;
+            d = nd;
+            if (vol_scatter) {
+                if ((C & CT_AOV) && !q.latched) {
+                    q.latched = true;
+                    q.aov_albedo = v3(0.8f, 0.8f, 0.8f);
+                    q.aov_normal = nrm;
+                    q.aov_depth = hit_t;
+                }
+                q.T = q.T * 0.8f;
+            }
+            if (face == 4) {  // VolumeBack: leave the medium through sample(ray, bounce + 1)
+                q.vol_obj = -1;
+                ++q.bounce;
+                if (q.bounce > p.max_bounces) finish = true;
+            } else {          // keep marching: sample_volumetric(.., volume_bounce + 1)
+                q.vol_obj = hit_obj;
+                ++q.vb;
+                if (q.vb > p.max_volume_bounces) finish = true;
+            }
+        } else {
+            float pdf = 1.0f, mpdf = 1.0f;
+            if (ev == EV_DIFFUSE) {
+                mpdf = dot(nrm, nd) * 0.318309886183790671538f;
+                const float pb = light_pdf<C>(sc.prims, sc.lights, light, pos, nd, p.clip_min, p.clip_max);
+                pdf = lerpf(mpdf, pb, 0.5f);
+            }
+            if (fabsf(pdf) <= 1e-5f) {
+                finish = true;  // no scatter: from_emitted(BLACK)
+            } else {
+                if ((C & CT_AOV) && !q.latched) {
+                    q.latched = true;
+                    q.aov_albedo = A;
+                    q.aov_normal = nrm;
+                    q.aov_depth = hit_t;
+                }
+                q.T = q.T * ((A * mpdf) * m_rcp(pdf));
+                o = pos;
+                d = nd;
+                q.vol_obj = -1;
+                ++q.bounce;
+                if (q.bounce > p.max_bounces) finish = true;  // sample(): black, AOVs already latched
+            }
+        }
+    }
+
+    if (finish) {
+        if ((C & CT_AOV) && !q.latched) {
+            q.aov_albedo = fin_albedo;
+            q.aov_normal = fin_normal;
+            q.aov_depth = fin_depth;
+        }
+        switch ((C & CT_AOV) ? p.output : 0) {  // mod.rs:306-315
+            case 0:  // (rounded separately from the pixel sum in every flavour: the product may travel through shared memory)
+                contrib = v3(__fmul_rn(q.T.x, fin_color.x), __fmul_rn(q.T.y, fin_color.y), __fmul_rn(q.T.z, fin_color.z));
+                break;
+            case 1: contrib = q.aov_albedo; break;
+            case 2: contrib = q.aov_normal; break;
+            default: {
+                float dn = (q.aov_depth - p.clip_min) * m_rcp(p.clip_max - p.clip_min);
+                dn = fminf(fmaxf(dn, 0.0f), 1.0f);
+                contrib = v3(dn, dn, dn);
+            }
+        }
+    }
+    return finish;
+}
+
 template <bool STATS, bool LENS, bool EXACT, int NL, bool BVH, int C>
 BT_DEV void render_body(const RenderParams& p) {
     extern __shared__ float4 smem[];
@@ -254,19 +496,15 @@ BT_DEV void render_body(const RenderParams& p) {
     uint32_t st_scans = 0, st_steps = 0, st_events = 0;  // STATS only
 
     // per-path state
-    Rng rng;
-    V3 o, d, T;
-    uint32_t bounce = 0, vb = 0;
-    int vol_obj = -1;
+    PathQ q;
+    path_reset(q);
+    V3 o, d;
     Flight fl;  // LENS: the geodesic this lane is flying (x, v alias o, d)
     flight_reset(fl);
     int fstate = FL_FLY;
     BvhTrav btrav;  // BVH && !LENS: the traversal this lane is in
     bvh_begin(btrav, 0.0f);
     int bstate = 0;  // 0 none, 1 traversing, 2 done
-    bool latched = false;
-    V3 aov_albedo, aov_normal;
-    float aov_depth = inf;
 
     uint32_t regen_waited = 0;
 #pragma unroll 1
@@ -281,22 +519,15 @@ BT_DEV void render_body(const RenderParams& p) {
         if (regen) regen_waited = 0;
         if (regen && !alive && !done) {
             if (path < p.paths_per_pixel) {
-                rng.seed_from_u64(splitmix_mix(pixel_key + 0xd1342543de82ef95ULL * (p.path_base + path + 1)));
-                camera_ray(p.cam, k, rng, px, py, sub_i, sub_j, o, d);
+                q.rng.seed_from_u64(splitmix_mix(pixel_key + 0xd1342543de82ef95ULL * (p.path_base + path + 1)));
+                camera_ray(p.cam, k, q.rng, px, py, sub_i, sub_j, o, d);
                 if (++sub_i == p.cam.sub_n) {  // the next path's sub-pixel, counted instead of divided out
                     sub_i = 0;
                     if (++sub_j == p.cam.sub_n) sub_j = 0;
                 }
-                T = v3(1.0f, 1.0f, 1.0f);
-                bounce = 0;
-                vb = 0;
-                vol_obj = -1;
+                path_reset(q);
                 flight_reset(fl);
                 fstate = FL_FLY;
-                latched = false;
-                aov_albedo = v3(0.0f, 0.0f, 0.0f);
-                aov_normal = v3(0.0f, 0.0f, 0.0f);
-                aov_depth = inf;
                 alive = true;
                 ++path;
             } else {
@@ -305,18 +536,8 @@ BT_DEV void render_body(const RenderParams& p) {
         }
         if (__all_sync(0xffffffffu, done)) break;
 
-        // ---- 1. trace one segment and classify the event ---------------------------------------
-        int ev = EV_TERMINAL, sk = SK_NONE;
-        bool finish = false;
-        V3 fin_color = v3(0.0f, 0.0f, 0.0f), fin_albedo = v3(0.0f, 0.0f, 0.0f), fin_normal = v3(0.0f, 0.0f, 0.0f);
-        float fin_depth = inf;
-        V3 pos = o, nrm = d, din = d, A = T, dir0 = d;  // event geometry (defaults are placeholders)
-        float rough = 0.0f, hit_t = 0.0f;
-        int face = 0, hit_obj = -1;
-        const float4* light = sc.lights;   // the light object picked by a Diffuse event (its pdf)
-        const float4* lsamp = sc.lights;   // the record its point is sampled from (a cuboid's face)
-        bool vol_scatter = false;
-        const bool in_volume = (C & CT_VOLUMES) && vol_obj >= 0;
+        // ---- 1. trace one segment ---------------------------------------------------------------
+        const bool in_volume = (C & CT_VOLUMES) && q.vol_obj >= 0;
 
         // Per-warp phase compaction: a bent ray is NOT traced to its end here.  Lanes in flight are
         // in one of two phases -- STEP (an RK4 step; chords shorter than the free distance commit at
@@ -356,7 +577,7 @@ BT_DEV void render_body(const RenderParams& p) {
                 bstate = 0;
             }
         } else if (alive && (!LENS || in_volume)) {
-            tr = trace_straight<BVH, C>(p, sc, o, d, in_volume ? 0.0f : p.clip_min, in_volume ? p.volume_step : p.clip_max, vol_obj);
+            tr = trace_straight<BVH, C>(p, sc, o, d, in_volume ? 0.0f : p.clip_min, in_volume ? p.volume_step : p.clip_max, q.vol_obj);
             has_event = true;
         }
         if (LENS) {
@@ -389,205 +610,21 @@ BT_DEV void render_body(const RenderParams& p) {
                 }
             }
         }
+        // ---- 2. classify + shade the event, sample the scattered ray (shade_event) ----------------
         if (alive && has_event) {
-            din = tr.d;
-            hit_t = tr.t_total;
             if (STATS) {
                 st_scans += tr.scans;
                 st_steps += tr.steps;
                 st_events++;
             }
-            if (tr.h.prim < 0) {
-                finish = true;
-                if (!tr.captured) {  // sample_root, mod.rs:429-452
-                    fin_color = v3(p.scene.root_color[0], p.scene.root_color[1], p.scene.root_color[2]);
-                    fin_albedo = v3(p.scene.root_albedo[0], p.scene.root_albedo[1], p.scene.root_albedo[2]);
-                    if (p.scene.root_keeps_normal) {
-                        fin_normal = -tr.d;
-                        fin_depth = p.clip_max;
-                    }
-                }
+            V3 contrib;
+            if (shade_event<C>(p, sc, k, tr, q, o, d, contrib)) {
+                acc = v3(__fadd_rn(acc.x, contrib.x), __fadd_rn(acc.y, contrib.y), __fadd_rn(acc.z, contrib.z));
+                alive = false;
             } else {
-                const Surface s = resolve_hit<C>(sc.prims, tr.h, tr.o, tr.d);
-                pos = s.position;
-                nrm = s.normal;
-                face = s.face;
-                hit_obj = s.obj;
-                if (!(C & CT_VOLUMES) || s.face <= 1) {
-                    // ---- sample_surface, mod.rs:454-486 + Material::shade, material.rs:81-199 ----
-                    const float4 m0 = sc.mats[s.mat * MAT_STRIDE], m1 = sc.mats[s.mat * MAT_STRIDE + 1];
-                    const int mk = __float_as_int(m0.w);
-                    A = v3(m0);
-                    if (mk == MAT_FLAT) {
-                        finish = true;  // ColorData::from_emitted(albedo)
-                        fin_color = A;
-                        fin_albedo = A;
-                    } else if (mk == MAT_EMISSIVE) {
-                        finish = true;
-                        fin_color = A * m1.z;
-                        fin_albedo = fin_color;
-                    } else if (mk == MAT_DIFFUSE) {
-                        ev = EV_DIFFUSE;
-                        light = sc.lights + uniform_index(rng, p.scene.n_lights, p.light_zone) * LIGHT_STRIDE;
-                        lsamp = light;
-                        if (gen_bool(rng, 0.5f)) {  // Pdf::Mix: true selects the light (material.rs:269-275)
-                            if ((C & CT_CUBOID_LIGHT) && (C & CT_RECTS) && __float_as_int(light[0].x) == LIGHT_CUBOID) {
-                                // Cuboid::random_point, cuboid.rs:48-54: WeightedIndex (one Uniform::new(0, total)
-                                // draw, partition_point(w <= chosen)), then that face's Rect::random_point
-                                const float4 c1 = light[1], c2 = light[2];
-                                const float chosen = uniform_f32(rng, 0.0f, c2.y);
-                                const int idx = (c1.x <= chosen) + (c1.y <= chosen) + (c1.z <= chosen) + (c1.w <= chosen) + (c2.x <= chosen);
-                                lsamp = sc.lights + (__float_as_int(c2.z) + idx) * LIGHT_STRIDE;
-                            }
-                            const int lt = __float_as_int(lsamp[0].x);
-                            sk = ((C & CT_SPHERES) && lt == LIGHT_SPHERE) ? SK_SPHERE : (((C & CT_RECTS) && lt == LIGHT_RECT) ? SK_RECT : SK_NONE);
-                        } else {
-                            sk = SK_COSINE;
-                        }
-                    } else if (C & (CT_METAL | CT_GLASS)) {
-                        ev = EV_SPECULAR;
-                        sk = SK_HEMI;
-                        rough = m1.x;
-                        if (!(C & CT_GLASS) || ((C & CT_METAL) && mk == MAT_METALLIC)) {
-                            dir0 = reflect(din, nrm);
-                        } else {  // MAT_GLASS, material.rs:231-261
-                            float ior = m1.y;
-                            if (s.face == 0) ior = m_rcp(ior);
-                            const float cos_theta = fminf(dot(-din, nrm), 1.0f);
-                            const float sin_theta = m_sqrt(1.0f - cos_theta * cos_theta);
-                            const float fr = fresnel(din, nrm, ior);
-                            if (ior * sin_theta > 1.0f || gen_bool(rng, fr))
-                                dir0 = reflect(din, nrm);
-                            else
-                                dir0 = refract(din, nrm, ior);
-                        }
-                    }
-                } else {
-                    // ---- sample_volume, mod.rs:488-523 + Volume::shade, volume.rs:26-60 ----
-                    ev = EV_VOLUME;
-                    if (!in_volume) vb = 0;  // entered from sample(): volume_bounce = 0
-                    const V3 bmin = v3(s.center.x - s.radius, s.center.y - s.radius, s.center.z - s.radius);
-                    const V3 bmax = v3(s.center.x + s.radius, s.center.y + s.radius, s.center.z + s.radius);
-                    const V3 coord = m_div(s.position - bmin, bmax - bmin);
-                    const float density = p.volume_step * density_trilinear(sc.vols + s.vol * VOL_STRIDE, sc.grids, coord);
-                    if (density >= 1.0f || gen_bool(rng, density)) {
-                        vol_scatter = true;
-                        sk = SK_SPHERE;
-                        if (s.face == 2) pos = pos - din * p.volume_step * standard_f32(rng);
-                    }
-                }
+                flight_reset(fl);  // the scattered ray starts a new flight
+                fstate = FL_FLY;
             }
-        }
-
-        // ---- 2. the shared direction sampler: two u32 draws, one sincos, one basis --------------
-        // UnitSphere / UnitHemisphere / Cosine (math/distr.rs:7-103) and Rect::random_point
-        // (rect.rs:82-86) all draw (r1, r2) in this order; only the combination differs.
-        V3 vec = v3(0.0f, 0.0f, 0.0f);
-        if (sk != SK_NONE) {
-            const float4 l1 = lsamp[1], l2 = lsamp[2];
-            const bool rect = (C & CT_RECTS) && sk == SK_RECT;
-            const float r1 = uniform_f32(rng, rect ? l1.w : 0.0f, rect ? lsamp[3].w : k.tau_scale);
-            const float r2 = uniform_f32(rng, rect ? l2.w : 0.0f, rect ? lsamp[4].w : k.one_scale);
-            float cx = r1, sy = r2, z = 0.0f;
-            V3 X = v3(l1), Y = v3(l2), Z = v3(0.0f, 0.0f, 0.0f);
-            if (!rect) {
-                float s, c;
-                bt_sincos(r1, &s, &c);
-                const float w = m_sqrt(sk == SK_COSINE ? r2 : r2 * (1.0f - r2));
-                const float two = sk == SK_COSINE ? 1.0f : 2.0f;
-                cx = c * two * w;
-                sy = s * two * w;
-                z = sk == SK_COSINE ? m_sqrt(1.0f - r2) : (((C & (CT_METAL | CT_GLASS)) && sk == SK_HEMI) ? 1.0f - r2 : 1.0f - 2.0f * r2);
-                X = v3(1.0f, 0.0f, 0.0f);
-                Y = v3(0.0f, 1.0f, 0.0f);
-                Z = v3(0.0f, 0.0f, 1.0f);
-                if (sk != SK_SPHERE) {
-                    Z = normalize_s(nrm);
-                    any_orthonormal_pair(Z, X, Y);
-                }
-            }
-            vec = (X * cx + Y * sy) + Z * z;
-        }
-
-        // ---- 3. the scattered ray ------------------------------------------------------------
-        if (ev != EV_TERMINAL) {
-            flight_reset(fl);  // the scattered ray starts a new flight
-            fstate = FL_FLY;
-            V3 dirvec = vec;  // Cosine, volume scatter
-            if (ev == EV_DIFFUSE && sk != SK_COSINE) {  // Pdf::Light: random_point(light) - origin
-                V3 point = v3(lsamp[1]);                                        // POINT: the translation
-                if (sk == SK_SPHERE) point = v3(lsamp[1]) + vec * lsamp[1].w;   // sphere.rs:40-42
-                if (sk == SK_RECT) point = mat_vec(v3(lsamp[3]), v3(lsamp[4]), v3(lsamp[5]), vec) + v3(lsamp[6]);
-                dirvec = point - pos;
-            }
-            if ((C & (CT_METAL | CT_GLASS)) && ev == EV_SPECULAR) dirvec = dir0 + vec * rough;
-            if (ev == EV_VOLUME && !vol_scatter) dirvec = din;
-            const V3 nd = normalize_a(dirvec);  // Ray::new
-
-            if ((C & CT_VOLUMES) && ev == EV_VOLUME) {
-                o = pos;
-                d = nd;
-                if (vol_scatter) {
-                    if ((C & CT_AOV) && !latched) {
-                        latched = true;
-                        aov_albedo = v3(0.8f, 0.8f, 0.8f);
-                        aov_normal = nrm;
-                        aov_depth = hit_t;
-                    }
-                    T = T * 0.8f;
-                }
-                if (face == 4) {  // VolumeBack: leave the medium through sample(ray, bounce + 1)
-                    vol_obj = -1;
-                    ++bounce;
-                    if (bounce > p.max_bounces) finish = true;
-                } else {          // keep marching: sample_volumetric(.., volume_bounce + 1)
-                    vol_obj = hit_obj;
-                    ++vb;
-                    if (vb > p.max_volume_bounces) finish = true;
-                }
-            } else {
-                float pdf = 1.0f, mpdf = 1.0f;
-                if (ev == EV_DIFFUSE) {
-                    mpdf = dot(nrm, nd) * 0.318309886183790671538f;
-                    const float pb = light_pdf<C>(sc.prims, sc.lights, light, pos, nd, p.clip_min, p.clip_max);
-                    pdf = lerpf(mpdf, pb, 0.5f);
-                }
-                if (fabsf(pdf) <= 1e-5f) {
-                    finish = true;  // no scatter: from_emitted(BLACK)
-                } else {
-                    if ((C & CT_AOV) && !latched) {
-                        latched = true;
-                        aov_albedo = A;
-                        aov_normal = nrm;
-                        aov_depth = hit_t;
-                    }
-                    T = T * ((A * mpdf) * m_rcp(pdf));
-                    o = pos;
-                    d = nd;
-                    vol_obj = -1;
-                    ++bounce;
-                    if (bounce > p.max_bounces) finish = true;  // sample(): black, AOVs already latched
-                }
-            }
-        }
-
-        if (finish) {
-            if ((C & CT_AOV) && !latched) {
-                aov_albedo = fin_albedo;
-                aov_normal = fin_normal;
-                aov_depth = fin_depth;
-            }
-            switch ((C & CT_AOV) ? p.output : 0) {  // mod.rs:306-315
-                case 0: acc = acc + T * fin_color; break;
-                case 1: acc = acc + aov_albedo; break;
-                case 2: acc = acc + aov_normal; break;
-                default: {
-                    float dn = (aov_depth - p.clip_min) * m_rcp(p.clip_max - p.clip_min);
-                    dn = fminf(fmaxf(dn, 0.0f), 1.0f);
-                    acc = acc + v3(dn, dn, dn);
-                }
-            }
-            alive = false;
         }
     }
 
@@ -621,6 +658,20 @@ __global__ void __launch_bounds__(LENS ? 128 : 256, LENS ? 5 : 3) render_kernel(
 template <bool LENS, bool EXACT, int NL, bool BVH, int C = CT_ALL>
 __global__ void __launch_bounds__(256, 2) render_kernel_stats(const __grid_constant__ RenderParams p) {
     render_body<true, LENS, EXACT, NL, BVH, C>(p);
+}
+
+#include "render_pool.cuh"
+// The pooled kernel is limited by shared memory (32 W slots of 80 .. 144 B per warp) as much as by registers:
+// three 192-thread CTAs of a lensed variant (18 warps at <= 112 registers), six 128-thread CTAs of a flat one.
+#define BT_POOL_BOUNDS(LENS) __launch_bounds__((LENS) ? 192 : 128, (LENS) ? 3 : 6)
+template <bool LENS, bool EXACT, int NL, int C = CT_ALL>
+__global__ void BT_POOL_BOUNDS(LENS) render_pool_kernel(const __grid_constant__ RenderParams p) {
+    render_pool_body<LENS, EXACT, NL, C>(p);
+}
+// the same kernel + scheduling counters (bt_render_pool_stats; the content-specialised variants only; never timed)
+template <bool LENS, bool EXACT, int NL, int C>
+__global__ void BT_POOL_BOUNDS(LENS) render_pool_kernel_pstats(const __grid_constant__ RenderParams p) {
+    render_pool_body<LENS, EXACT, NL, C, true>(p);
 }
 
 template <bool LENS, bool EXACT, int NL, bool BVH>
@@ -780,10 +831,82 @@ size_t render_smem_bytes(const RenderParams& p, unsigned threads) {
         else BT_LAUNCH_(KERNEL, true, true, 0, false, TAIL, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);                                      \
     } while (0)
 
+namespace {
+// persistent grid of the pooled kernel: as many CTAs as fit the GPU at once (each warp walks the tiles
+// g, g + G, ...), or fewer when the frame has fewer 8 x 4 tiles than that
+template <class K>
+cudaError_t launch_pool(K kernel, const RenderParams& p, bool lens, bool aov, cudaStream_t stream) {
+    const unsigned cap = lens ? 192 : 128;  // BT_POOL_BOUNDS
+    const unsigned threads = p.pool_threads ? std::min(p.pool_threads, cap) : cap, warps = threads / 32;
+    const size_t smem = (size_t)p.scene.stage_f4 * sizeof(float4) + warps * pool_warp_bytes(p.pool_w, lens, aov);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0, dev = 0, sms = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)threads, smem)) != cudaSuccess) return e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    const uint64_t tiles = (uint64_t)((p.width + 7) / 8) * ((p.row_end - p.row0 + 3) / 4);
+    const uint64_t need = (tiles + warps - 1) / warps, fit = (uint64_t)per_sm * sms;
+    kernel<<<(unsigned)std::max<uint64_t>(1, std::min(need, fit)), threads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+}  // namespace
+
 cudaError_t BT_SFX(launch_render)(const RenderParams& p, cudaStream_t stream, uint64_t* launches) {
+    // (the pooled kernel packs a path's counters into 8 bits each and its volume object into 7: render_pool.cuh)
+    const bool pool_ok = p.pool_w != 0 && p.scene.n_bvh == 0 && p.max_bounces <= POOL_MAX_BOUNCES && p.max_volume_bounces <= POOL_MAX_BOUNCES &&
+                         p.scene.n_prims <= POOL_MAX_OBJECTS;
+    if (pool_ok && p.pool_stats) {
+        const uint32_t ct = p.scene.content;
+        const bool lensed = p.scene.n_lens != 0, ok = p.output == 0 && !(lensed && (p.scene.lens_exact || p.scene.n_lens != 1));
+#define BT_FITS_(C) ((ct & ~(uint32_t)(C)) == 0)
+#define BT_POOL_(L, E, N, C) e_ = launch_pool(render_pool_kernel_pstats<L, E, N, C>, p, L, false, stream)
+        cudaError_t e_ = cudaErrorNotSupported;
+        if (ok && !lensed && BT_FITS_(CT_RECTS)) BT_POOL_(false, false, 0, CT_RECTS);
+        else if (ok && !lensed && BT_FITS_(CT_RECTS | CT_METAL)) BT_POOL_(false, false, 0, CT_RECTS | CT_METAL);
+        else if (ok && !lensed && BT_FITS_(CT_SPHERES | CT_VOLUMES)) BT_POOL_(false, false, 0, CT_SPHERES | CT_VOLUMES);
+        else if (ok && !lensed && BT_FITS_(CT_SPHERES | CT_METAL | CT_GLASS)) BT_POOL_(false, false, 0, CT_SPHERES | CT_METAL | CT_GLASS);
+        else if (ok && lensed && BT_FITS_(CT_SPHERES | CT_METAL | CT_GLASS)) BT_POOL_(true, false, 1, CT_SPHERES | CT_METAL | CT_GLASS);
+        else if (ok && lensed && BT_FITS_(CT_SPHERES | CT_VOLUMES)) BT_POOL_(true, false, 1, CT_SPHERES | CT_VOLUMES);
+#undef BT_POOL_
+#undef BT_FITS_
+        ++*launches;
+        return e_;
+    }
+    if (pool_ok && !p.stats) {
+        // the pooled kernel (render_pool.cuh): the same variants as below
+        const uint32_t ct = p.scene.content | (p.output != 0 ? (uint32_t)CT_AOV : 0u);
+        const bool lensed = p.scene.n_lens != 0, one = p.scene.n_lens == 1, exact = p.scene.lens_exact != 0;
+        const bool special = !(lensed && (exact || !one));
+#define BT_FITS_(C) ((ct & ~(uint32_t)(C)) == 0)
+#define BT_POOL_(L, E, N, C) e_ = launch_pool(render_pool_kernel<L, E, N, C>, p, L, ((C) & CT_AOV) != 0, stream)
+        cudaError_t e_;
+        if (special && !lensed && BT_FITS_(CT_RECTS)) BT_POOL_(false, false, 0, CT_RECTS);
+        else if (special && !lensed && BT_FITS_(CT_RECTS | CT_METAL)) BT_POOL_(false, false, 0, CT_RECTS | CT_METAL);
+        else if (special && !lensed && BT_FITS_(CT_SPHERES | CT_VOLUMES)) BT_POOL_(false, false, 0, CT_SPHERES | CT_VOLUMES);
+        else if (special && !lensed && BT_FITS_(CT_SPHERES | CT_METAL | CT_GLASS)) BT_POOL_(false, false, 0, CT_SPHERES | CT_METAL | CT_GLASS);
+        else if (special && lensed && BT_FITS_(CT_SPHERES | CT_METAL | CT_GLASS)) BT_POOL_(true, false, 1, CT_SPHERES | CT_METAL | CT_GLASS);
+        else if (special && lensed && BT_FITS_(CT_SPHERES | CT_VOLUMES)) BT_POOL_(true, false, 1, CT_SPHERES | CT_VOLUMES);
+        else if (ct & CT_CUBOID_LIGHT) {
+            if (!lensed) BT_POOL_(false, false, 0, CT_ALL);
+            else if (exact) BT_POOL_(true, true, 0, CT_ALL);
+            else if (one) BT_POOL_(true, false, 1, CT_ALL);
+            else BT_POOL_(true, false, 0, CT_ALL);
+        } else {
+            if (!lensed) BT_POOL_(false, false, 0, CT_ALL & ~CT_CUBOID_LIGHT);
+            else if (exact) BT_POOL_(true, true, 0, CT_ALL & ~CT_CUBOID_LIGHT);
+            else if (one) BT_POOL_(true, false, 1, CT_ALL & ~CT_CUBOID_LIGHT);
+            else BT_POOL_(true, false, 0, CT_ALL & ~CT_CUBOID_LIGHT);
+        }
+#undef BT_POOL_
+#undef BT_FITS_
+        ++*launches;
+        return e_;
+    }
     // 128-thread CTAs (16 x 8 pixels): at 72..78 registers seven of them fit an SM (28 warps) where three
     // 256-thread CTAs gave 24 -- cornell2 +3.7 %; BT_WIDE_CTAS=1 keeps 256 threads for the flat kernels (A/B)
-    const bool small = !p.stats && (p.scene.n_lens != 0 || !std::getenv("BT_WIDE_CTAS"));
+    const bool small = !p.stats && (p.scene.n_lens != 0 || !p.wide_ctas);
     const uint32_t rows = p.row_end - p.row0;
     dim3 grid((p.width + 15) / 16, small ? (rows + 7) / 8 : (rows + 15) / 16), block(small ? 128 : 256);
     size_t smem = render_smem_bytes(p, block.x);
@@ -843,6 +966,9 @@ cudaError_t BT_SFX(launch_camera_rays)(const RenderParams& p, uint32_t n, const 
 cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t stream, uint64_t* launches) {
     if (p.n == 0) return cudaSuccess;
     size_t smem = (size_t)p.n_lens * LENS_STRIDE * sizeof(float4);
+    // BT_INTEGRATE_SMEM_PAD=<bytes>: extra dynamic shared memory per CTA, i.e. fewer resident warps per SM
+    // (tools/occupancy_probe.py: how many warps the FMA-dense stepper needs to stay issue-bound)
+    if (const char* pad = std::getenv("BT_INTEGRATE_SMEM_PAD")) smem += (size_t)std::atol(pad);
     cudaError_t e;
     const unsigned grid = (p.n + 255) / 256;
 #define BT_INTEGRATE(EXACT, NL)                                                                \

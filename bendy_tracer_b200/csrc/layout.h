@@ -124,6 +124,13 @@ struct RenderParams {
     uint32_t regen_lanes, regen_patience;      // idle lanes a warp collects before it runs the ray-generation phase
     uint32_t scan_lanes, scan_patience;
     uint32_t steps_per_turn;                   // RK4 steps a flying lane takes between two rounds of ballots        // pending chords a warp collects before it runs the intersection phase
+    // the pooled kernel (render_pool.cuh): 0 = render_body (one path per lane), W > 0 = 32 W path slots per warp
+    uint32_t pool_w;
+    uint32_t pool_refill;            // STEP: lanes that wait for a flight before the warp pays for a refill round
+    uint32_t pool_step_min;          // STEP: with the stack empty, keep stepping while at least this many lanes fly
+    uint32_t pool_threads;           // CTA size of the pooled kernel
+    uint32_t pool_stats;             // launch the pooled kernel's counter variant (bt_render_pool_stats): stats[0..11]
+    uint32_t wide_ctas;              // render_body, flat variants: 256-thread CTAs instead of 128 (A/B knob)
     unsigned long long* stats;       // render_kernel_stats only: {paths, scan calls, RK4 steps, events}
 };
 

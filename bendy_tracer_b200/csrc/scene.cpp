@@ -51,6 +51,14 @@ struct Parser {
         throw ParseError(buf);
     }
     const char* start;
+    int depth = 0;  // serde_json's recursion limit: 128 nested arrays / objects, then an error (never a stack overflow)
+    struct Nest {
+        Parser& ps;
+        explicit Nest(Parser& p_) : ps(p_) {
+            if (++ps.depth > 128) ps.fail("recursion limit exceeded");
+        }
+        ~Nest() { --ps.depth; }
+    };
     void ws() {
         while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p;
     }
@@ -60,6 +68,7 @@ struct Parser {
         JPtr v(new JValue());
         char c = *p;
         if (c == '{') {
+            Nest nest(*this);
             v->type = JValue::Object;
             ++p;
             ws();
@@ -88,6 +97,7 @@ struct Parser {
             }
         }
         if (c == '[') {
+            Nest nest(*this);
             v->type = JValue::Array;
             ++p;
             ws();
@@ -958,16 +968,22 @@ struct BvhBuild {
         int axis = 0;
         for (int k = 1; k < 3; ++k)
             if (cb.hi[k] - cb.lo[k] > cb.hi[axis] - cb.lo[axis]) axis = k;
-        if (count <= 4 || depth >= (int)BVH_STACK - 2 || !(cb.hi[axis] > cb.lo[axis])) {
-            if (count > 127) throw SceneError("BVH: more than 127 coincident primitives in one leaf");
+        // The traversal stack bounds the depth.  A skewed SAH split is only taken while median splits could
+        // still bring what remains down to leaf size; coincident centroids (no axis to split on) are halved by
+        // index -- a leaf holds at most 127 records.
+        const int remaining = (int)BVH_STACK - 2 - depth;
+        const bool degenerate = !(cb.hi[axis] > cb.lo[axis]);
+        if (count <= 4 || remaining <= 0 || (degenerate && count <= 127)) {
+            if (count > 127) throw SceneError("BVH: the scene is too large for the traversal stack");
             return leaf_ref(first, count);
         }
+        const bool force_median = degenerate || (uint64_t)count > ((uint64_t)64 << std::max(0, remaining - 2));
         // binned SAH on the widest centroid axis
         const int NB = 16;
         Bounds bin_box[NB];
         uint32_t bin_n[NB];
         for (int i = 0; i < NB; ++i) { bin_box[i] = empty(); bin_n[i] = 0; }
-        const float scale = (float)NB / (cb.hi[axis] - cb.lo[axis]);
+        const float scale = degenerate ? 0.0f : (float)NB / (cb.hi[axis] - cb.lo[axis]);
         auto bin_of = [&](uint32_t prim) {
             int k = (int)((0.5f * (b[prim].lo[axis] + b[prim].hi[axis]) - cb.lo[axis]) * scale);
             return std::min(std::max(k, 0), NB - 1);
@@ -995,7 +1011,7 @@ struct BvhBuild {
             if (cost < best_cost) { best_cost = cost; best = i; }
         }
         uint32_t mid;
-        if (best >= 0) {
+        if (best >= 0 && !force_median) {
             mid = (uint32_t)(std::partition(order.begin() + first, order.begin() + first + count,
                                             [&](uint32_t prim) { return bin_of(prim) <= best; }) - order.begin());
         } else {

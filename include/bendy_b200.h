@@ -113,6 +113,17 @@ int bt_engine_create(int device, bt_engine** out);
 void bt_engine_destroy(bt_engine* engine);
 /* number of kernels this engine has launched since creation (bench.py's gpu_launches) */
 uint64_t bt_engine_launch_count(const bt_engine* engine);
+/* Scheduling knobs of the kernels -- the counterpart of Config::chunks_x / chunks_y (reference
+ * src/tracer/mod.rs:22-23): they decide how the work is laid out on the device and never change an
+ * image.  Each knob is read ONCE from the environment when the engine is created (BT_<NAME>,
+ * upper case) and can be set per engine here; value < 0 restores the built-in default.
+ *   pool_w          path slots per warp / 32 of the pooled render kernel; 0 = one path per lane
+ *   pool_refill, pool_step_min, pool_threads     refill batch, step-phase exit level, CTA size of that kernel
+ *   host_bands      row bands a BT_MEM_HOST frame is pipelined in (bt_render)
+ *   compact_lanes, compact_patience, regen_lanes, regen_patience, scan_lanes, scan_patience,
+ *   steps_per_turn, wide_ctas                    thresholds of the one-path-per-lane kernel
+ *   lens_no_skip    1: as BT_LENS_NO_SKIP for every scene */
+int bt_engine_set_tuning(bt_engine* engine, const char* name, int64_t value);
 
 /* ---- scene ----------------------------------------------------------------------------- */
 /* serde_json::from_reader(GzDecoder|BufReader) -> Scene, reference src/main.rs:93-102.
@@ -172,7 +183,7 @@ void bt_render_config_default(bt_render_config* cfg);  /* RenderConfig::DEFAULT,
  * Blocking.  mem = BT_MEM_HOST copies the buffer to the device and back inside the call: the frame
  * is pipelined through the GPU in row bands over two streams (upload and download of a band run
  * under its neighbours' kernels; pin the buffer -- cudaHostAlloc / cudaHostRegister -- for the
- * overlap to be real).  The image does not depend on the banding (BT_HOST_BANDS=n overrides it). */
+ * overlap to be real).  The image does not depend on the banding (tuning knob host_bands). */
 int bt_render(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_config* config,
               const bt_render_config* render_config, uint64_t seed, uint64_t sample_base,
               float* rgba32f, int mem, uint32_t width, uint32_t height, uint64_t* samples_inout,
@@ -191,6 +202,15 @@ int bt_render_async(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, con
 int bt_render_stats(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_config* config,
                     const bt_render_config* render_config, uint64_t seed, uint64_t sample_base,
                     uint32_t width, uint32_t height, uint64_t stats_out[4]);
+
+/* Scheduling counters of the pooled render kernel for the same call (an instrumented copy, never timed):
+ * stats_out = {STEP iterations, flying lanes summed over them, refill rounds, STEP entries, SCAN passes,
+ * slots scanned, SHADE passes, slots shaded, REGEN passes, paths issued, paths retired, turns} summed over
+ * all warps -- lanes per pass = slots / passes.  BT_ERR_UNSUPPORTED when pool_w = 0 or the scene runs a
+ * generic (not content-specialised) kernel. */
+int bt_render_pool_stats(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_config* config,
+                         const bt_render_config* render_config, uint64_t seed, uint64_t sample_base,
+                         uint32_t width, uint32_t height, uint64_t stats_out[12]);
 
 /* Buffer::preview, reference src/tracer/buffer.rs:117-138 (+ ColorSpace::convert_linear :19-30,
  * linear_to_srgb / f32_to_u8 src/color.rs:14-24).  rgba8 lives where rgba32f lives. */

@@ -141,7 +141,7 @@ def test_render_contract(oracle):
 
 
 @pytest.mark.parametrize("name,lens", [("cornell2", None), ("scene", LENS_SCENE)])
-def test_host_buffer_bands(oracle, name, lens, monkeypatch):
+def test_host_buffer_bands(oracle, name, lens):
     """bt_render with a host buffer pipelines the frame in row bands over two streams (upload and
     download under the neighbouring band's kernel).  The image must not depend on the banding: one
     band, three ragged bands, many bands and a device-resident buffer agree bit for bit, and the
@@ -152,13 +152,13 @@ def test_host_buffer_bands(oracle, name, lens, monkeypatch):
     start = np.random.default_rng(3).random((h, w, 4), dtype=np.float32)
     images = {}
     for bands in ("1", "3", "64", None):
-        if bands is None:
-            monkeypatch.delenv("BT_HOST_BANDS", raising=False)
-        else:
-            monkeypatch.setenv("BT_HOST_BANDS", bands)
-        buf = bt.Buffer(w, h)
-        buf.data[...] = start
-        images[bands] = engine_render(esc, cam, w, h, 3, 2, 0, seed=9, buffer=buf)[0].copy()
+        bt.Engine.default(0).set_tuning(host_bands=None if bands is None else int(bands))   # (knobs are read per engine, not per call)
+        try:
+            buf = bt.Buffer(w, h)
+            buf.data[...] = start
+            images[bands] = engine_render(esc, cam, w, h, 3, 2, 0, seed=9, buffer=buf)[0].copy()
+        finally:
+            bt.Engine.default(0).set_tuning(host_bands=None)
         assert buf.samples() == 12
     for bands in ("3", "64", None):
         assert np.array_equal(images[bands], images["1"]), bands
