@@ -426,8 +426,9 @@ class Tracer:
             check(lib.bt_render_async(engine.handle, scene.handle, camera, C.byref(cfg), C.byref(rc), self.seed,
                                       sample_base, ptr, buffer.width(), buffer.height(), C.byref(samples),
                                       C.byref(status), C.c_void_p(s)))
-            if sync:
-                torch.cuda.current_stream(buffer.data.device).synchronize()
+            if sync:   # the stream the work was enqueued on, which need not be torch's current one
+                (torch.cuda.ExternalStream(s, device=buffer.data.device) if stream is not None
+                 else torch.cuda.current_stream(buffer.data.device)).synchronize()
         buffer._samples = samples.value
         return Status(status.value)
 

@@ -63,9 +63,14 @@ struct bt_engine {
     cudaStream_t stream2;   // second lane of the host-buffer pipeline (bt_render, BT_MEM_HOST)
     cudaEvent_t ev_fork, ev_join;
     uint64_t launches;
-    // scratch for host-memory calls
+    // scratch for host-memory calls (every user synchronises before it returns)
     void* d_scratch;
     size_t scratch_bytes;
+    // lens tables too large for the kernel parameters (bt_geodesic_integrate): their own buffer, guarded by an event
+    // recorded after the kernel that reads it, because the device-memory flavour of that call does not synchronise
+    float4* d_lens;
+    size_t lens_cap;
+    cudaEvent_t ev_lens;
     int sm_count;
     int clock_khz;
 };
@@ -74,7 +79,9 @@ struct bt_scene;
 static bool use_exact(const bt_engine* e, const bt_scene* s);
 
 struct bt_scene {
-    bt_engine* engine;
+    bt_engine* engine;  // identity of the engine the scene is bound to (compared, never dereferenced: the engine may die first)
+    int device;         // that engine's CUDA device (-1: not bound yet)
+    cudaEvent_t ev_use; // recorded after every kernel that reads d_blob / d_grids: a re-upload waits for it
     Scene scene;
     FlatScene flat;
     int accel;          // ACCEL_AUTO / ACCEL_LINEAR / ACCEL_BVH
@@ -115,6 +122,8 @@ int refresh_scene(bt_scene* s, cudaStream_t stream) {
         s->device_dirty = true;
     }
     if (s->device_dirty) {
+        // a render enqueued without synchronising (bt_render_async) may still be reading the old copy
+        if (s->ev_use) CK(cudaEventSynchronize(s->ev_use));
         size_t bb = s->flat.blob.size() * sizeof(float4), gb = s->flat.grids.size() * sizeof(float);
         if (bb > s->blob_cap) {
             if (s->d_blob) cudaFree(s->d_blob);
@@ -222,6 +231,22 @@ int build_params(const bt_engine* en, bt_scene* s, uint64_t camera_ref, bool nee
     return BT_OK;
 }
 
+// a scene created without an engine binds to the first engine that uses it
+int bind_scene(bt_engine* engine, bt_scene* scene) {
+    if (!scene->engine) {
+        scene->engine = engine;
+        scene->device = engine->device;
+    }
+    if (scene->engine != engine) return fail(BT_ERR_INVALID_ARG, "scene belongs to another engine");
+    return BT_OK;
+}
+// every kernel that reads the scene's device copy is followed by this (refresh_scene / bt_scene_destroy wait for it)
+int mark_scene_use(bt_scene* s, cudaStream_t stream) {
+    if (!s->ev_use) CK(cudaEventCreateWithFlags(&s->ev_use, cudaEventDisableTiming));
+    CK(cudaEventRecord(s->ev_use, stream));
+    return BT_OK;
+}
+
 int check_renderable(const bt_scene* s) {
     if (s->flat.diffuse_without_light)
         return fail(BT_ERR_SCENE, "Uniform::new called with `low >= high` (a Diffuse surface needs at least one LIGHT object)");
@@ -266,6 +291,9 @@ int bt_engine_create(int device, bt_engine** out) {
     en->launches = 0;
     en->d_scratch = 0;
     en->scratch_bytes = 0;
+    en->d_lens = 0;
+    en->lens_cap = 0;
+    en->ev_lens = 0;
     en->sm_count = prop.multiProcessorCount;
     int khz = 0;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
@@ -288,6 +316,8 @@ void bt_engine_destroy(bt_engine* engine) {
     if (!engine) return;
     cudaSetDevice(engine->device);
     if (engine->d_scratch) cudaFree(engine->d_scratch);
+    if (engine->d_lens) cudaFree(engine->d_lens);
+    if (engine->ev_lens) cudaEventDestroy(engine->ev_lens);
     if (engine->ev_fork) cudaEventDestroy(engine->ev_fork);
     if (engine->ev_join) cudaEventDestroy(engine->ev_join);
     if (engine->stream2) cudaStreamDestroy(engine->stream2);
@@ -312,6 +342,8 @@ int bt_scene_create_json(bt_engine* engine, const void* bytes, size_t n, bt_scen
     GUARD_BEGIN
     bt_scene* s = new bt_scene();
     s->engine = engine;
+    s->device = engine ? engine->device : -1;
+    s->ev_use = 0;
     s->d_blob = 0;
     s->d_grids = 0;
     s->blob_cap = s->grids_cap = 0;
@@ -351,7 +383,11 @@ void bt_free(void* p) { std::free(p); }
 
 void bt_scene_destroy(bt_scene* scene) {
     if (!scene) return;
-    if (scene->engine) cudaSetDevice(scene->engine->device);
+    if (scene->device >= 0) cudaSetDevice(scene->device);
+    if (scene->ev_use) {
+        cudaEventSynchronize(scene->ev_use);
+        cudaEventDestroy(scene->ev_use);
+    }
     if (scene->d_blob) cudaFree(scene->d_blob);
     if (scene->d_grids) cudaFree(scene->d_grids);
     delete scene;
@@ -488,13 +524,13 @@ int render_rows(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const b
     p.row0 = row0;
     p.row_end = row_end;
     CK(use_exact(engine, scene) ? launch_render_exact(p, stream, &engine->launches) : launch_render_fast(p, stream, &engine->launches));
+    if ((rcode = mark_scene_use(scene, stream)) != BT_OK) return rcode;
     if (sub_count_out) *sub_count_out = p.sub_count;
     return BT_OK;
 }
 int check_render_args(bt_engine* engine, bt_scene* scene, const bt_config* config, const bt_render_config* rc, const float* fb,
                       uint32_t width, uint32_t height) {
-    if (!scene->engine) scene->engine = engine;  // a scene created without an engine binds on first use
-    if (scene->engine != engine) return fail(BT_ERR_INVALID_ARG, "scene belongs to another engine");
+    if (int b = bind_scene(engine, scene)) return b;
     if (!fb || width == 0 || height == 0) return fail(BT_ERR_INVALID_ARG, "empty buffer");
     if (config->output < 0 || config->output > 3 || (rc->has_output && (rc->output < 0 || rc->output > 3)))
         return fail(BT_ERR_INVALID_ARG, "invalid Output");
@@ -530,8 +566,7 @@ int bt_render_stats(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, con
                     uint64_t stats_out[4]) {
     if (!engine || !scene || !config || !rc || !stats_out) return fail(BT_ERR_INVALID_ARG, "NULL argument");
     GUARD_BEGIN
-    if (!scene->engine) scene->engine = engine;
-    if (scene->engine != engine) return fail(BT_ERR_INVALID_ARG, "scene belongs to another engine");
+    if (int b = bind_scene(engine, scene)) return b;
     for (int i = 0; i < 4; ++i) stats_out[i] = 0;
     if (rc->samples == 0) return BT_OK;
     CK(cudaSetDevice(engine->device));
@@ -559,8 +594,7 @@ int bt_render_pool_stats(bt_engine* engine, bt_scene* scene, uint64_t camera_ref
                          uint64_t stats_out[12]) {
     if (!engine || !scene || !config || !rc || !stats_out) return fail(BT_ERR_INVALID_ARG, "NULL argument");
     GUARD_BEGIN
-    if (!scene->engine) scene->engine = engine;
-    if (scene->engine != engine) return fail(BT_ERR_INVALID_ARG, "scene belongs to another engine");
+    if (int b = bind_scene(engine, scene)) return b;
     for (int i = 0; i < 12; ++i) stats_out[i] = 0;
     if (rc->samples == 0) return BT_OK;
     CK(cudaSetDevice(engine->device));
@@ -677,8 +711,7 @@ int bt_trace_segments(bt_engine* engine, bt_scene* scene, const bt_config* confi
                       const float* origins, const float* dirs, bt_segment* out) {
     if (!engine || !scene || !config || (n && (!origins || !dirs || !out))) return fail(BT_ERR_INVALID_ARG, "NULL argument");
     GUARD_BEGIN
-    if (!scene->engine) scene->engine = engine;
-    if (scene->engine != engine) return fail(BT_ERR_INVALID_ARG, "scene belongs to another engine");
+    if (int b = bind_scene(engine, scene)) return b;
     CK(cudaSetDevice(engine->device));
     int r = refresh_scene(scene, engine->stream);
     if (r != BT_OK) return r;
@@ -718,8 +751,7 @@ int bt_camera_rays(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, cons
                    uint32_t n, const uint32_t* xs, const uint32_t* ys, const uint64_t* path_index, float* out) {
     if (!engine || !scene || !config || !rc || (n && (!xs || !ys || !path_index || !out))) return fail(BT_ERR_INVALID_ARG, "NULL argument");
     GUARD_BEGIN
-    if (!scene->engine) scene->engine = engine;
-    if (scene->engine != engine) return fail(BT_ERR_INVALID_ARG, "scene belongs to another engine");
+    if (int b = bind_scene(engine, scene)) return b;
     CK(cudaSetDevice(engine->device));
     int r = refresh_scene(scene, engine->stream);
     if (r != BT_OK) return r;
@@ -755,15 +787,27 @@ int bt_geodesic_integrate(bt_engine* engine, const float* xyzr, uint32_t n_lense
         lens.push_back(e0);
         lens.push_back(e1);
     }
-    size_t lens_bytes = (lens.size() * sizeof(float4) + 255) & ~(size_t)255;
-    size_t xv_bytes = (size_t)n * 6 * sizeof(float);
-    int r = ensure_scratch(engine, lens_bytes + 256 + (mem == BT_MEM_HOST ? xv_bytes : 0));
-    if (r != BT_OK) return r;
-    char* base = (char*)engine->d_scratch;
-    if (!lens.empty()) CK(cudaMemcpyAsync(base, lens.data(), lens.size() * sizeof(float4), cudaMemcpyHostToDevice, stream));
     IntegrateParams p;
-    p.lens = (const float4*)base;
+    std::memset(&p, 0, sizeof p);
     p.n_lens = (uint32_t)(lens.size() / LENS_STRIDE);
+    if (p.n_lens <= INTEGRATE_INLINE_LENSES) {
+        std::copy(lens.begin(), lens.end(), p.inline_lens);  // by value: nothing to upload, nothing to race with
+    } else {
+        // a table of its own, never shared with the scratch of the other entry points; the previous launch that read
+        // it (possibly still running on the caller's stream) must be over before it is overwritten
+        const size_t bytes = lens.size() * sizeof(float4);
+        if (engine->ev_lens) CK(cudaEventSynchronize(engine->ev_lens));
+        if (bytes > engine->lens_cap) {
+            if (engine->d_lens) cudaFree(engine->d_lens);
+            engine->d_lens = 0;
+            engine->lens_cap = 0;
+            CK(cudaMalloc((void**)&engine->d_lens, bytes));
+            engine->lens_cap = bytes;
+        }
+        CK(cudaMemcpyAsync(engine->d_lens, lens.data(), bytes, cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));  // the upload reads a stack vector
+        p.lens = engine->d_lens;
+    }
     p.kappa = c.kappa;
     p.h_min = c.h_min;
     p.h_max = c.h_max;
@@ -771,7 +815,10 @@ int bt_geodesic_integrate(bt_engine* engine, const float* xyzr, uint32_t n_lense
     p.n_steps = n_steps;
     p.exact = c.flags & BT_LENS_EXACT_RSQRT;
     if (mem == BT_MEM_HOST) {
-        float* d_xv = (float*)(base + lens_bytes + 256);
+        size_t xv_bytes = (size_t)n * 6 * sizeof(float);
+        int r = ensure_scratch(engine, xv_bytes + 256);
+        if (r != BT_OK) return r;
+        float* d_xv = (float*)engine->d_scratch;
         CK(cudaMemcpyAsync(d_xv, xv, xv_bytes, cudaMemcpyHostToDevice, stream));
         p.xv = d_xv;
         CK(launch_integrate(p, stream, &engine->launches));
@@ -779,8 +826,11 @@ int bt_geodesic_integrate(bt_engine* engine, const float* xyzr, uint32_t n_lense
         CK(cudaStreamSynchronize(stream));
     } else {
         p.xv = xv;
-        CK(cudaStreamSynchronize(stream));  // the lens table upload reads a stack vector
         CK(launch_integrate(p, stream, &engine->launches));
+        if (p.lens) {
+            if (!engine->ev_lens) CK(cudaEventCreateWithFlags(&engine->ev_lens, cudaEventDisableTiming));
+            CK(cudaEventRecord(engine->ev_lens, stream));
+        }
     }
     return BT_OK;
 }

@@ -728,9 +728,10 @@ __global__ void camera_rays_kernel(const __grid_constant__ RenderParams p, uint3
 // The geodesic stepper in isolation: n_steps RK4 steps per ray, state in registers, the lens
 // table in shared memory.  No memory traffic in the loop: this is the FP32-roofline kernel.
 template <bool EXACT, int NL>
-__global__ void __launch_bounds__(256) integrate_kernel(const IntegrateParams p) {
+__global__ void __launch_bounds__(256) integrate_kernel(const __grid_constant__ IntegrateParams p) {
     extern __shared__ float4 slens[];
-    for (uint32_t i = threadIdx.x; i < p.n_lens * LENS_STRIDE; i += blockDim.x) slens[i] = p.lens[i];
+    for (uint32_t i = threadIdx.x; i < p.n_lens * LENS_STRIDE; i += blockDim.x)
+        slens[i] = p.n_lens <= INTEGRATE_INLINE_LENSES ? p.inline_lens[i] : p.lens[i];
     __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;

@@ -15,8 +15,12 @@ struct DeviceSegment {  // mirrors bt_segment (include/bendy_b200.h) with the ob
     float position[3], normal[3], direction[3];
 };
 
+enum { INTEGRATE_INLINE_LENSES = 16 };
 struct IntegrateParams {
-    const float4* lens;   // LENS_STRIDE records, device memory
+    // tables of up to INTEGRATE_INLINE_LENSES masses travel BY VALUE in the kernel parameters (no upload, nothing
+    // for an asynchronous caller to race with); larger ones are read from `lens`
+    float4 inline_lens[INTEGRATE_INLINE_LENSES * LENS_STRIDE];
+    const float4* lens;   // LENS_STRIDE records, device memory (n_lens > INTEGRATE_INLINE_LENSES)
     uint32_t n_lens;
     float kappa, h_min, h_max;
     float* xv;            // n * 6

@@ -71,5 +71,36 @@ def test_render_sharded_gloo(world, samples, all_ranks):
             assert np.allclose(data[..., :3], expect, rtol=1e-6) and n == 8 + samples * 4
             assert (data[..., 3] == 1.0).all()                       # alpha is not summed
         else:
-            assert (data[..., :3] == 2.0).all() and n == 8           # non-root buffers untouched
+            assert (data[..., :3] == 2.0).all()                      # non-root images untouched ...
+            assert n == 8 + samples * 4                              # ... but every rank's pass counter advances (it keys the next call)
     assert sorted(covered) == list(range(10, 10 + samples))          # disjoint, complete pass ranges
+
+
+def _progressive_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rc = bt.RenderConfig.with_samples_subsample(3, bt.Subsample.subpixel(2))
+        tracer, buf = FakeTracer(), bt.Buffer(5, 3)
+        for _ in range(2):                                   # the reference's progressive loop (main.rs:245-254): default sample_base
+            bt.render_sharded(tracer, None, 0, rc, buf, all_ranks=True)
+        once_tracer, once = FakeTracer(), bt.Buffer(5, 3)
+        bt.render_sharded(once_tracer, None, 0, bt.RenderConfig.with_samples_subsample(6, bt.Subsample.subpixel(2)), once, all_ranks=True)
+        out[rank] = (buf.data.copy(), buf.samples(), once.data.copy(), once.samples(), tracer.calls)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_render_sharded_progressive_calls_draw_new_passes():
+    """two calls of 3 passes into one buffer == one call of 6 passes: the default sample_base continues at the
+    buffer's pass count on every rank, so repeated calls never re-render the same sample sets"""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_progressive_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    covered = []
+    for rank in range(2):
+        twice, n2, once, n1, calls = out[rank]
+        assert n2 == n1 == 24
+        assert np.allclose(twice, once, rtol=1e-6)
+        covered += [g for base, cnt in calls for g in range(base, base + cnt)]
+    assert sorted(covered) == list(range(6))                 # global passes 0..5, each rendered exactly once
