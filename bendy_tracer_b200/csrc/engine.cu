@@ -39,7 +39,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 // engine is created (BT_<NAME>), and settable per engine with bt_engine_set_tuning; -1 = the built-in default.
 struct Tuning {
     int64_t compact_lanes = -1, compact_patience = -1, regen_lanes = -1, regen_patience = -1, scan_lanes = -1, scan_patience = -1;
-    int64_t steps_per_turn = -1, lens_no_skip = -1, host_bands = -1, wide_ctas = -1;
+    int64_t steps_per_turn = -1, lens_no_skip = -1, lens_bound_all = -1, host_bands = -1, wide_ctas = -1;
     int64_t pool_w = -1, pool_refill = -1, pool_step_min = -1, pool_threads = -1;
 };
 struct TuningName {
@@ -50,7 +50,7 @@ static const TuningName kTuning[] = {
     {"compact_lanes", &Tuning::compact_lanes}, {"compact_patience", &Tuning::compact_patience},
     {"regen_lanes", &Tuning::regen_lanes},     {"regen_patience", &Tuning::regen_patience},
     {"scan_lanes", &Tuning::scan_lanes},       {"scan_patience", &Tuning::scan_patience},
-    {"steps_per_turn", &Tuning::steps_per_turn}, {"lens_no_skip", &Tuning::lens_no_skip},
+    {"steps_per_turn", &Tuning::steps_per_turn}, {"lens_no_skip", &Tuning::lens_no_skip}, {"lens_bound_all", &Tuning::lens_bound_all},
     {"host_bands", &Tuning::host_bands},       {"wide_ctas", &Tuning::wide_ctas},
     {"pool_w", &Tuning::pool_w},               {"pool_refill", &Tuning::pool_refill},
     {"pool_step_min", &Tuning::pool_step_min}, {"pool_threads", &Tuning::pool_threads},
@@ -71,6 +71,10 @@ struct bt_engine {
     float4* d_lens;
     size_t lens_cap;
     cudaEvent_t ev_lens;
+    // path-state arenas of the pooled render kernel (render_pool.cuh), one per pipeline lane of bt_render: two launches
+    // that may overlap (neighbouring row bands on the two streams) never share one
+    char* d_pool_q[2];
+    size_t pool_q_cap[2];
     int sm_count;
     int clock_khz;
 };
@@ -218,12 +222,13 @@ int build_params(const bt_engine* en, bt_scene* s, uint64_t camera_ref, bool nee
     p.scan_lanes = knob(tn.scan_lanes, 8);      // (profiles/r1_sweep_nearest_sphere_bound.log: flat within 1 % from 6/2 to 8/4)
     p.scan_patience = knob(tn.scan_patience, 3);
     if (tn.lens_no_skip > 0) p.scene.lens_skip = 0;
+    if (tn.lens_bound_all > 0 && p.scene.lens_skip) p.scene.lens_skip = 2;
     p.steps_per_turn = std::max(1u, knob(tn.steps_per_turn, long_flights ? 3 : 2));
     p.wide_ctas = knob(tn.wide_ctas, 0);
     // the pooled kernel (render_pool.cuh): 32 W path slots per warp; 0 = one path per lane (render_body)
     p.pool_w = std::min(knob(tn.pool_w, 0), 8u);
-    p.pool_refill = std::max(1u, knob(tn.pool_refill, 6));
-    p.pool_step_min = knob(tn.pool_step_min, 24);
+    p.pool_refill = std::max(1u, knob(tn.pool_refill, 3));   // (gpurun_out/r2_sweep_pool_C3c.log: 3 / 32 best of {3, 6, 9} x {24, 28, 32})
+    p.pool_step_min = knob(tn.pool_step_min, 32);
     p.pool_threads = knob(tn.pool_threads, 0) & ~31u;  // 0: the kernel's own CTA size (launch_pool)
     p.tau_scale = uniform_scale_inclusive(0.0f, 6.28318530717958647692f);
     p.one_scale = uniform_scale_inclusive(0.0f, 1.0f);
@@ -294,6 +299,8 @@ int bt_engine_create(int device, bt_engine** out) {
     en->d_lens = 0;
     en->lens_cap = 0;
     en->ev_lens = 0;
+    en->d_pool_q[0] = en->d_pool_q[1] = 0;
+    en->pool_q_cap[0] = en->pool_q_cap[1] = 0;
     en->sm_count = prop.multiProcessorCount;
     int khz = 0;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
@@ -317,6 +324,8 @@ void bt_engine_destroy(bt_engine* engine) {
     cudaSetDevice(engine->device);
     if (engine->d_scratch) cudaFree(engine->d_scratch);
     if (engine->d_lens) cudaFree(engine->d_lens);
+    for (int i = 0; i < 2; ++i)
+        if (engine->d_pool_q[i]) cudaFree(engine->d_pool_q[i]);
     if (engine->ev_lens) cudaEventDestroy(engine->ev_lens);
     if (engine->ev_fork) cudaEventDestroy(engine->ev_fork);
     if (engine->ev_join) cudaEventDestroy(engine->ev_join);
@@ -512,9 +521,26 @@ namespace {
 // The body of Tracer::render for pixel rows [row0, row_end) of the frame at `fb` (device memory):
 // checks, per-call constants, ONE kernel launch on `stream`.  bt_render_async renders the whole
 // frame with it; bt_render pipelines a host frame through it in bands.
+int ensure_pool_arena(bt_engine* e, int lane, RenderParams* p) {
+    if (p->pool_w == 0) return BT_OK;
+    const size_t bytes = render_pool_arena_bytes(p->pool_w, e->sm_count);
+    if (bytes > e->pool_q_cap[lane]) {
+        // (only ever grows; a kernel that may still read the old arena was launched on this lane's stream, and
+        // cudaFree synchronises the device)
+        if (e->d_pool_q[lane]) cudaFree(e->d_pool_q[lane]);
+        e->d_pool_q[lane] = 0;
+        e->pool_q_cap[lane] = 0;
+        CK(cudaMalloc((void**)&e->d_pool_q[lane], bytes));
+        e->pool_q_cap[lane] = bytes;
+    }
+    p->pool_q = e->d_pool_q[lane];
+    p->pool_q_cap = e->pool_q_cap[lane];
+    return BT_OK;
+}
+
 int render_rows(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_config* config, const bt_render_config* rc,
                 uint64_t seed, uint64_t sample_base, float* fb, uint32_t width, uint32_t height, uint32_t row0, uint32_t row_end,
-                cudaStream_t stream, uint32_t* sub_count_out) {
+                cudaStream_t stream, int lane, uint32_t* sub_count_out) {
     int rcode = refresh_scene(scene, stream);
     if (rcode != BT_OK) return rcode;
     if ((rcode = check_renderable(scene)) != BT_OK) return rcode;
@@ -523,6 +549,7 @@ int render_rows(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const b
     p.fb = (float4*)fb;
     p.row0 = row0;
     p.row_end = row_end;
+    if ((rcode = ensure_pool_arena(engine, lane, &p)) != BT_OK) return rcode;
     CK(use_exact(engine, scene) ? launch_render_exact(p, stream, &engine->launches) : launch_render_fast(p, stream, &engine->launches));
     if ((rcode = mark_scene_use(scene, stream)) != BT_OK) return rcode;
     if (sub_count_out) *sub_count_out = p.sub_count;
@@ -553,7 +580,7 @@ int bt_render_async(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, con
     cudaStream_t stream = (cudaStream_t)cuda_stream;  // NULL is the CUDA default stream, taken literally
     uint32_t sub_count = 1;
     if ((rcode = render_rows(engine, scene, camera_ref, config, rc, seed, sample_base, rgba32f_device, width, height, 0, height,
-                             stream, &sub_count)) != BT_OK)
+                             stream, 0, &sub_count)) != BT_OK)
         return rcode;
     if (samples_inout) *samples_inout += rc->samples * sub_count;  // mod.rs:199
     *status = BT_STATUS_IN_PROGRESS;
@@ -591,11 +618,11 @@ int bt_render_stats(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, con
 
 int bt_render_pool_stats(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_config* config,
                          const bt_render_config* rc, uint64_t seed, uint64_t sample_base, uint32_t width, uint32_t height,
-                         uint64_t stats_out[12]) {
+                         uint64_t stats_out[17]) {
     if (!engine || !scene || !config || !rc || !stats_out) return fail(BT_ERR_INVALID_ARG, "NULL argument");
     GUARD_BEGIN
     if (int b = bind_scene(engine, scene)) return b;
-    for (int i = 0; i < 12; ++i) stats_out[i] = 0;
+    for (int i = 0; i < 17; ++i) stats_out[i] = 0;
     if (rc->samples == 0) return BT_OK;
     CK(cudaSetDevice(engine->device));
     int rcode = refresh_scene(scene, engine->stream);
@@ -605,18 +632,19 @@ int bt_render_pool_stats(bt_engine* engine, bt_scene* scene, uint64_t camera_ref
     if ((rcode = build_params(engine, scene, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return rcode;
     if (p.pool_w == 0) return fail(BT_ERR_UNSUPPORTED, "the pooled kernel is switched off (tuning knob pool_w = 0)");
     size_t fb_bytes = (size_t)width * height * 16;
-    if ((rcode = ensure_scratch(engine, fb_bytes + 128)) != BT_OK) return rcode;
-    CK(cudaMemsetAsync(engine->d_scratch, 0, fb_bytes + 128, engine->stream));
+    if ((rcode = ensure_scratch(engine, fb_bytes + 256)) != BT_OK) return rcode;
+    CK(cudaMemsetAsync(engine->d_scratch, 0, fb_bytes + 256, engine->stream));
     p.fb = (float4*)engine->d_scratch;
     p.stats = (unsigned long long*)((char*)engine->d_scratch + fb_bytes);
     p.pool_stats = 1;
+    if ((rcode = ensure_pool_arena(engine, 0, &p)) != BT_OK) return rcode;
     cudaError_t ce = use_exact(engine, scene) ? launch_render_exact(p, engine->stream, &engine->launches) : launch_render_fast(p, engine->stream, &engine->launches);
     if (ce == cudaErrorNotSupported) return fail(BT_ERR_UNSUPPORTED, "scheduling counters exist for the content-specialised pooled kernels only");
     CK(ce);
-    unsigned long long host[12];
+    unsigned long long host[17];
     CK(cudaMemcpyAsync(host, p.stats, sizeof host, cudaMemcpyDeviceToHost, engine->stream));
     CK(cudaStreamSynchronize(engine->stream));
-    for (int i = 0; i < 12; ++i) stats_out[i] = host[i];
+    for (int i = 0; i < 17; ++i) stats_out[i] = host[i];
     return BT_OK;
     GUARD_END
 }
@@ -667,7 +695,7 @@ int bt_render(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_
         cudaError_t ce = cudaMemcpyAsync(dev, host, n, cudaMemcpyHostToDevice, st);
         if (ce == cudaSuccess) {
             r = render_rows(engine, scene, camera_ref, config, rc, seed, sample_base, (float*)engine->d_scratch, width, height, row0,
-                            row_end, st, &sub_count);
+                            row_end, st, band & 1, &sub_count);
             if (r == BT_OK) ce = cudaMemcpyAsync(host, dev, n, cudaMemcpyDeviceToHost, st);
         }
         if (ce != cudaSuccess || r != BT_OK) {  // drain both lanes before reporting
@@ -799,6 +827,8 @@ int bt_geodesic_integrate(bt_engine* engine, const float* xyzr, uint32_t n_lense
         if (engine->ev_lens) CK(cudaEventSynchronize(engine->ev_lens));
         if (bytes > engine->lens_cap) {
             if (engine->d_lens) cudaFree(engine->d_lens);
+    for (int i = 0; i < 2; ++i)
+        if (engine->d_pool_q[i]) cudaFree(engine->d_pool_q[i]);
             engine->d_lens = 0;
             engine->lens_cap = 0;
             CK(cudaMalloc((void**)&engine->d_lens, bytes));

@@ -126,7 +126,17 @@ BT_DEV int geodesic_step(const RenderParams& p, const L& lens, const float4* pri
     if (far) return FL_PEND_FAR;
     const V3 x0 = x;
     float free = f.free;
-    if ((C & CT_SPHERES) && f.near >= 0) {
+    if ((C & CT_SPHERES) && !(C & CT_RECTS) && p.scene.lens_skip == 2) {
+        // EXPERIMENT (tuning knob lens_bound_all): the exact bound of EVERY sphere at every step -- the floor of the
+        // number of intersection passes that any free-distance scheme can reach (not a production path: 13 instructions per sphere)
+        free = __int_as_float(0x7f800000);
+        for (int i = 0; i < (int)p.scene.n_prims; ++i) {
+            const float4* q = prims + i * PRIM_STRIDE;
+            const float4 q0 = q[0], q1 = q[1];
+            const V3 oc = x0 - v3(q0);
+            free = fminf(free, sphere_free_bound(q0, q1, fmaf(oc.z, oc.z, fmaf(oc.y, oc.y, oc.x * oc.x))));
+        }
+    } else if ((C & CT_SPHERES) && f.near >= 0) {
         const float4* q = prims + f.near * PRIM_STRIDE;
         const float4 q0 = q[0], q1 = q[1];
         const V3 oc = x0 - v3(q0);
@@ -661,9 +671,9 @@ __global__ void __launch_bounds__(256, 2) render_kernel_stats(const __grid_const
 }
 
 #include "render_pool.cuh"
-// The pooled kernel is limited by shared memory (32 W slots of 80 .. 144 B per warp) as much as by registers:
-// three 192-thread CTAs of a lensed variant (18 warps at <= 112 registers), six 128-thread CTAs of a flat one.
-#define BT_POOL_BOUNDS(LENS) __launch_bounds__((LENS) ? 192 : 128, (LENS) ? 3 : 6)
+// 128-thread CTAs: five of a lensed variant per SM (20 warps at <= 96 registers; 32 W slots x 64 B of shared memory
+// per warp), six of a flat one.
+#define BT_POOL_BOUNDS(LENS) __launch_bounds__(128, (LENS) ? 5 : 6)
 template <bool LENS, bool EXACT, int NL, int C = CT_ALL>
 __global__ void BT_POOL_BOUNDS(LENS) render_pool_kernel(const __grid_constant__ RenderParams p) {
     render_pool_body<LENS, EXACT, NL, C>(p);
@@ -806,6 +816,9 @@ cudaError_t ensure_smem(K kernel, size_t bytes) {
 }  // namespace
 
 #ifndef BT_EXACT_SCAN
+size_t render_pool_arena_bytes(uint32_t pool_w, int sm_count) {
+    return (size_t)sm_count * 8 /* CTAs per SM at most */ * 6 /* warps per CTA at most */ * pool_q_bytes(pool_w);
+}
 size_t render_smem_bytes(const RenderParams& p, unsigned threads) {
     return (size_t)p.scene.stage_f4 * sizeof(float4) + (p.scene.n_bvh ? (size_t)BVH_STACK * threads * 2 * sizeof(uint32_t) : 0);
 }
@@ -837,9 +850,10 @@ namespace {
 // g, g + G, ...), or fewer when the frame has fewer 8 x 4 tiles than that
 template <class K>
 cudaError_t launch_pool(K kernel, const RenderParams& p, bool lens, bool aov, cudaStream_t stream) {
-    const unsigned cap = lens ? 192 : 128;  // BT_POOL_BOUNDS
+    const unsigned cap = 128;  // BT_POOL_BOUNDS
     const unsigned threads = p.pool_threads ? std::min(p.pool_threads, cap) : cap, warps = threads / 32;
-    const size_t smem = (size_t)p.scene.stage_f4 * sizeof(float4) + warps * pool_warp_bytes(p.pool_w, lens, aov);
+    (void)aov;
+    const size_t smem = (size_t)p.scene.stage_f4 * sizeof(float4) + warps * pool_warp_bytes(p.pool_w, lens);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0, dev = 0, sms = 0;
@@ -849,7 +863,9 @@ cudaError_t launch_pool(K kernel, const RenderParams& p, bool lens, bool aov, cu
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     const uint64_t tiles = (uint64_t)((p.width + 7) / 8) * ((p.row_end - p.row0 + 3) / 4);
     const uint64_t need = (tiles + warps - 1) / warps, fit = (uint64_t)per_sm * sms;
-    kernel<<<(unsigned)std::max<uint64_t>(1, std::min(need, fit)), threads, smem, stream>>>(p);
+    const uint64_t room = p.pool_q_cap / (pool_q_bytes(p.pool_w) * warps);  // CTAs the path-state arena has room for
+    if (room < 1 || !p.pool_q) return cudaErrorMemoryAllocation;
+    kernel<<<(unsigned)std::max<uint64_t>(1, std::min(std::min(need, fit), room)), threads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 }  // namespace

@@ -50,29 +50,34 @@ enum { POOL_MAX_BOUNCES = 254, POOL_MAX_OBJECTS = 126 };
 BT_DEV uint32_t pack_misc(uint32_t ring, bool latched, int vol_obj, uint32_t bounce, uint32_t vb) {
     return ring | (latched ? 16u : 0u) | ((uint32_t)(vol_obj + 1) << 5) | (bounce << 12) | (vb << 20);
 }
-// bytes of one warp's pool (host + device)
-__host__ __device__ inline size_t pool_warp_bytes(uint32_t w, bool lens, bool aov) {
+// Bytes of one warp's pool.  Shared memory holds what the STEP and SCAN phases touch: the flights F, the slot states
+// and the queues.  The path state Q (48 B per slot, + 32 B of AOV latches) is read and written once per EVENT (1.5 .. 5
+// per path) by SHADE / REGEN only and lives in global memory (an L2-resident scratch arena of the engine,
+// pool_q_bytes per warp of the persistent grid): the shared memory it would take is worth two more CTAs per SM.
+__host__ __device__ inline size_t pool_warp_bytes(uint32_t w, bool lens) {
     const size_t P = 32u * w;
-    return P * (lens ? 64 : 32) + P * 48 + (aov ? P * 32 : 0) + 3 * P + POOL_RING * 32;
+    return P * (lens ? 64 : 32) + 3 * P + POOL_RING * 32;
 }
+__host__ __device__ inline size_t pool_q_bytes(uint32_t w) { return (size_t)32u * w * 80; }
 template <bool LENS, bool AOV>
-BT_DEV Pool pool_carve(char* base, uint32_t P) {
+BT_DEV Pool pool_carve(char* base, char* qbase, uint32_t P) {
     Pool pl;
     float4* f = reinterpret_cast<float4*>(base);
     pl.fa = f; f += P;
     pl.fb = f; f += P;
     pl.fc = pl.fd = f;
     if (LENS) { pl.fc = f; f += P; pl.fd = f; f += P; }
-    pl.qa = reinterpret_cast<uint4*>(f); f += P;
-    pl.qb = reinterpret_cast<uint4*>(f); f += P;
-    pl.qc = f; f += P;
-    pl.qe = pl.qf = f;
-    if (AOV) { pl.qe = f; f += P; pl.qf = f; f += P; }
     uint8_t* b = reinterpret_cast<uint8_t*>(f);
     pl.st = b; b += P;
     pl.list = b; b += P;
     pl.stack = b; b += P;
     pl.ring = b;
+    float4* q = reinterpret_cast<float4*>(qbase);
+    pl.qa = reinterpret_cast<uint4*>(q);
+    pl.qb = reinterpret_cast<uint4*>(q + P);
+    pl.qc = q + 2 * P;
+    pl.qe = q + 3 * P;
+    pl.qf = q + 4 * P;
     return pl;
 }
 // The slots whose state lies in [lo, hi], compacted into pl.list (ballot + popc); stops once 32 are found.
@@ -101,7 +106,7 @@ BT_DEV void unpack_hit(uint32_t w, Hit& h) {
 
 // PSTATS: scheduling counters (bt_render_pool_stats; never timed): p.stats[0..11] = STEP iterations, flying lanes summed
 // over them, refill rounds, STEP entries, SCAN passes, slots scanned, SHADE passes, slots shaded, REGEN passes,
-// paths issued, paths retired, turns
+// paths issued, paths retired, turns; [12..16] = SM clocks the warps spent in STEP, SCAN, SHADE, REGEN and in the kernel
 template <bool LENS, bool EXACT, int NL, int C, bool PSTATS = false>
 BT_DEV void render_pool_body(const RenderParams& p) {
     extern __shared__ float4 smem[];
@@ -116,7 +121,8 @@ BT_DEV void render_pool_body(const RenderParams& p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t W = p.pool_w, P = 32u * W;
-    const Pool pl = pool_carve<LENS, AOV>(reinterpret_cast<char*>(smem + p.scene.stage_f4) + warp * pool_warp_bytes(W, LENS, AOV), P);
+    const Pool pl = pool_carve<LENS, AOV>(reinterpret_cast<char*>(smem + p.scene.stage_f4) + warp * pool_warp_bytes(W, LENS),
+                                          p.pool_q + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * pool_q_bytes(W), P);
     for (uint32_t w = 0; w < W; ++w) pl.st[w * 32 + lane] = ST_IDLE;
     __syncwarp();
 
@@ -133,6 +139,8 @@ BT_DEV void render_pool_body(const RenderParams& p) {
     bool regen_futile = false;
     uint32_t turn = 0, w0 = 0;  // w0: the pool row the slot lists start at (rotates)
     uint32_t ps[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // PSTATS only (warp-uniform)
+    long long pc[5] = {0, 0, 0, 0, 0}, pc_t0 = 0;            // PSTATS only: SM clocks in STEP / SCAN / SHADE / REGEN, and in all
+    if (PSTATS) pc_t0 = clock64();
 
 #pragma unroll 1
     for (;;) {
@@ -144,7 +152,11 @@ BT_DEV void render_pool_body(const RenderParams& p) {
         if (best == 0) break;
         if (++w0 >= W) w0 = 0;
 
+        long long pc_in = 0;
+        if (PSTATS) pc_in = clock64();
+        int pc_phase = 3;
         if (LENS && c_step == best) {
+            if (PSTATS) pc_phase = 0;
             // ================================ STEP ================================
             // A lane keeps its flight in registers while it flies.  Lanes whose flight left the FLY state
             // (a chord to intersect, an escape, a capture) write it back and take another one from the
@@ -221,6 +233,7 @@ BT_DEV void render_pool_body(const RenderParams& p) {
             }
             __syncwarp();
         } else if (c_scan == best) {
+            if (PSTATS) pc_phase = 1;
             // ================================ SCAN ================================
             const uint32_t n = min(pool_collect(pl, W, w0, ST_PEND, ST_PEND_STRAIGHT, lane), 32u);
             bool to_fly = false, resolved = false;
@@ -280,6 +293,7 @@ BT_DEV void render_pool_body(const RenderParams& p) {
             }
             __syncwarp();
         } else if (c_shade == best) {
+            if (PSTATS) pc_phase = 2;
             // ================================ SHADE ===============================
             const uint32_t n = min(pool_collect(pl, W, w0, ST_HIT, ST_HIT_STRAIGHT, lane), 32u);
             bool to_fly = false, to_pend = false, finished = false;
@@ -478,10 +492,14 @@ BT_DEV void render_pool_body(const RenderParams& p) {
             regen_futile = n_ret == 0 && take == 0;  // nothing to do here until a path finishes (SHADE clears it)
             __syncwarp();
         }
+        if (PSTATS) pc[pc_phase] += clock64() - pc_in;
     }
     if (PSTATS) {
         ps[11] = turn;
-        if (lane == 0)
+        pc[4] = clock64() - pc_t0;
+        if (lane == 0) {
             for (int i = 0; i < 12; ++i) atomicAdd(p.stats + i, (unsigned long long)ps[i]);
+            for (int i = 0; i < 5; ++i) atomicAdd(p.stats + 12 + i, (unsigned long long)pc[i]);
+        }
     }
 }

@@ -205,12 +205,13 @@ int bt_render_stats(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, con
 
 /* Scheduling counters of the pooled render kernel for the same call (an instrumented copy, never timed):
  * stats_out = {STEP iterations, flying lanes summed over them, refill rounds, STEP entries, SCAN passes,
- * slots scanned, SHADE passes, slots shaded, REGEN passes, paths issued, paths retired, turns} summed over
- * all warps -- lanes per pass = slots / passes.  BT_ERR_UNSUPPORTED when pool_w = 0 or the scene runs a
+ * slots scanned, SHADE passes, slots shaded, REGEN passes, paths issued, paths retired, turns, SM clocks the
+ * warps spent in STEP, SCAN, SHADE, REGEN, SM clocks of the warps' whole lives} summed over all warps -- lanes
+ * per pass = slots / passes.  BT_ERR_UNSUPPORTED when pool_w = 0 or the scene runs a
  * generic (not content-specialised) kernel. */
 int bt_render_pool_stats(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_config* config,
                          const bt_render_config* render_config, uint64_t seed, uint64_t sample_base,
-                         uint32_t width, uint32_t height, uint64_t stats_out[12]);
+                         uint32_t width, uint32_t height, uint64_t stats_out[17]);
 
 /* Buffer::preview, reference src/tracer/buffer.rs:117-138 (+ ColorSpace::convert_linear :19-30,
  * linear_to_srgb / f32_to_u8 src/color.rs:14-24).  rgba8 lives where rgba32f lives. */

@@ -12,11 +12,14 @@ sys.path.insert(0, ROOT)
 import bendy_tracer_b200 as bt  # noqa: E402
 from bench import SCENE_DIR, WORKLOADS  # noqa: E402
 
+full = "--full" in sys.argv
+sys.argv = [a for a in sys.argv if a != "--full"]
 name = sys.argv[1] if len(sys.argv) > 1 else "C3"
 passes = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 knobs = dict(kv.split("=") for kv in sys.argv[3:])
 scene_name, w, h, _, sub, lens = WORKLOADS[name]
-w, h = min(w, 1920), min(h, 1080)
+if not full:
+    w, h = min(w, 1920), min(h, 1080)
 scene = bt.Scene.load(os.path.join(SCENE_DIR, scene_name + ".json.gz"))
 cam = scene.find_by_tag("camera")
 scene.set_camera_aspect(cam, float(np.float32(w) / np.float32(h)))

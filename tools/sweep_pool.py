@@ -48,11 +48,11 @@ if __name__ == "__main__":
     names = sys.argv[1:] or ["C3", "C2", "C4-cloud"]
     for name in names:
         print(f"{name}: lane kernel (pool_w=0) {measure(name, pool_w=0):9.1f} Msamples/s", flush=True)
-        for w, threads in itertools.product((2, 3, 4), (64, 128, 192)):
+        for w, threads in itertools.product((2, 3, 4, 5), (64, 128)):
             try:
                 print(f"{name}: pool_w={w} threads={threads:3d} {measure(name, pool_w=w, pool_threads=threads):9.1f}", flush=True)
             except Exception as e:   # the pool does not fit shared memory
                 print(f"{name}: pool_w={w} threads={threads}: {e}", flush=True)
         if WORKLOADS[name][5]:
-            for refill, smin in itertools.product((2, 3, 4, 6, 8), (16, 24)):
-                print(f"{name}: pool_w=3 refill={refill:2d} step_min={smin} {measure(name, pool_w=3, pool_refill=refill, pool_step_min=smin):9.1f}", flush=True)
+            for w, refill, smin in itertools.product((3, 4), (3, 6, 9), (24, 28, 32)):
+                print(f"{name}: pool_w={w} refill={refill:2d} step_min={smin} {measure(name, pool_w=w, pool_refill=refill, pool_step_min=smin):9.1f}", flush=True)
