@@ -39,7 +39,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 // engine is created (BT_<NAME>), and settable per engine with bt_engine_set_tuning; -1 = the built-in default.
 struct Tuning {
     int64_t compact_lanes = -1, compact_patience = -1, regen_lanes = -1, regen_patience = -1, scan_lanes = -1, scan_patience = -1;
-    int64_t steps_per_turn = -1, lens_no_skip = -1, lens_bound_all = -1, host_bands = -1, wide_ctas = -1;
+    int64_t steps_per_turn = -1, lens_no_skip = -1, lens_dist_grid = -1, host_bands = -1;
     int64_t pool_w = -1, pool_refill = -1, pool_step_min = -1, pool_threads = -1;
 };
 struct TuningName {
@@ -50,8 +50,8 @@ static const TuningName kTuning[] = {
     {"compact_lanes", &Tuning::compact_lanes}, {"compact_patience", &Tuning::compact_patience},
     {"regen_lanes", &Tuning::regen_lanes},     {"regen_patience", &Tuning::regen_patience},
     {"scan_lanes", &Tuning::scan_lanes},       {"scan_patience", &Tuning::scan_patience},
-    {"steps_per_turn", &Tuning::steps_per_turn}, {"lens_no_skip", &Tuning::lens_no_skip}, {"lens_bound_all", &Tuning::lens_bound_all},
-    {"host_bands", &Tuning::host_bands},       {"wide_ctas", &Tuning::wide_ctas},
+    {"steps_per_turn", &Tuning::steps_per_turn}, {"lens_no_skip", &Tuning::lens_no_skip}, {"lens_dist_grid", &Tuning::lens_dist_grid},
+    {"host_bands", &Tuning::host_bands},
     {"pool_w", &Tuning::pool_w},               {"pool_refill", &Tuning::pool_refill},
     {"pool_step_min", &Tuning::pool_step_min}, {"pool_threads", &Tuning::pool_threads},
 };
@@ -96,6 +96,8 @@ struct bt_scene {
     size_t blob_cap;
     float* d_grids;
     size_t grids_cap;
+    uint8_t* d_dist;    // free-distance grid (FlatScene::dist)
+    size_t dist_cap;
 };
 
 // Which arithmetic flavour of the kernels renders this scene.  AUTO: volumetric scenes are chaotic
@@ -145,6 +147,15 @@ int refresh_scene(bt_scene* s, cudaStream_t stream) {
         }
         CK(cudaMemcpyAsync(s->d_blob, s->flat.blob.data(), bb, cudaMemcpyHostToDevice, stream));
         CK(cudaMemcpyAsync(s->d_grids, s->flat.grids.data(), gb, cudaMemcpyHostToDevice, stream));
+        const size_t db = s->flat.dist.size();
+        if (db > s->dist_cap) {
+            if (s->d_dist) cudaFree(s->d_dist);
+            s->d_dist = 0;
+            s->dist_cap = 0;
+            CK(cudaMalloc((void**)&s->d_dist, db));
+            s->dist_cap = db;
+        }
+        if (db) CK(cudaMemcpyAsync(s->d_dist, s->flat.dist.data(), db, cudaMemcpyHostToDevice, stream));
         CK(cudaStreamSynchronize(stream));  // the host vectors may change after we return
         s->device_dirty = false;
     }
@@ -190,6 +201,7 @@ int build_params(const bt_engine* en, bt_scene* s, uint64_t camera_ref, bool nee
     p.cam.sub_n = sub_n;
     p.blob = s->d_blob;
     p.grids = s->d_grids;
+    p.dist = s->d_dist;
     p.width = width;
     p.height = height;
     if (m.samples * p.sub_count > 0xffffffffULL) return fail(BT_ERR_INVALID_ARG, "samples * subpixel_count exceeds 2^32 per call");
@@ -222,11 +234,12 @@ int build_params(const bt_engine* en, bt_scene* s, uint64_t camera_ref, bool nee
     p.scan_lanes = knob(tn.scan_lanes, 8);      // (profiles/r1_sweep_nearest_sphere_bound.log: flat within 1 % from 6/2 to 8/4)
     p.scan_patience = knob(tn.scan_patience, 3);
     if (tn.lens_no_skip > 0) p.scene.lens_skip = 0;
-    if (tn.lens_bound_all > 0 && p.scene.lens_skip) p.scene.lens_skip = 2;
+    if (tn.lens_dist_grid == 0 && p.scene.lens_skip == 3) p.scene.lens_skip = 1;  // (A/B: the per-flight bookkeeping)
     p.steps_per_turn = std::max(1u, knob(tn.steps_per_turn, long_flights ? 3 : 2));
-    p.wide_ctas = knob(tn.wide_ctas, 0);
     // the pooled kernel (render_pool.cuh): 32 W path slots per warp; 0 = one path per lane (render_body)
-    p.pool_w = std::min(knob(tn.pool_w, 0), 8u);
+    // default: on for lens fields (long flights: C3 +8 %, cornell2 + lens +28 %, cloud + lens +5 % over the lane kernel), off for
+    // flat ones, whose scan -> shade ping-pong gains nothing from compaction and pays for the state traffic (C2 -25 %)
+    p.pool_w = std::min(knob(tn.pool_w, p.scene.n_lens != 0 ? 3 : 0), 8u);
     p.pool_refill = std::max(1u, knob(tn.pool_refill, 3));   // (gpurun_out/r2_sweep_pool_C3c.log: 3 / 32 best of {3, 6, 9} x {24, 28, 32})
     p.pool_step_min = knob(tn.pool_step_min, 32);
     p.pool_threads = knob(tn.pool_threads, 0) & ~31u;  // 0: the kernel's own CTA size (launch_pool)
@@ -355,7 +368,8 @@ int bt_scene_create_json(bt_engine* engine, const void* bytes, size_t n, bt_scen
     s->ev_use = 0;
     s->d_blob = 0;
     s->d_grids = 0;
-    s->blob_cap = s->grids_cap = 0;
+    s->d_dist = 0;
+    s->blob_cap = s->grids_cap = s->dist_cap = 0;
     try {
         s->accel = ACCEL_AUTO;
         s->precision = BT_PRECISION_AUTO;
@@ -399,6 +413,7 @@ void bt_scene_destroy(bt_scene* scene) {
     }
     if (scene->d_blob) cudaFree(scene->d_blob);
     if (scene->d_grids) cudaFree(scene->d_grids);
+    if (scene->d_dist) cudaFree(scene->d_dist);
     delete scene;
 }
 

@@ -110,6 +110,44 @@ BT_DEV void flight_reset(Flight& f) {
     f.h.prim = -1;
     f.h.face = 0;
 }
+// Lower bound on the distance from x to the nearest primitive surface, from the scene's free-distance grid
+// (SceneHeader::dist_*, built by scene.cpp: build_dist_grid) and the exact distance of its scene-spanning spheres.
+// One byte load.  It is split in two so that the load is ISSUED before the RK4 arithmetic of the step that needs it
+// and its value first TOUCHED after (grid_bound_finish): L2 latency then hides under ~150 instructions.
+struct GridFetch {
+    uint32_t raw;   // the cell's byte (inside the box)
+    float other;    // min(outside-the-box bound or +inf, the scene-spanning spheres' exact bounds)
+};
+BT_DEV GridFetch grid_bound_fetch(const RenderParams& p, const float4* prims, V3 x) {
+    const SceneHeader& s = p.scene;
+    // cell index: a negative coordinate converts to a negative int, i.e. a huge unsigned one
+    const uint32_t ix = (uint32_t)__float2int_rd((x.x - s.dist_lo[0]) * s.dist_inv_cell), iy = (uint32_t)__float2int_rd((x.y - s.dist_lo[1]) * s.dist_inv_cell),
+                   iz = (uint32_t)__float2int_rd((x.z - s.dist_lo[2]) * s.dist_inv_cell);
+    GridFetch g;
+    g.raw = 0xffffu;  // (x q: beyond every stored value -- the box does not bound this point, `other` does)
+    g.other = __int_as_float(0x7f800000);
+    if (ix < s.dist_nx && iy < s.dist_ny && iz < s.dist_nz) {
+        g.raw = __ldg(p.dist + ((iz * s.dist_ny + iy) * s.dist_nx + ix));
+    } else {  // outside the box: every gridded primitive lies dist_pad inside its faces; the scene-spanning spheres exactly
+        const float dx = fmaxf(fmaxf(s.dist_lo[0] - x.x, x.x - s.dist_hi[0]), 0.0f);
+        const float dy = fmaxf(fmaxf(s.dist_lo[1] - x.y, x.y - s.dist_hi[1]), 0.0f);
+        const float dz = fmaxf(fmaxf(s.dist_lo[2] - x.z, x.z - s.dist_hi[2]), 0.0f);
+        g.other = (sqrt_approx(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) + s.dist_pad) * 0.999f - 1e-3f;
+#pragma unroll 1
+        for (uint32_t i = 0; i < s.n_far; ++i) {  // (0 .. 2, uniform)
+            const float4* q = prims + s.far_prim[i] * PRIM_STRIDE;
+            const float4 q0 = q[0], q1 = q[1];
+            const V3 oc = x - v3(q0);
+            g.other = fminf(g.other, sphere_free_bound(q0, q1, fmaf(oc.z, oc.z, fmaf(oc.y, oc.y, oc.x * oc.x))));
+        }
+    }
+    return g;
+}
+// `late`: any value computed at the end of the step.  The byte is converted only after it (late != late is false for every
+// finite value; the compiler cannot know), which keeps ptxas from scheduling the first use of the load right behind it.
+BT_DEV float grid_bound_finish(const RenderParams& p, const GridFetch& g, float late) {
+    return fminf((float)(g.raw + (late != late ? 1u : 0u)) * p.scene.dist_q, g.other);
+}
 // STEP phase: one RK4 step of a bent ray.  A chord shorter than the free distance cannot touch
 // anything and is committed at once; otherwise it is left pending for the intersection phase.
 // The free distance decays with the distance flown, except for the sphere that bounded it at the
@@ -126,16 +164,15 @@ BT_DEV int geodesic_step(const RenderParams& p, const L& lens, const float4* pri
     if (far) return FL_PEND_FAR;
     const V3 x0 = x;
     float free = f.free;
-    if ((C & CT_SPHERES) && !(C & CT_RECTS) && p.scene.lens_skip == 2) {
-        // EXPERIMENT (tuning knob lens_bound_all): the exact bound of EVERY sphere at every step -- the floor of the
-        // number of intersection passes that any free-distance scheme can reach (not a production path: 13 instructions per sphere)
-        free = __int_as_float(0x7f800000);
-        for (int i = 0; i < (int)p.scene.n_prims; ++i) {
-            const float4* q = prims + i * PRIM_STRIDE;
-            const float4 q0 = q[0], q1 = q[1];
-            const V3 oc = x0 - v3(q0);
-            free = fminf(free, sphere_free_bound(q0, q1, fmaf(oc.z, oc.z, fmaf(oc.y, oc.y, oc.x * oc.x))));
-        }
+    GridFetch gf;
+    gf.raw = 0;
+    gf.other = 0.0f;
+    // Grid mode: the bound decays with the distance flown (f.free) and is re-read from the grid only when the coming chord
+    // (about as long as the last one, f.rest) could outrun it -- a byte gather by all 32 lanes at every step is 32 L1
+    // wavefronts per warp instruction and made the step L1-bound (C3: -6 %); a quarter of the lanes is not.
+    const bool grid = p.scene.lens_skip == 3, refresh = grid && free <= 1.4f * f.rest;
+    if (grid) {
+        if (refresh) gf = grid_bound_fetch(p, prims, x0);
     } else if ((C & CT_SPHERES) && f.near >= 0) {
         const float4* q = prims + f.near * PRIM_STRIDE;
         const float4 q0 = q[0], q1 = q[1];
@@ -145,9 +182,10 @@ BT_DEV int geodesic_step(const RenderParams& p, const L& lens, const float4* pri
     rk4_from_k1<EXACT>(lens, cache, x, v, k1, step_size(p.scene.kappa, p.scene.h_min, p.scene.h_max, rmin));
     float len;
     (void)normalize_fma<EXACT>(x - x0, &len);
+    if (refresh) free = fmaxf(free, grid_bound_finish(p, gf, len));
     if (len * 1.02f < free) {  // nothing within reach: the chord needs no intersection test
         f.free = free - len;
-        f.rest -= len;
+        f.rest = grid ? len : f.rest - len;
         f.travelled += len;
         f.steps++;
         return (f.travelled >= tmax || f.steps >= p.scene.max_steps) ? FL_ESCAPED : FL_FLY;
@@ -171,7 +209,7 @@ BT_DEV int geodesic_scan(const RenderParams& p, const SceneView& sc, V3 x, V3 v,
     bound.sphere = -1;
     if (BVH)
         f.h = bvh_closest<!EXACT>(sc.prims, sc.nodes, sc.stack, o, dir, cmin, cmax);
-    else if (p.scene.lens_skip)
+    else if (p.scene.lens_skip != 0 && p.scene.lens_skip != 3)
         f.h = scan_prims_t<true, C, !EXACT>(sc.prims, sc.bounds, sc.boxes, (int)p.scene.n_prims, o, dir, cmin, cmax, -1, &bound);
     else
         f.h = scan_prims_t<false, C, !EXACT>(sc.prims, nullptr, sc.boxes, (int)p.scene.n_prims, o, dir, cmin, cmax, -1, nullptr);
@@ -180,8 +218,8 @@ BT_DEV int geodesic_scan(const RenderParams& p, const SceneView& sc, V3 x, V3 v,
     if (far) return FL_ESCAPED;
     f.travelled += len;
     f.steps++;
-    f.free = bound.nearest - len;  // the bounds were taken at the chord's start
-    f.rest = bound.rest - len;
+    f.free = bound.nearest - len;  // the bounds were taken at the chord's start (grid mode: unknown, 0 -- the next step reads the grid)
+    f.rest = p.scene.lens_skip == 3 ? len : bound.rest - len;
     f.near = bound.sphere;
     return (f.travelled >= tmax || f.steps >= p.scene.max_steps) ? FL_ESCAPED : FL_FLY;
 }
@@ -661,7 +699,7 @@ BT_DEV void render_body(const RenderParams& p) {
 // them 96 registers (20 warps / SM) instead of 80 with spills (24 warps / SM).  The flat variants keep
 // the 85-register cap of (256, 3) and are launched with 128 threads as well (launch_render).
 template <bool LENS, bool EXACT, int NL, bool BVH, int C = CT_ALL>
-__global__ void __launch_bounds__(LENS ? 128 : 256, LENS ? 5 : 3) render_kernel(const __grid_constant__ RenderParams p) {
+__global__ void __launch_bounds__(128, LENS ? 5 : 7) render_kernel(const __grid_constant__ RenderParams p) {
     render_body<false, LENS, EXACT, NL, BVH, C>(p);
 }
 // the same kernel + work counters for bench.py's roofline accounting (never timed)
@@ -921,9 +959,9 @@ cudaError_t BT_SFX(launch_render)(const RenderParams& p, cudaStream_t stream, ui
         ++*launches;
         return e_;
     }
-    // 128-thread CTAs (16 x 8 pixels): at 72..78 registers seven of them fit an SM (28 warps) where three
-    // 256-thread CTAs gave 24 -- cornell2 +3.7 %; BT_WIDE_CTAS=1 keeps 256 threads for the flat kernels (A/B)
-    const bool small = !p.stats && (p.scene.n_lens != 0 || !p.wide_ctas);
+    // 128-thread CTAs (16 x 8 pixels): at <= 72 registers seven of them fit an SM (28 warps) where three
+    // 256-thread CTAs gave 24 -- cornell2 +3.7 % (the work-counter variant keeps 256 threads)
+    const bool small = !p.stats;
     const uint32_t rows = p.row_end - p.row0;
     dim3 grid((p.width + 15) / 16, small ? (rows + 7) / 8 : (rows + 15) / 16), block(small ? 128 : 256);
     size_t smem = render_smem_bytes(p, block.x);

@@ -89,7 +89,18 @@ struct SceneHeader {
     float kappa, h_min, h_max;
     uint32_t max_steps;
     uint32_t lens_exact;             // BT_LENS_EXACT_RSQRT
-    uint32_t lens_skip;              // 1: chords shorter than the free distance are not intersected (!BT_LENS_NO_SKIP)
+    uint32_t lens_skip;              // 0: every chord is intersected (BT_LENS_NO_SKIP); 1: chords shorter than the free distance are
+                                     // not, the distance tracked per flight (nearest sphere exactly, the rest decaying);
+                                     // 3: the same, the distance read from the grid below
+    // ---- free-distance grid (extension; lensed linear-scan scenes): dist[(z * ny + y) * nx + x] * dist_q is a lower bound on the
+    // distance from ANY point of the cell to the surface of ANY primitive, already reduced by the rounding margins of the hit
+    // tests.  The box spans every primitive but the `n_far` scene-spanning spheres listed in far_prim, with dist_pad to spare:
+    // outside it the bound is min(distance to the box + dist_pad, exact distance to those spheres).
+    float dist_lo[3], dist_hi[3];
+    float dist_inv_cell, dist_q, dist_pad;
+    uint32_t dist_nx, dist_ny, dist_nz;
+    uint32_t n_far;
+    int32_t far_prim[2];
 };
 
 struct CameraBlock {                 // reference src/tracer/mod.rs:244-267 hoisted per render call
@@ -109,6 +120,7 @@ struct RenderParams {
     CameraBlock cam;
     const float4* blob;
     const float* grids;
+    const uint8_t* dist;             // the free-distance grid (SceneHeader::dist_*), device memory
     float4* fb;
     uint32_t width, height;
     uint32_t paths_per_pixel;        // samples * subpixel_count of this call
@@ -132,7 +144,6 @@ struct RenderParams {
     char* pool_q;                    // the pooled kernel's path-state arena: pool_q_bytes per warp of its grid (device memory)
     uint64_t pool_q_cap;             // bytes available at pool_q (bounds the grid)
     uint32_t pool_stats;             // launch the pooled kernel's counter variant (bt_render_pool_stats): stats[0..11]
-    uint32_t wide_ctas;              // render_body, flat variants: 256-thread CTAs instead of 128 (A/B knob)
     unsigned long long* stats;       // render_kernel_stats only: {paths, scan calls, RK4 steps, events}
 };
 

@@ -444,6 +444,11 @@ inline float as_f(uint32_t u) {
     std::memcpy(&f, &u, 4);
     return f;
 }
+inline uint32_t as_u(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    return u;
+}
 
 }  // namespace
 
@@ -1032,6 +1037,108 @@ struct BvhBuild {
     }
 };
 
+// The free-distance grid of a lensed linear-scan scene (SceneHeader::dist_*).  A geodesic chord shorter than the distance
+// from its start to the nearest primitive surface cannot hit anything and is not intersected ("Geodesic
+// flights"); the grid makes that distance one byte load per RK4 step instead of per-flight bookkeeping that decays and is
+// refreshed by intersection passes.  Every cell stores a LOWER bound valid for all of its points: the distance from the
+// cell centre to the nearest primitive (spheres exactly, everything else through its world AABB), minus the cell's half
+// diagonal, minus the rounding margins of the hit tests (those of scan_prims_t<DIST>), rounded down to the quantum.
+// Spheres that span the scene (the r = 100 ground of the shipped scenes) would blow the box up: up to two of them are
+// left out of the BOX (the cells inside it account for them like for every other primitive) and evaluated exactly for
+// points outside it.  Returns false (the per-flight scheme stays) when there are
+// more, or nothing to put in a grid.
+bool build_dist_grid(const std::vector<float4>& prims, const std::vector<Bounds>& bounds, SceneHeader& h, std::vector<uint8_t>* out) {
+    const uint32_t n = h.n_prims;
+    if (n == 0 || bounds.size() < n) return false;
+    std::vector<float> size(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        float e = 0.0f;
+        for (int k = 0; k < 3; ++k) e = std::max(e, bounds[i].hi[k] - bounds[i].lo[k]);
+        size[i] = e;
+    }
+    std::vector<float> sorted(size);
+    std::sort(sorted.begin(), sorted.end());
+    const float median = sorted[n / 2];
+    std::vector<char> far(n, 0);
+    h.n_far = 0;
+    h.far_prim[0] = h.far_prim[1] = -1;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t type = as_u(prims[i * PRIM_STRIDE + 4].x) & 3u;
+        if (type == PRIM_SPHERE && n > 1 && size[i] > 16.0f * median) {
+            if (h.n_far == 2) return false;
+            far[i] = 1;
+            h.far_prim[h.n_far++] = (int32_t)i;
+        }
+    }
+    Bounds box = BvhBuild::empty();
+    uint32_t n_in = 0;
+    for (uint32_t i = 0; i < n; ++i)
+        if (!far[i]) {
+            BvhBuild::grow(box, bounds[i]);
+            ++n_in;
+        }
+    if (n_in == 0) return false;
+    float extent = 0.0f;
+    for (int k = 0; k < 3; ++k) extent = std::max(extent, box.hi[k] - box.lo[k]);
+    if (!(extent > 0.0f) || !std::isfinite(extent)) return false;
+    const float pad = std::max(0.1f * extent, 0.25f);
+    double volume = 1.0;
+    for (int k = 0; k < 3; ++k) {
+        box.lo[k] -= pad;
+        box.hi[k] += pad;
+        volume *= (double)(box.hi[k] - box.lo[k]);
+    }
+    // 2^21 cells at most, and at most 2^24 cell x primitive distance evaluations on the host
+    const double max_cells = std::min(2097152.0, 16777216.0 / (double)n);
+    const float cell = (float)std::cbrt(volume / max_cells) * 1.0001f;
+    uint32_t dims[3];
+    for (int k = 0; k < 3; ++k) dims[k] = std::max(1u, (uint32_t)std::ceil((box.hi[k] - box.lo[k]) / cell));
+    const float q = 0.5f * cell;
+    // a point is binned with float arithmetic and may land one ulp into the neighbouring cell: the half diagonal is padded
+    const double half_diag = 0.5 * std::sqrt(3.0) * (double)cell * 1.01 + 1e-5;
+    out->assign((size_t)dims[0] * dims[1] * dims[2], 0);
+    for (uint32_t z = 0; z < dims[2]; ++z)
+        for (uint32_t y = 0; y < dims[1]; ++y)
+            for (uint32_t x = 0; x < dims[0]; ++x) {
+                const double c[3] = {box.lo[0] + (x + 0.5) * (double)cell, box.lo[1] + (y + 0.5) * (double)cell, box.lo[2] + (z + 0.5) * (double)cell};
+                const double l1 = std::fabs(c[0]) + std::fabs(c[1]) + std::fabs(c[2]) + 3.0 * half_diag;
+                double best = 1e30;
+                for (uint32_t i = 0; i < n; ++i) {  // (the scene-spanning spheres too: they are only left out of the BOX)
+                    const float4* rec = &prims[i * PRIM_STRIDE];
+                    double b;
+                    if ((as_u(rec[4].x) & 3u) == PRIM_SPHERE) {
+                        const double dx = c[0] - rec[0].x, dy = c[1] - rec[0].y, dz = c[2] - rec[0].z, r = rec[0].w;
+                        const double dc = std::sqrt(dx * dx + dy * dy + dz * dz), dmax = dc + half_diag;
+                        // sphere_free_bound's margin at the farthest point of the cell (rec[1].z = 2e-5 / r)
+                        b = std::fabs(dc - r) - (dmax * dmax * (double)rec[1].z + 2e-5 * (dmax + r) + 1e-6);
+                    } else {
+                        double d2 = 0.0, ext = 0.0;
+                        for (int k = 0; k < 3; ++k) {
+                            const double d = std::max(std::max((double)bounds[i].lo[k] - c[k], c[k] - (double)bounds[i].hi[k]), 0.0);
+                            d2 += d * d;
+                            ext += std::fabs((double)bounds[i].hi[k] - (double)bounds[i].lo[k]);
+                        }
+                        // the margin of the rect / box bounds of scan_prims_t<DIST>
+                        b = std::sqrt(d2) - (1e-4 * (l1 + ext + std::sqrt(d2)) + 1e-4);
+                    }
+                    best = std::min(best, b);
+                }
+                const double v = std::floor((best - half_diag) / (double)q);
+                (*out)[((size_t)z * dims[1] + y) * dims[0] + x] = (uint8_t)std::min(std::max(v, 0.0), 255.0);
+            }
+    for (int k = 0; k < 3; ++k) {
+        h.dist_lo[k] = box.lo[k];
+        h.dist_hi[k] = box.lo[k] + (float)dims[k] * cell;
+    }
+    h.dist_inv_cell = 1.0f / cell;
+    h.dist_q = q;
+    h.dist_pad = pad;
+    h.dist_nx = dims[0];
+    h.dist_ny = dims[1];
+    h.dist_nz = dims[2];
+    return true;
+}
+
 }  // namespace
 
 FlatScene flatten(const Scene& scene, int accel) {
@@ -1305,6 +1412,7 @@ FlatScene flatten(const Scene& scene, int accel) {
             fs.blob.push_back(f4(bounds[i].lo[0], bounds[i].lo[1], bounds[i].lo[2], 0.0f));
             fs.blob.push_back(f4(bounds[i].hi[0], bounds[i].hi[1], bounds[i].hi[2], 0.0f));
         }
+        if (!std::getenv("BT_NO_DIST_GRID") && build_dist_grid(prims, bounds, h, &fs.dist)) h.lens_skip = 3;
     }
     h.bvh_off = (uint32_t)fs.blob.size();
     h.n_bvh = (uint32_t)(nodes.size() / BVH_STRIDE);

@@ -113,6 +113,7 @@ struct FlatScene {
     SceneHeader header;
     std::vector<float4> blob;
     std::vector<float> grids;
+    std::vector<uint8_t> dist;          // free-distance grid (SceneHeader::dist_*); empty unless header.lens_skip == 3
     std::vector<uint64_t> object_refs;  // object index -> ObjectRef
     std::vector<uint32_t> prim_order;   // record position -> canonical primitive index (identity without a BVH)
     bool diffuse_without_light;         // a Diffuse material is reachable but no LIGHT exists

@@ -14,7 +14,7 @@ from bench import SCENE_DIR, WORKLOADS  # noqa: E402
 
 eng = bt.Engine.default(0)
 jobs = []
-for name, passes in (("C3", 2), ("C2", 8), ("C4-cloud", 8)):
+for name, passes in (("C3", 4), ("C2", 8), ("C4-cloud", 8)):
     scene_name, w, h, _, sub, lens = WORKLOADS[name]
     w, h = 1920, 1080
     scene = bt.Scene.load(os.path.join(SCENE_DIR, scene_name + ".json.gz"))
