@@ -48,6 +48,8 @@ class BtSceneInfo(C.Structure):
 _P = C.c_void_p
 SIGNATURES = {
     "bt_engine_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "bt_engine_create_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    "bt_engine_device_count": (C.c_int, [_P]),
     "bt_engine_destroy": (None, [_P]),
     "bt_engine_launch_count": (C.c_uint64, [_P]),
     "bt_engine_set_tuning": (C.c_int, [_P, C.c_char_p, C.c_int64]),

@@ -140,11 +140,20 @@ class Engine:
     _default = {}
     _lock = threading.Lock()
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
+        """`devices=[0, 1, ...]`: one engine over several GPUs of the box (bt_engine_create_multi): every render call
+        splits its passes across them and sums the slices on devices[0], where device buffers must live"""
         h = C.c_void_p()
-        check(lib.bt_engine_create(int(device), C.byref(h)))
+        if devices is not None:
+            devices = [int(d) for d in devices]
+            arr = (C.c_int * len(devices))(*devices)
+            check(lib.bt_engine_create_multi(arr, len(devices), C.byref(h)))
+            device = devices[0]
+        else:
+            check(lib.bt_engine_create(int(device), C.byref(h)))
         self.handle = h
         self.device = int(device)
+        self.devices = devices or [self.device]
 
     @classmethod
     def default(cls, device=0):

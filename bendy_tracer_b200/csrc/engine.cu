@@ -77,27 +77,40 @@ struct bt_engine {
     size_t pool_q_cap[2];
     int sm_count;
     int clock_khz;
+    // ---- multi-device engine (bt_engine_create_multi): this engine is device 0 and owns the others ----
+    std::vector<bt_engine*> peers;     // devices 1 .. n-1 (each a complete engine: stream, scratch frame, arenas)
+    std::vector<char> peer_direct;     // its slice is readable from device 0 through a peer mapping (or lives on device 0)
+    cudaEvent_t ev_slice;              // (on a peer) its slice of the frame is rendered
+    cudaEvent_t ev_reduced;            // (on device 0) the last framebuffer reduce has read the peers' slices
+    float4* d_stage;                   // (on device 0) staging frame for peers without a peer mapping
+    size_t stage_cap;
 };
 
 struct bt_scene;
 static bool use_exact(const bt_engine* e, const bt_scene* s);
 
-struct bt_scene {
-    bt_engine* engine;  // identity of the engine the scene is bound to (compared, never dereferenced: the engine may die first)
-    int device;         // that engine's CUDA device (-1: not bound yet)
-    cudaEvent_t ev_use; // recorded after every kernel that reads d_blob / d_grids: a re-upload waits for it
-    Scene scene;
-    FlatScene flat;
-    int accel;          // ACCEL_AUTO / ACCEL_LINEAR / ACCEL_BVH
-    int precision;      // BT_PRECISION_AUTO / _FAST / _EXACT
-    bool flat_dirty;    // host flattening out of date
-    bool device_dirty;  // device copy out of date
+// the device copy of a scene on one GPU (a multi-device engine keeps one per device)
+struct SceneDev {
+    int device;
+    uint64_t version;   // FlatScene version this copy holds (0: none)
+    cudaEvent_t ev_use; // recorded after every kernel that reads the copy: a re-upload waits for it
     float4* d_blob;
     size_t blob_cap;
     float* d_grids;
     size_t grids_cap;
     uint8_t* d_dist;    // free-distance grid (FlatScene::dist)
     size_t dist_cap;
+};
+
+struct bt_scene {
+    bt_engine* engine;  // identity of the engine the scene is bound to (compared, never dereferenced: the engine may die first)
+    Scene scene;
+    FlatScene flat;
+    uint64_t flat_version;  // bumped by every re-flatten
+    int accel;          // ACCEL_AUTO / ACCEL_LINEAR / ACCEL_BVH
+    int precision;      // BT_PRECISION_AUTO / _FAST / _EXACT
+    bool flat_dirty;    // host flattening out of date
+    std::vector<SceneDev> devs;
 };
 
 // Which arithmetic flavour of the kernels renders this scene.  AUTO: volumetric scenes are chaotic
@@ -121,44 +134,56 @@ int ensure_scratch(bt_engine* e, size_t bytes) {
     return BT_OK;
 }
 
-int refresh_scene(bt_scene* s, cudaStream_t stream) {
+// Brings the scene's copy on the CURRENT device (cudaSetDevice done by the caller) up to date; *out = that copy.
+int refresh_scene(bt_scene* s, int device, cudaStream_t stream, SceneDev** out) {
     if (s->flat_dirty) {
         s->flat = flatten(s->scene, s->accel);
         s->flat_dirty = false;
-        s->device_dirty = true;
+        ++s->flat_version;
     }
-    if (s->device_dirty) {
+    SceneDev* d = 0;
+    for (SceneDev& c : s->devs)
+        if (c.device == device) d = &c;
+    if (!d) {
+        SceneDev c;
+        std::memset(&c, 0, sizeof c);
+        c.device = device;
+        s->devs.push_back(c);
+        d = &s->devs.back();
+    }
+    if (d->version != s->flat_version) {
         // a render enqueued without synchronising (bt_render_async) may still be reading the old copy
-        if (s->ev_use) CK(cudaEventSynchronize(s->ev_use));
+        if (d->ev_use) CK(cudaEventSynchronize(d->ev_use));
         size_t bb = s->flat.blob.size() * sizeof(float4), gb = s->flat.grids.size() * sizeof(float);
-        if (bb > s->blob_cap) {
-            if (s->d_blob) cudaFree(s->d_blob);
-            s->d_blob = 0;
-            s->blob_cap = 0;
-            CK(cudaMalloc((void**)&s->d_blob, bb));
-            s->blob_cap = bb;
+        if (bb > d->blob_cap) {
+            if (d->d_blob) cudaFree(d->d_blob);
+            d->d_blob = 0;
+            d->blob_cap = 0;
+            CK(cudaMalloc((void**)&d->d_blob, bb));
+            d->blob_cap = bb;
         }
-        if (gb > s->grids_cap) {
-            if (s->d_grids) cudaFree(s->d_grids);
-            s->d_grids = 0;
-            s->grids_cap = 0;
-            CK(cudaMalloc((void**)&s->d_grids, gb));
-            s->grids_cap = gb;
+        if (gb > d->grids_cap) {
+            if (d->d_grids) cudaFree(d->d_grids);
+            d->d_grids = 0;
+            d->grids_cap = 0;
+            CK(cudaMalloc((void**)&d->d_grids, gb));
+            d->grids_cap = gb;
         }
-        CK(cudaMemcpyAsync(s->d_blob, s->flat.blob.data(), bb, cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(s->d_grids, s->flat.grids.data(), gb, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d->d_blob, s->flat.blob.data(), bb, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d->d_grids, s->flat.grids.data(), gb, cudaMemcpyHostToDevice, stream));
         const size_t db = s->flat.dist.size();
-        if (db > s->dist_cap) {
-            if (s->d_dist) cudaFree(s->d_dist);
-            s->d_dist = 0;
-            s->dist_cap = 0;
-            CK(cudaMalloc((void**)&s->d_dist, db));
-            s->dist_cap = db;
+        if (db > d->dist_cap) {
+            if (d->d_dist) cudaFree(d->d_dist);
+            d->d_dist = 0;
+            d->dist_cap = 0;
+            CK(cudaMalloc((void**)&d->d_dist, db));
+            d->dist_cap = db;
         }
-        if (db) CK(cudaMemcpyAsync(s->d_dist, s->flat.dist.data(), db, cudaMemcpyHostToDevice, stream));
+        if (db) CK(cudaMemcpyAsync(d->d_dist, s->flat.dist.data(), db, cudaMemcpyHostToDevice, stream));
         CK(cudaStreamSynchronize(stream));  // the host vectors may change after we return
-        s->device_dirty = false;
+        d->version = s->flat_version;
     }
+    *out = d;
     return BT_OK;
 }
 
@@ -187,7 +212,7 @@ uint32_t clamp_u32(uint64_t v) { return v > 0xfffffffeULL ? 0xfffffffeu : (uint3
 
 uint32_t knob(int64_t v, uint32_t dflt) { return v < 0 ? dflt : (uint32_t)v; }
 
-int build_params(const bt_engine* en, bt_scene* s, uint64_t camera_ref, bool need_camera, const bt_config* config,
+int build_params(const bt_engine* en, bt_scene* s, const SceneDev* dev, uint64_t camera_ref, bool need_camera, const bt_config* config,
                  const bt_render_config* rc, uint64_t seed, uint64_t sample_base, uint32_t width, uint32_t height, RenderParams* out) {
     const Tuning& tn = en->tune;
     Merged m = merge(*config, *rc);
@@ -199,9 +224,9 @@ int build_params(const bt_engine* en, bt_scene* s, uint64_t camera_ref, bool nee
     p.sub_count = sub_n * sub_n;
     if (need_camera) p.cam = make_camera_block(s->scene, camera_ref, width, height, m.subsample);
     p.cam.sub_n = sub_n;
-    p.blob = s->d_blob;
-    p.grids = s->d_grids;
-    p.dist = s->d_dist;
+    p.blob = dev->d_blob;
+    p.grids = dev->d_grids;
+    p.dist = dev->d_dist;
     p.width = width;
     p.height = height;
     if (m.samples * p.sub_count > 0xffffffffULL) return fail(BT_ERR_INVALID_ARG, "samples * subpixel_count exceeds 2^32 per call");
@@ -251,17 +276,14 @@ int build_params(const bt_engine* en, bt_scene* s, uint64_t camera_ref, bool nee
 
 // a scene created without an engine binds to the first engine that uses it
 int bind_scene(bt_engine* engine, bt_scene* scene) {
-    if (!scene->engine) {
-        scene->engine = engine;
-        scene->device = engine->device;
-    }
+    if (!scene->engine) scene->engine = engine;
     if (scene->engine != engine) return fail(BT_ERR_INVALID_ARG, "scene belongs to another engine");
     return BT_OK;
 }
 // every kernel that reads the scene's device copy is followed by this (refresh_scene / bt_scene_destroy wait for it)
-int mark_scene_use(bt_scene* s, cudaStream_t stream) {
-    if (!s->ev_use) CK(cudaEventCreateWithFlags(&s->ev_use, cudaEventDisableTiming));
-    CK(cudaEventRecord(s->ev_use, stream));
+int mark_scene_use(SceneDev* d, cudaStream_t stream) {
+    if (!d->ev_use) CK(cudaEventCreateWithFlags(&d->ev_use, cudaEventDisableTiming));
+    CK(cudaEventRecord(d->ev_use, stream));
     return BT_OK;
 }
 
@@ -314,6 +336,9 @@ int bt_engine_create(int device, bt_engine** out) {
     en->ev_lens = 0;
     en->d_pool_q[0] = en->d_pool_q[1] = 0;
     en->pool_q_cap[0] = en->pool_q_cap[1] = 0;
+    en->ev_slice = en->ev_reduced = 0;
+    en->d_stage = 0;
+    en->stage_cap = 0;
     en->sm_count = prop.multiProcessorCount;
     int khz = 0;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
@@ -334,7 +359,11 @@ int bt_engine_create(int device, bt_engine** out) {
 
 void bt_engine_destroy(bt_engine* engine) {
     if (!engine) return;
+    for (bt_engine* peer : engine->peers) bt_engine_destroy(peer);
     cudaSetDevice(engine->device);
+    if (engine->ev_slice) cudaEventDestroy(engine->ev_slice);
+    if (engine->ev_reduced) cudaEventDestroy(engine->ev_reduced);
+    if (engine->d_stage) cudaFree(engine->d_stage);
     if (engine->d_scratch) cudaFree(engine->d_scratch);
     if (engine->d_lens) cudaFree(engine->d_lens);
     for (int i = 0; i < 2; ++i)
@@ -347,13 +376,67 @@ void bt_engine_destroy(bt_engine* engine) {
     delete engine;
 }
 
-uint64_t bt_engine_launch_count(const bt_engine* engine) { return engine ? engine->launches : 0; }
+uint64_t bt_engine_launch_count(const bt_engine* engine) {
+    if (!engine) return 0;
+    uint64_t n = engine->launches;
+    for (const bt_engine* peer : engine->peers) n += peer->launches;
+    return n;
+}
+
+int bt_engine_create_multi(const int* devices, int n_devices, bt_engine** out) {
+    if (!devices || !out || n_devices < 1) return fail(BT_ERR_INVALID_ARG, "need at least one device");
+    if (n_devices > MAX_PEER_FRAMES + 1) return fail(BT_ERR_INVALID_ARG, "too many devices");
+    bt_engine* head = 0;
+    int r = bt_engine_create(devices[0], &head);
+    if (r != BT_OK) return r;
+    for (int i = 1; i < n_devices; ++i) {
+        bt_engine* peer = 0;
+        if ((r = bt_engine_create(devices[i], &peer)) != BT_OK) {
+            bt_engine_destroy(head);
+            return r;
+        }
+        head->peers.push_back(peer);
+        cudaError_t e = cudaEventCreateWithFlags(&peer->ev_slice, cudaEventDisableTiming);
+        int can = devices[i] == devices[0];
+        if (e == cudaSuccess && !can) {
+            // read the peer's slice in place over NVLink where the topology allows it
+            if (cudaDeviceCanAccessPeer(&can, devices[0], devices[i]) != cudaSuccess) can = 0;
+            if (can) {
+                cudaSetDevice(devices[0]);
+                cudaError_t pe = cudaDeviceEnablePeerAccess(devices[i], 0);
+                if (pe == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+                else if (pe != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    can = 0;
+                }
+            }
+        }
+        head->peer_direct.push_back((char)can);
+        if (e != cudaSuccess) {
+            bt_engine_destroy(head);
+            return cuda_fail(e, "cudaEventCreate");
+        }
+    }
+    cudaSetDevice(devices[0]);
+    if (!head->peers.empty()) {
+        cudaError_t e = cudaEventCreateWithFlags(&head->ev_reduced, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            bt_engine_destroy(head);
+            return cuda_fail(e, "cudaEventCreate");
+        }
+    }
+    *out = head;
+    return BT_OK;
+}
+
+int bt_engine_device_count(const bt_engine* engine) { return engine ? 1 + (int)engine->peers.size() : 0; }
 
 int bt_engine_set_tuning(bt_engine* engine, const char* name, int64_t value) {
     if (!engine || !name) return fail(BT_ERR_INVALID_ARG, "NULL argument");
     for (const TuningName& t : kTuning)
         if (!std::strcmp(t.name, name)) {
             engine->tune.*(t.field) = value;
+            for (bt_engine* peer : engine->peers) peer->tune.*(t.field) = value;
             return BT_OK;
         }
     return fail(BT_ERR_INVALID_ARG, std::string("unknown tuning knob `") + name + "`");
@@ -364,12 +447,7 @@ int bt_scene_create_json(bt_engine* engine, const void* bytes, size_t n, bt_scen
     GUARD_BEGIN
     bt_scene* s = new bt_scene();
     s->engine = engine;
-    s->device = engine ? engine->device : -1;
-    s->ev_use = 0;
-    s->d_blob = 0;
-    s->d_grids = 0;
-    s->d_dist = 0;
-    s->blob_cap = s->grids_cap = s->dist_cap = 0;
+    s->flat_version = 1;
     try {
         s->accel = ACCEL_AUTO;
         s->precision = BT_PRECISION_AUTO;
@@ -382,7 +460,6 @@ int bt_scene_create_json(bt_engine* engine, const void* bytes, size_t n, bt_scen
         throw;
     }
     s->flat_dirty = false;
-    s->device_dirty = true;
     *out = s;
     return BT_OK;
     GUARD_END
@@ -406,14 +483,16 @@ void bt_free(void* p) { std::free(p); }
 
 void bt_scene_destroy(bt_scene* scene) {
     if (!scene) return;
-    if (scene->device >= 0) cudaSetDevice(scene->device);
-    if (scene->ev_use) {
-        cudaEventSynchronize(scene->ev_use);
-        cudaEventDestroy(scene->ev_use);
+    for (SceneDev& d : scene->devs) {
+        cudaSetDevice(d.device);
+        if (d.ev_use) {
+            cudaEventSynchronize(d.ev_use);
+            cudaEventDestroy(d.ev_use);
+        }
+        if (d.d_blob) cudaFree(d.d_blob);
+        if (d.d_grids) cudaFree(d.d_grids);
+        if (d.d_dist) cudaFree(d.d_dist);
     }
-    if (scene->d_blob) cudaFree(scene->d_blob);
-    if (scene->d_grids) cudaFree(scene->d_grids);
-    if (scene->d_dist) cudaFree(scene->d_dist);
     delete scene;
 }
 
@@ -556,18 +635,83 @@ int ensure_pool_arena(bt_engine* e, int lane, RenderParams* p) {
 int render_rows(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_config* config, const bt_render_config* rc,
                 uint64_t seed, uint64_t sample_base, float* fb, uint32_t width, uint32_t height, uint32_t row0, uint32_t row_end,
                 cudaStream_t stream, int lane, uint32_t* sub_count_out) {
-    int rcode = refresh_scene(scene, stream);
+    SceneDev* sdev = 0;
+    int rcode = refresh_scene(scene, engine->device, stream, &sdev);
     if (rcode != BT_OK) return rcode;
     if ((rcode = check_renderable(scene)) != BT_OK) return rcode;
     RenderParams p;
-    if ((rcode = build_params(engine, scene, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return rcode;
+    if ((rcode = build_params(engine, scene, sdev, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return rcode;
     p.fb = (float4*)fb;
     p.row0 = row0;
     p.row_end = row_end;
     if ((rcode = ensure_pool_arena(engine, lane, &p)) != BT_OK) return rcode;
     CK(use_exact(engine, scene) ? launch_render_exact(p, stream, &engine->launches) : launch_render_fast(p, stream, &engine->launches));
-    if ((rcode = mark_scene_use(scene, stream)) != BT_OK) return rcode;
+    if ((rcode = mark_scene_use(sdev, stream)) != BT_OK) return rcode;
     if (sub_count_out) *sub_count_out = p.sub_count;
+    return BT_OK;
+}
+// Tracer::render on a multi-device engine.  The reference fans the tiles of one frame out over its thread pool INSIDE
+// render (mod.rs:190-197); here the frame's passes [sample_base, sample_base + samples) are cut into one contiguous slice
+// per device (samples are i.i.d. and the buffer is a running sum).  Device 0 adds its slice straight into the
+// caller's frame `fb` (device-0 memory) on `stream`; every other device renders its slice into a zeroed frame of its own on
+// its own stream, and one kernel on device 0 then adds those frames to `fb`, reading them in place over NVLink
+// (accumulate_frames_kernel).  One host thread drives all devices; the kernels of the different GPUs run concurrently.
+int render_multi(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_config* config, const bt_render_config* rc,
+                 uint64_t seed, uint64_t sample_base, float* fb, uint32_t width, uint32_t height, cudaStream_t stream,
+                 uint32_t* sub_count_out) {
+    const uint64_t n = 1 + engine->peers.size(), total = rc->samples;
+    const size_t bytes = (size_t)width * height * 4 * sizeof(float);
+    bt_render_config part = *rc;
+    PeerFrames direct;
+    direct.n = 0;
+    std::vector<size_t> staged;  // peers whose slice has to be copied to device 0 first
+    int r = BT_OK;
+    for (uint64_t g = 1; g < n && r == BT_OK; ++g) {
+        const uint64_t lo = total * g / n, hi = total * (g + 1) / n;
+        if (hi == lo) continue;
+        bt_engine* peer = engine->peers[g - 1];
+        CK(cudaSetDevice(peer->device));
+        if ((r = ensure_scratch(peer, bytes)) != BT_OK) break;
+        CK(cudaStreamWaitEvent(peer->stream, engine->ev_reduced, 0));  // the previous reduce is done with this frame
+        CK(cudaMemsetAsync(peer->d_scratch, 0, bytes, peer->stream));
+        part.samples = hi - lo;
+        r = render_rows(peer, scene, camera_ref, config, &part, seed, sample_base + lo, (float*)peer->d_scratch, width, height, 0, height,
+                        peer->stream, 0, nullptr);
+        if (r != BT_OK) break;
+        CK(cudaEventRecord(peer->ev_slice, peer->stream));
+        if (engine->peer_direct[g - 1]) direct.src[direct.n++] = (const float4*)peer->d_scratch;
+        else staged.push_back(g - 1);
+    }
+    CK(cudaSetDevice(engine->device));
+    if (r != BT_OK) return r;
+    part.samples = total / n;  // slice 0 = [0, total / n)
+    if (part.samples) {
+        if ((r = render_rows(engine, scene, camera_ref, config, &part, seed, sample_base, fb, width, height, 0, height, stream, 0,
+                             sub_count_out)) != BT_OK)
+            return r;
+    } else if (sub_count_out) {
+        *sub_count_out = rc->subsample == 0 ? 1u : rc->subsample * rc->subsample;
+    }
+    // ONE framebuffer reduce per call
+    for (uint64_t g = 1; g < n; ++g)
+        if (total * g / n != total * (g + 1) / n) CK(cudaStreamWaitEvent(stream, engine->peers[g - 1]->ev_slice, 0));
+    CK(launch_accumulate_frames((float4*)fb, direct, width * height, engine->sm_count, stream, &engine->launches));
+    for (size_t i : staged) {  // no peer mapping (not NVLink-connected): through a staging frame on device 0
+        bt_engine* peer = engine->peers[i];
+        if (bytes > engine->stage_cap) {
+            if (engine->d_stage) cudaFree(engine->d_stage);
+            engine->d_stage = 0;
+            engine->stage_cap = 0;
+            CK(cudaMalloc((void**)&engine->d_stage, bytes));
+            engine->stage_cap = bytes;
+        }
+        CK(cudaMemcpyPeerAsync(engine->d_stage, engine->device, peer->d_scratch, peer->device, bytes, stream));
+        PeerFrames one;
+        one.n = 1;
+        one.src[0] = engine->d_stage;
+        CK(launch_accumulate_frames((float4*)fb, one, width * height, engine->sm_count, stream, &engine->launches));
+    }
+    CK(cudaEventRecord(engine->ev_reduced, stream));
     return BT_OK;
 }
 int check_render_args(bt_engine* engine, bt_scene* scene, const bt_config* config, const bt_render_config* rc, const float* fb,
@@ -594,9 +738,12 @@ int bt_render_async(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, con
     CK(cudaSetDevice(engine->device));
     cudaStream_t stream = (cudaStream_t)cuda_stream;  // NULL is the CUDA default stream, taken literally
     uint32_t sub_count = 1;
-    if ((rcode = render_rows(engine, scene, camera_ref, config, rc, seed, sample_base, rgba32f_device, width, height, 0, height,
-                             stream, 0, &sub_count)) != BT_OK)
-        return rcode;
+    if (!engine->peers.empty())
+        rcode = render_multi(engine, scene, camera_ref, config, rc, seed, sample_base, rgba32f_device, width, height, stream, &sub_count);
+    else
+        rcode = render_rows(engine, scene, camera_ref, config, rc, seed, sample_base, rgba32f_device, width, height, 0, height, stream, 0,
+                            &sub_count);
+    if (rcode != BT_OK) return rcode;
     if (samples_inout) *samples_inout += rc->samples * sub_count;  // mod.rs:199
     *status = BT_STATUS_IN_PROGRESS;
     return BT_OK;
@@ -612,11 +759,12 @@ int bt_render_stats(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, con
     for (int i = 0; i < 4; ++i) stats_out[i] = 0;
     if (rc->samples == 0) return BT_OK;
     CK(cudaSetDevice(engine->device));
-    int rcode = refresh_scene(scene, engine->stream);
+    SceneDev* sdev = 0;
+    int rcode = refresh_scene(scene, engine->device, engine->stream, &sdev);
     if (rcode != BT_OK) return rcode;
     if ((rcode = check_renderable(scene)) != BT_OK) return rcode;
     RenderParams p;
-    if ((rcode = build_params(engine, scene, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return rcode;
+    if ((rcode = build_params(engine, scene, sdev, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return rcode;
     size_t fb_bytes = (size_t)width * height * 16;
     if ((rcode = ensure_scratch(engine, fb_bytes + 64)) != BT_OK) return rcode;
     CK(cudaMemsetAsync(engine->d_scratch, 0, fb_bytes + 64, engine->stream));
@@ -640,11 +788,12 @@ int bt_render_pool_stats(bt_engine* engine, bt_scene* scene, uint64_t camera_ref
     for (int i = 0; i < 17; ++i) stats_out[i] = 0;
     if (rc->samples == 0) return BT_OK;
     CK(cudaSetDevice(engine->device));
-    int rcode = refresh_scene(scene, engine->stream);
+    SceneDev* sdev = 0;
+    int rcode = refresh_scene(scene, engine->device, engine->stream, &sdev);
     if (rcode != BT_OK) return rcode;
     if ((rcode = check_renderable(scene)) != BT_OK) return rcode;
     RenderParams p;
-    if ((rcode = build_params(engine, scene, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return rcode;
+    if ((rcode = build_params(engine, scene, sdev, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return rcode;
     if (p.pool_w == 0) return fail(BT_ERR_UNSUPPORTED, "the pooled kernel is switched off (tuning knob pool_w = 0)");
     size_t fb_bytes = (size_t)width * height * 16;
     if ((rcode = ensure_scratch(engine, fb_bytes + 256)) != BT_OK) return rcode;
@@ -692,11 +841,25 @@ int bt_render(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, const bt_
     if (r != BT_OK) return r;
     const size_t row_bytes = (size_t)width * 4 * sizeof(float), bytes = row_bytes * height;
     if ((r = ensure_scratch(engine, bytes)) != BT_OK) return r;
+    if (!engine->peers.empty()) {
+        // multi-device engine: the caller's running sums go to device 0, every device adds its pass slice (render_multi:
+        // one reduce over NVLink), the summed frame comes back
+        uint32_t sub = 1;
+        CK(cudaMemcpyAsync(engine->d_scratch, rgba32f, bytes, cudaMemcpyHostToDevice, engine->stream));
+        r = render_multi(engine, scene, camera_ref, config, rc, seed, sample_base, (float*)engine->d_scratch, width, height, engine->stream, &sub);
+        if (r == BT_OK) CK(cudaMemcpyAsync(rgba32f, engine->d_scratch, bytes, cudaMemcpyDeviceToHost, engine->stream));
+        CK(cudaStreamSynchronize(engine->stream));
+        if (r != BT_OK) return r;
+        if (samples_inout) *samples_inout += rc->samples * sub;  // mod.rs:199
+        *status = BT_STATUS_IN_PROGRESS;
+        return BT_OK;
+    }
     uint32_t bands = (uint32_t)std::min<size_t>(8, std::max<size_t>(1, bytes / (8u << 20)));
     if (engine->tune.host_bands > 0) bands = (uint32_t)engine->tune.host_bands;
     uint32_t band_rows = ((height + bands - 1) / bands + 15u) & ~15u;  // whole 16-row CTAs
     // the scene's device copy is refreshed on the first stream; the second one waits for it
-    if ((r = refresh_scene(scene, engine->stream)) != BT_OK) return r;
+    SceneDev* sdev0 = 0;
+    if ((r = refresh_scene(scene, engine->device, engine->stream, &sdev0)) != BT_OK) return r;
     CK(cudaEventRecord(engine->ev_fork, engine->stream));
     CK(cudaStreamWaitEvent(engine->stream2, engine->ev_fork, 0));
     uint32_t sub_count = 1;
@@ -756,14 +919,15 @@ int bt_trace_segments(bt_engine* engine, bt_scene* scene, const bt_config* confi
     GUARD_BEGIN
     if (int b = bind_scene(engine, scene)) return b;
     CK(cudaSetDevice(engine->device));
-    int r = refresh_scene(scene, engine->stream);
+    SceneDev* sdev = 0;
+    int r = refresh_scene(scene, engine->device, engine->stream, &sdev);
     if (r != BT_OK) return r;
     if ((r = check_renderable(scene)) != BT_OK && r != BT_ERR_SCENE) return r;
     bt_render_config rc;
     bt_render_config_default(&rc);
     rc.samples = 1;
     RenderParams p;
-    if ((r = build_params(engine, scene, 0, false, config, &rc, 0, 0, 1, 1, &p)) != BT_OK) return r;
+    if ((r = build_params(engine, scene, sdev, 0, false, config, &rc, 0, 0, 1, 1, &p)) != BT_OK) return r;
     size_t in_bytes = (size_t)n * 3 * sizeof(float), out_bytes = (size_t)n * sizeof(DeviceSegment);
     size_t off_d = (in_bytes + 255) & ~(size_t)255, off_o = 2 * off_d;
     if ((r = ensure_scratch(engine, off_o + out_bytes + 256)) != BT_OK) return r;
@@ -796,10 +960,11 @@ int bt_camera_rays(bt_engine* engine, bt_scene* scene, uint64_t camera_ref, cons
     GUARD_BEGIN
     if (int b = bind_scene(engine, scene)) return b;
     CK(cudaSetDevice(engine->device));
-    int r = refresh_scene(scene, engine->stream);
+    SceneDev* sdev = 0;
+    int r = refresh_scene(scene, engine->device, engine->stream, &sdev);
     if (r != BT_OK) return r;
     RenderParams p;
-    if ((r = build_params(engine, scene, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return r;
+    if ((r = build_params(engine, scene, sdev, camera_ref, true, config, rc, seed, sample_base, width, height, &p)) != BT_OK) return r;
     size_t b32 = ((size_t)n * 4 + 255) & ~(size_t)255, b64 = ((size_t)n * 8 + 255) & ~(size_t)255, bo = (size_t)n * 24;
     if ((r = ensure_scratch(engine, 2 * b32 + b64 + bo + 256)) != BT_OK) return r;
     char* base = (char*)engine->d_scratch;

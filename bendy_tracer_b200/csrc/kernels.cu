@@ -826,6 +826,24 @@ __global__ void resolve_kernel(const float4* __restrict__ fb, uint32_t n, float 
     out[i] = o;
 }
 
+// The framebuffer reduce of a multi-device render: dst.rgb += sum of the peers' slices (Buffer::write_color over
+// the slices rendered on the other GPUs; alpha untouched).  The peers' frames are read IN PLACE through peer
+// mappings (NVLink / NVSwitch loads, coalesced float4): the transfer and the sum are one kernel on the device that
+// owns the caller's frame, and no staging copy of W x H x 16 B per peer exists.
+__global__ void __launch_bounds__(256) accumulate_frames_kernel(float4* __restrict__ dst, const PeerFrames pf, uint32_t n_pixels) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pixels; i += gridDim.x * blockDim.x) {
+        float4 v = dst[i];
+#pragma unroll 1
+        for (int g = 0; g < pf.n; ++g) {
+            const float4 s = pf.src[g][i];
+            v.x += s.x;
+            v.y += s.y;
+            v.z += s.z;
+        }
+        dst[i] = v;
+    }
+}
+
 // FP32 peak probe: FP32_PEAK_CHAINS independent FMA chains per thread.
 __global__ void __launch_bounds__(FP32_PEAK_THREADS) fp32_peak_kernel(float* out, uint32_t iters) {
     float a[FP32_PEAK_CHAINS];
@@ -1046,6 +1064,14 @@ cudaError_t launch_resolve(const float4* fb, uint32_t n_pixels, uint64_t samples
     if (n_pixels == 0) return cudaSuccess;
     float samples_recip = 1.0f / (float)samples;  // buffer.rs:124
     resolve_kernel<<<(n_pixels + 255) / 256, 256, 0, stream>>>(fb, n_pixels, samples_recip, color_space, out);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_accumulate_frames(float4* dst, const PeerFrames& pf, uint32_t n_pixels, int sm_count, cudaStream_t stream, uint64_t* launches) {
+    if (n_pixels == 0 || pf.n == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)n_pixels + 255) / 256, (uint64_t)sm_count * 8);
+    accumulate_frames_kernel<<<blocks, 256, 0, stream>>>(dst, pf, n_pixels);
     ++*launches;
     return cudaGetLastError();
 }

@@ -44,6 +44,13 @@ BT_DECLARE_LAUNCHERS(_exact)
 cudaError_t launch_integrate(const IntegrateParams& p, cudaStream_t stream, uint64_t* launches);
 cudaError_t launch_resolve(const float4* fb, uint32_t n_pixels, uint64_t samples, int color_space, uchar4* out,
                            cudaStream_t stream, uint64_t* launches);
+// slices of a multi-device render, summed into the frame on the device that owns it (peer-mapped or local pointers)
+enum { MAX_PEER_FRAMES = 15 };
+struct PeerFrames {
+    const float4* src[MAX_PEER_FRAMES];
+    int n;
+};
+cudaError_t launch_accumulate_frames(float4* dst, const PeerFrames& pf, uint32_t n_pixels, int sm_count, cudaStream_t stream, uint64_t* launches);
 cudaError_t launch_fp32_peak(float* out, uint32_t iters, int blocks, cudaStream_t stream, uint64_t* launches);
 
 size_t render_smem_bytes(const RenderParams& p, unsigned threads = 256);

@@ -110,6 +110,16 @@ typedef struct {
 /* ---- engine ---------------------------------------------------------------------------- */
 /* Replaces Tracer::new / with_config's implicit "use the rayon global pool" (mod.rs:170-177,194). */
 int bt_engine_create(int device, bt_engine** out);
+/* One engine over n CUDA devices of this box: the counterpart of the rayon fan-out INSIDE Tracer::render (reference
+ * src/tracer/mod.rs:190-197), so that a caller of bt_render / bt_render_async uses 8 GPUs without changing a line.
+ * Every render call cuts its passes [sample_base, sample_base + samples) into one contiguous slice per device (the RNG
+ * is keyed by the global pass index: the union of the slices IS the one-device sample set); devices[0] owns the caller's
+ * frame (BT_MEM_DEVICE buffers live there) and adds its slice into it, the others render into frames of their own, and
+ * ONE kernel on devices[0] sums those in place over NVLink peer mappings (through a staging copy where the topology has
+ * none).  The image equals the one-device image up to f32 summation order.  One host thread drives all devices.  A device
+ * may be listed more than once (its kernels then share that GPU).  Probes, resolve and the stepper run on devices[0]. */
+int bt_engine_create_multi(const int* devices, int n_devices, bt_engine** out);
+int bt_engine_device_count(const bt_engine* engine);
 void bt_engine_destroy(bt_engine* engine);
 /* number of kernels this engine has launched since creation (bench.py's gpu_launches) */
 uint64_t bt_engine_launch_count(const bt_engine* engine);
