@@ -232,21 +232,27 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
-    name = args.workload or default_workload(world)
+    # `--gpus N` without torchrun: ONE process drives N GPUs through the multi-device engine of the C ABI
+    # (bt_engine_create_multi: the pass split and the peer-memory reduce happen inside bt_render)
+    in_process = world == 1 and args.gpus > 1
+    n_gpus = args.gpus if in_process else world
+    name = args.workload or default_workload(n_gpus)
     scene_name, w, h, passes, sub, lens = WORKLOADS[name]
-    d = describe(name, world)
+    d = describe(name, n_gpus)
     scene = bt.Scene.load(os.path.join(SCENE_DIR, scene_name + ".json.gz"))
     cam = scene.find_by_tag("camera")
     scene.set_camera_aspect(cam, float(np.float32(w) / np.float32(h)))
     if lens:
         scene.set_lenses(np.array([lens], np.float32))
-    engine = bt.Engine.default(local)
+    engine = bt.Engine(devices=list(range(args.gpus))) if in_process else bt.Engine.default(local)
     tracer = bt.Tracer(bt.Config(chunks_x=8, chunks_y=4), engine=engine, seed=0)
     strong = name in STRONG
-    if strong:
+    if strong and not in_process:
         if passes % world:
             raise SystemExit(f"{name}: {passes} passes do not split across {world} ranks")
         passes //= world                      # this rank's share of the frame's passes
+    if in_process and not strong:
+        passes *= n_gpus                      # weak scaling: every device renders a full pass slice; the engine splits the call
     rc = bt.RenderConfig.with_samples_subsample(passes, bt.Subsample(sub))
     frame = bt.Buffer(w, h, device=dev)       # this rank's slice of the frame
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -295,7 +301,7 @@ def main():
         t = torch.tensor([ms, reduce_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, reduce_ms = float(t[0].item()), float(t[1].item())
-    samples_per_step = w * h * d["spp"] * (1 if strong else world)
+    samples_per_step = w * h * d["spp"] * (1 if strong else n_gpus)
     value = samples_per_step * args.steps / (ms * 1e-3) / 1e6
 
     # ---- e2e: the same step with HOST buffers at N ranks -------------------------------------------
@@ -353,10 +359,10 @@ def main():
     exact = scene_name in ("cloud", "volume")     # bt_scene_set_precision AUTO: exact for volumetric scenes, fast otherwise
     pool_w = int(os.environ.get("BT_POOL_W", "-1"))
     result = {
-        "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": make_config(name, world),
+        "config": make_config(name, n_gpus),
         "gpu_launches": launches, "clocks": clocks, "wall_s": t_wall,
         "e2e": {"value": samples_per_step * n_e2e / te / 1e6, "unit": METRIC,
                 "h2d_bytes_per_step": w * h * 16, "d2h_bytes_per_step": w * h * 16, "steps": n_e2e,
@@ -369,7 +375,9 @@ def main():
                                 "fast flavour (f32; FMA contraction, MUFU rcp / sqrt / rsqrt within ~1 ulp; tested <= 1e-4 MAE on surface scenes)",
                   "stepper": "MUFU.RSQ (default; endpoints <= 1e-4 relative vs the f64 oracle)" if lens else None,
                   "kernel": "pool_w=%s (env BT_POOL_W; -1: engine default)" % pool_w,
-                  "primitives": info["n_primitives"], "lenses": info["n_lenses"]},
+                  "primitives": info["n_primitives"], "lenses": info["n_lenses"],
+                  "process_model": ("one process, %d GPUs through bt_engine_create_multi (pass slices + peer-memory reduce inside bt_render)" % n_gpus
+                                    if in_process else "one process per GPU (torch.distributed / NCCL)" if world > 1 else "one process, one GPU")},
     }
     if world > 1:
         result["reduce_ms"] = reduce_ms
@@ -388,7 +396,7 @@ def main():
         # above 4K are counted on their 3840x2160 version and scaled.
         cw, ch = (w, h) if w * h <= 3840 * 2160 else (3840, 2160)
         st = tracer.render_stats(scene, cam, rc, cw, ch, sample_base=args.warmup * world * passes)
-        scale = (w * h) / (cw * ch) * (world if strong else 1)     # the whole frame's work, all ranks
+        scale = (w * h) / (cw * ch) * (world if strong and not in_process else 1)     # the whole frame's work, all ranks
         st = {k_: v * scale for k_, v in st.items()}
         flops, fl_scan, fl_step = algorithmic_flops(st, scene_name, 1 if lens else 0)
         step_s = ms / args.steps * 1e-3
@@ -399,8 +407,8 @@ def main():
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_peak, hbm_src = (json.load(open(peaks_path))["hbm_gbs"], "measured") if os.path.exists(peaks_path) else (6650.0, "fallback")
         result["roofline"] = {
-            "bound": "fp32", "kernel": "render kernel (render_pool_kernel / render_kernel)", "unit": "TFLOP/s", "peak": peak * world,
-            "achieved": flops / step_s / 1e12, "frac": flops / step_s / 1e12 / (peak * world), "traffic": traffic,
+            "bound": "fp32", "kernel": "render kernel (render_pool_kernel / render_kernel)", "unit": "TFLOP/s", "peak": peak * n_gpus,
+            "achieved": flops / step_s / 1e12, "frac": flops / step_s / 1e12 / (peak * n_gpus), "traffic": traffic,
             "work": {**st, "segments_per_path": st["events"] / max(st["paths"], 1),
                      "flops_per_scan": fl_scan, "flops_per_rk4_step": fl_step},
             "note": "CUDA-core FP32 issue bound (no dense contraction on this path: neither the hbm nor the tensor "
@@ -415,7 +423,7 @@ def main():
             result["pool"] = tracer.render_pool_stats(scene, cam, bt.RenderConfig.with_samples_subsample(1, bt.Subsample(sub)), min(w, 1920), min(h, 1080))
         except bt.BendyError:
             result["pool"] = None
-    if rank == 0 and not args.no_extras and world == 1:
+    if rank == 0 and not args.no_extras and n_gpus == 1:
         # ---- the other shipped scenes / the synthetic lens (1 warm-up + 2 timed steps each) ----
         scenes = {}
         for other in ("C1", "C2", "C3", "C4-cloud", "C4-volume", "C4-cloud-lens"):

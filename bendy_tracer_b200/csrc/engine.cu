@@ -262,9 +262,9 @@ int build_params(const bt_engine* en, bt_scene* s, const SceneDev* dev, uint64_t
     if (tn.lens_dist_grid == 0 && p.scene.lens_skip == 3) p.scene.lens_skip = 1;  // (A/B: the per-flight bookkeeping)
     p.steps_per_turn = std::max(1u, knob(tn.steps_per_turn, long_flights ? 3 : 2));
     // the pooled kernel (render_pool.cuh): 32 W path slots per warp; 0 = one path per lane (render_body)
-    // default: on for lens fields (long flights: C3 +8 %, cornell2 + lens +28 %, cloud + lens +5 % over the lane kernel), off for
-    // flat ones, whose scan -> shade ping-pong gains nothing from compaction and pays for the state traffic (C2 -25 %)
-    p.pool_w = std::min(knob(tn.pool_w, p.scene.n_lens != 0 ? 3 : 0), 8u);
+    // default: on for lens fields (long flights: C3 +22 %, cornell2 + lens +60 %, cloud + lens +16 % over the lane kernel), off for
+    // flat ones, whose scan -> shade ping-pong gains nothing from compaction and pays for the state traffic (C2 -12 %)
+    p.pool_w = std::min(knob(tn.pool_w, p.scene.n_lens != 0 ? 4 : 0), 8u);
     p.pool_refill = std::max(1u, knob(tn.pool_refill, 3));   // (gpurun_out/r2_sweep_pool_C3c.log: 3 / 32 best of {3, 6, 9} x {24, 28, 32})
     p.pool_step_min = knob(tn.pool_step_min, 32);
     p.pool_threads = knob(tn.pool_threads, 0) & ~31u;  // 0: the kernel's own CTA size (launch_pool)
@@ -627,8 +627,9 @@ int ensure_pool_arena(bt_engine* e, int lane, RenderParams* p) {
         CK(cudaMalloc((void**)&e->d_pool_q[lane], bytes));
         e->pool_q_cap[lane] = bytes;
     }
-    p->pool_q = e->d_pool_q[lane];
-    p->pool_q_cap = e->pool_q_cap[lane];
+    p->pool_counter = (unsigned long long*)e->d_pool_q[lane];
+    p->pool_q = e->d_pool_q[lane] + 256;
+    p->pool_q_cap = e->pool_q_cap[lane] - 256;
     return BT_OK;
 }
 

@@ -873,7 +873,7 @@ cudaError_t ensure_smem(K kernel, size_t bytes) {
 
 #ifndef BT_EXACT_SCAN
 size_t render_pool_arena_bytes(uint32_t pool_w, int sm_count) {
-    return (size_t)sm_count * 8 /* CTAs per SM at most */ * 6 /* warps per CTA at most */ * pool_q_bytes(pool_w);
+    return 256 /* the tile counter */ + (size_t)sm_count * 8 /* CTAs per SM at most */ * 6 /* warps per CTA at most */ * pool_q_bytes(pool_w);
 }
 size_t render_smem_bytes(const RenderParams& p, unsigned threads) {
     return (size_t)p.scene.stage_f4 * sizeof(float4) + (p.scene.n_bvh ? (size_t)BVH_STACK * threads * 2 * sizeof(uint32_t) : 0);
@@ -920,7 +920,8 @@ cudaError_t launch_pool(K kernel, const RenderParams& p, bool lens, bool aov, cu
     const uint64_t tiles = (uint64_t)((p.width + 7) / 8) * ((p.row_end - p.row0 + 3) / 4);
     const uint64_t need = (tiles + warps - 1) / warps, fit = (uint64_t)per_sm * sms;
     const uint64_t room = p.pool_q_cap / (pool_q_bytes(p.pool_w) * warps);  // CTAs the path-state arena has room for
-    if (room < 1 || !p.pool_q) return cudaErrorMemoryAllocation;
+    if (room < 1 || !p.pool_q || !p.pool_counter) return cudaErrorMemoryAllocation;
+    if ((e = cudaMemsetAsync(p.pool_counter, 0, sizeof(unsigned long long), stream)) != cudaSuccess) return e;
     kernel<<<(unsigned)std::max<uint64_t>(1, std::min(std::min(need, fit), room)), threads, smem, stream>>>(p);
     return cudaGetLastError();
 }

@@ -19,9 +19,12 @@
 //
 // The next phase is the one with the most slots waiting (a ballot-compacted list in shared memory: the
 // "warp-shuffle ballot queues" of the north star), so every pass runs with a full or nearly full warp.
-// A lane is a PIXEL STREAM: it owns one pixel at a time (its sum lives in registers), walks the tiles
-// g, g + G, g + 2G, ... (g: this warp, G: warps in the grid) at its own pace and issues its pixel's
-// paths in the reference's order (pass-major, sub-pixel minor, mod.rs:277-278).  Paths finish out of
+// A lane is a PIXEL STREAM: it owns one pixel at a time (its sum lives in registers) -- pixel `lane` of the
+// warp's k-th 8 x 4 tile -- and issues its pixel's paths in the reference's order (pass-major, sub-pixel
+// minor, mod.rs:277-278).  The warps of the persistent grid draw their tiles from ONE global counter
+// (dynamic: a tile under the lens costs several times a tile of sky, and a static split left the slowest
+// warp 10 % behind the average); the lanes of a warp advance through the warp's tiles at their own pace,
+// at most POOL_TILES tiles apart.  Paths finish out of
 // order; a finished path keeps its slot (state DONE, contribution in place of the throughput) until the
 // pixel's earlier paths have been added, so the pixel sum is formed in exactly the order render_body
 // forms it: the two kernels give bit-identical images, whatever the scheduling.
@@ -34,6 +37,7 @@ enum {
     ST_HIT_STRAIGHT = 10
 };
 enum { POOL_RING = 16 };  // paths of one pixel in flight at most (in-order retirement window)
+enum { POOL_TILES = 8 };  // window of tiles a warp's lanes may be spread over
 
 struct Pool {
     // F, a flight:  fa = (x, travelled)  fb = (v, free)  fc = (rest, near, steps, h.t)  fd = (xp, h.prim | face)
@@ -43,6 +47,7 @@ struct Pool {
     float4* qc;                 //    (T, misc)   misc = ring index | latched << 4 | (vol_obj + 1) << 5 | bounce << 12 | volume bounce << 20
     float4 *qe, *qf;            //    AOV latches (albedo, depth) (normal, -)   [CT_AOV kernels]
     uint8_t *st, *list, *stack, *ring;
+    unsigned long long* tiles;  // the warp's window of tile indices: tile k of its stream is tiles[k % POOL_TILES]
 };
 // misc packs the counters of a path into 8 bits each: the pooled kernel serves max_bounces, max_volume_bounces <= POOL_MAX_BOUNCES
 // and scenes of up to 126 objects (launch_render falls back to render_body otherwise)
@@ -56,7 +61,7 @@ BT_DEV uint32_t pack_misc(uint32_t ring, bool latched, int vol_obj, uint32_t bou
 // pool_q_bytes per warp of the persistent grid): the shared memory it would take is worth two more CTAs per SM.
 __host__ __device__ inline size_t pool_warp_bytes(uint32_t w, bool lens) {
     const size_t P = 32u * w;
-    return P * (lens ? 64 : 32) + 3 * P + POOL_RING * 32;
+    return P * (lens ? 64 : 32) + POOL_TILES * 8 + 3 * P + POOL_RING * 32;
 }
 __host__ __device__ inline size_t pool_q_bytes(uint32_t w) { return (size_t)32u * w * 80; }
 template <bool LENS, bool AOV>
@@ -67,7 +72,8 @@ BT_DEV Pool pool_carve(char* base, char* qbase, uint32_t P) {
     pl.fb = f; f += P;
     pl.fc = pl.fd = f;
     if (LENS) { pl.fc = f; f += P; pl.fd = f; f += P; }
-    uint8_t* b = reinterpret_cast<uint8_t*>(f);
+    pl.tiles = reinterpret_cast<unsigned long long*>(f);
+    uint8_t* b = reinterpret_cast<uint8_t*>(pl.tiles + POOL_TILES);
     pl.st = b; b += P;
     pl.list = b; b += P;
     pl.stack = b; b += P;
@@ -126,9 +132,10 @@ BT_DEV void render_pool_body(const RenderParams& p) {
     for (uint32_t w = 0; w < W; ++w) pl.st[w * 32 + lane] = ST_IDLE;
     __syncwarp();
 
-    // ---- this lane's pixel stream: tile g + seq * G of the band, pixel (lane & 7, lane >> 3) of it ----------------
+    // ---- this lane's pixel stream: pixel (lane & 7, lane >> 3) of the warp's tile number `seq` ---------------------
     // (everything that is only needed when a pixel starts or ends is recomputed there: the STEP loop is short of registers)
-    uint32_t seq = 0;
+    uint32_t seq = 0;       // the next tile of the warp's stream this lane will work on
+    uint32_t fetched = 0;   // tiles the warp has drawn from the global counter so far (warp-uniform)
     bool have_pixel = false, exhausted = false;
     uint32_t px = 0, py = 0;
     V3 acc = v3(0.0f, 0.0f, 0.0f);
@@ -416,32 +423,47 @@ BT_DEV void render_pool_body(const RenderParams& p) {
             const uint32_t n_ret = __reduce_add_sync(0xffffffffu, r_cnt);
             n_done -= n_ret;
             n_free += n_ret;
-            // 2. the next pixel of this lane's stream
-            if (!have_pixel && !exhausted) {
-                const uint32_t warps_per_cta = blockDim.x >> 5;
-                const uint64_t g = (uint64_t)blockIdx.x * warps_per_cta + warp, G = (uint64_t)gridDim.x * warps_per_cta;
+            // 2. the next pixel of this lane's stream: pixel `lane` of the warp's tile number seq.  The warp draws tiles from
+            //    the grid-wide counter as its lanes reach them; a lane may run at most POOL_TILES tiles ahead of the slowest one.
+            {
                 const uint32_t tiles_x = (p.width + 7) / 8, tiles_y = (p.row_end - p.row0 + 3) / 4;
-                const uint64_t n_tiles = (uint64_t)tiles_x * tiles_y;
+                const unsigned long long n_tiles = (unsigned long long)tiles_x * tiles_y;
+#pragma unroll 1
                 for (;;) {
-                    const uint64_t t = g + (uint64_t)seq * G;
-                    if (t >= n_tiles) {
-                        exhausted = true;
-                        break;
+                    const uint32_t at = exhausted ? 0xffffffffu : (have_pixel ? seq - 1 : seq);
+                    const uint32_t lo = __reduce_min_sync(0xffffffffu, at);
+                    const bool want = !have_pixel && !exhausted && seq - lo < POOL_TILES;
+                    const uint32_t upto = __reduce_max_sync(0xffffffffu, want ? seq + 1 : 0u);
+                    if (upto == 0) break;  // nobody can take a pixel now
+                    while (fetched < upto) {
+                        if (lane == 0) pl.tiles[fetched % POOL_TILES] = atomicAdd(p.pool_counter, 1ULL);
+                        ++fetched;
                     }
-                    ++seq;
-                    const uint32_t ty = (uint32_t)(t / tiles_x), tx = (uint32_t)(t - (uint64_t)ty * tiles_x);
-                    px = tx * 8 + (lane & 7);
-                    py = p.row0 + ty * 4 + (lane >> 3);
-                    if (px < p.width && py < p.row_end) {
-                        acc = v3(0.0f, 0.0f, 0.0f);
-                        issued = retired = 0;
-                        sub_i = sub_j = 0;  // path_base is a multiple of sub_count: a call starts at sub-pixel (0, 0)
-                        have_pixel = true;
-                        break;
+                    __syncwarp();
+                    bool skipped = false;
+                    if (want) {
+                        const unsigned long long t = pl.tiles[seq % POOL_TILES];
+                        ++seq;
+                        if (t >= n_tiles) {
+                            exhausted = true;
+                        } else {
+                            const uint32_t ty = (uint32_t)(t / tiles_x), tx = (uint32_t)(t - (unsigned long long)ty * tiles_x);
+                            px = tx * 8 + (lane & 7);
+                            py = p.row0 + ty * 4 + (lane >> 3);
+                            if (px < p.width && py < p.row_end) {
+                                acc = v3(0.0f, 0.0f, 0.0f);
+                                issued = retired = 0;
+                                sub_i = sub_j = 0;  // path_base is a multiple of sub_count: a call starts at sub-pixel (0, 0)
+                                have_pixel = true;
+                            } else {
+                                skipped = true;  // a tile that hangs over the frame's edge: on to the next one
+                            }
+                        }
                     }
+                    __syncwarp();
+                    if (!__any_sync(0xffffffffu, skipped)) break;
                 }
             }
-            __syncwarp();
             // 3. start new camera paths in idle slots
             const bool can_issue = have_pixel && issued < p.paths_per_pixel && issued - retired < POOL_RING;
             const uint32_t rot = turn & 31u;
