@@ -4,6 +4,7 @@ import gzip
 import json
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -294,3 +295,75 @@ def test_bench_reference_arm_contract():
     assert "C1" in d["config"]["workload"]
     other = subprocess.run(cmd, capture_output=True, text=True, check=True, env={**os.environ, "RANK": "1"})
     assert other.stdout.strip() == ""
+
+
+def test_rust_sys_crate_matches_header():
+    """bendy-b200-sys/src/lib.rs declares every function of include/bendy_b200.h with the same arity and pointer
+    shape, every #[repr(C)] struct with the header's fields in the header's order, and every enum constant with its
+    value; build.rs compiles the same translation units as csrc/Makefile; the generated file is not stale."""
+    import re
+    import subprocess
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_rust_sys as G
+    opaque, structs, consts, funcs = G.parse_header()
+    rs = open(os.path.join(ROOT, "bendy-b200-sys", "src", "lib.rs")).read()
+    assert subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_rust_sys.py"), "--check"]).returncode == 0, "lib.rs is stale"
+    assert len(funcs) >= 30 and {"bt_config", "bt_render_config", "bt_lens_config", "bt_segment", "bt_scene_info"} <= set(structs)
+    for name, ret, params in funcs:
+        m = re.search(r"pub fn %s\((.*?)\)( -> ([^;]+))?;" % name, rs)
+        assert m, f"{name} missing from lib.rs"
+        args = [a for a in m.group(1).split(", ") if a]
+        assert len(args) == len(params), name
+        for (pname, ctype), a in zip(params, args):
+            rname, rtype = a.split(": ")
+            assert rname.replace("r#", "") == pname
+            assert rtype.count("*") == ctype.count("*"), (name, pname)
+            if "*" in ctype:
+                assert rtype.startswith("*const") == ctype.startswith("const"), (name, pname)
+        assert (m.group(3) is None) == (ret == "void"), name
+    for name, fields in structs.items():
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % name, rs, flags=re.S).group(1)
+        got = re.findall(r"pub (\w+): ([^,]+),", body)
+        assert [f for f, _ in got] == [f for f, _, _ in fields], name
+        for (f, ctype, arr), (_, rtype) in zip(fields, got):
+            assert rtype == (f"[{G.SCALARS[ctype]}; {arr}]" if arr else G.SCALARS[ctype]), (name, f)
+    for name, value in consts:
+        assert re.search(r"pub const %s: c_int = %d;" % (name, value), rs), name
+    for name in opaque:
+        assert f"pub struct {name} {{" in rs
+    # the ctypes binding and the Rust crate describe the same ABI: every header function is bound by both
+    from bendy_tracer_b200 import _ffi
+    assert {n for n, _, _ in funcs} == set(_ffi.SIGNATURES)
+    build_rs = open(os.path.join(ROOT, "bendy-b200-sys", "build.rs")).read()
+    for unit in ("engine.cu", "kernels.cu", "scene.cpp", "-DBT_EXACT_SCAN", "compute_100a"):
+        assert unit in build_rs
+
+
+def test_reference_patch_is_well_formed():
+    """patches/bendy_tracer_b200.patch (the change a maintainer applies to the reference crate) only touches the render
+    boundary, calls entry points that the header declares, and fills every field of the two config structs"""
+    import re
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_rust_sys as G
+    _, structs, _, funcs = G.parse_header()
+    patch = open(os.path.join(ROOT, "patches", "bendy_tracer_b200.patch")).read()
+    files = re.findall(r"^\+\+\+ b/(\S+)", patch, flags=re.M)
+    assert files == ["Cargo.toml", "src/scene/object/mod.rs", "src/tracer/buffer.rs", "src/tracer/mod.rs"]
+    added = "\n".join(l[1:] for l in patch.splitlines() if l.startswith("+") and not l.startswith("+++"))
+    declared = {n for n, _, _ in funcs}
+    used = set(re.findall(r"sys::(bt_\w+)\(", added))
+    assert used and used <= declared, used - declared
+    assert {"bt_engine_create_multi", "bt_scene_create_json", "bt_render", "bt_engine_destroy", "bt_scene_destroy"} <= used
+    for struct in ("bt_config", "bt_render_config"):
+        body = re.search(r"sys::%s \{(.*?)\n        \};" % struct, added, flags=re.S).group(1)
+        assert re.findall(r"^\s+(\w+):", body, flags=re.M) == [f for f, _, _ in structs[struct]], struct
+    if os.path.isdir("/root/reference/src"):      # (not on the GPU box) the patch applies to the reference as it is
+        import shutil
+        import subprocess
+        import tempfile
+        with tempfile.TemporaryDirectory() as tmp:
+            shutil.copytree("/root/reference/src", os.path.join(tmp, "src"))
+            shutil.copy("/root/reference/Cargo.toml", tmp)
+            r = subprocess.run(["patch", "-p1", "--dry-run", "-i", os.path.join(ROOT, "patches", "bendy_tracer_b200.patch")],
+                               cwd=tmp, capture_output=True, text=True)
+            assert r.returncode == 0, r.stdout + r.stderr
