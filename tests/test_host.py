@@ -356,7 +356,7 @@ def test_reference_patch_is_well_formed():
     assert {"bt_engine_create_multi", "bt_scene_create_json", "bt_render", "bt_engine_destroy", "bt_scene_destroy"} <= used
     for struct in ("bt_config", "bt_render_config"):
         body = re.search(r"sys::%s \{(.*?)\n        \};" % struct, added, flags=re.S).group(1)
-        assert re.findall(r"^\s+(\w+):", body, flags=re.M) == [f for f, _, _ in structs[struct]], struct
+        assert re.findall(r"^ {12}(\w+):", body, flags=re.M) == [f for f, _, _ in structs[struct]], struct
     if os.path.isdir("/root/reference/src"):      # (not on the GPU box) the patch applies to the reference as it is
         import shutil
         import subprocess
