@@ -258,6 +258,10 @@ int build_params(const bt_engine* en, bt_scene* s, const SceneDev* dev, uint64_t
     p.regen_patience = knob(tn.regen_patience, long_flights ? 8 : (cheap_scans ? 32 : 16));
     p.scan_lanes = knob(tn.scan_lanes, 8);      // (profiles/r1_sweep_nearest_sphere_bound.log: flat within 1 % from 6/2 to 8/4)
     p.scan_patience = knob(tn.scan_patience, 3);
+    // The exact arithmetic flavour means EVERY operation of the path is the oracle's, the stepper's 1 / |d| included: a scene that
+    // AUTO renders exactly (volumetric spheres: a 1e-5 position error flips scatter decisions of the 33-step march at a visible
+    // rate -- cloud + lens at 64 spp: MAE 1.2e-3 .. 2.3e-3 with MUFU.RSQ, ~1e-7 with the rounded rsqrt) gets the exact stepper too.
+    if (use_exact(en, s) && p.scene.n_lens != 0) p.scene.lens_exact = 1;
     if (tn.lens_no_skip > 0) p.scene.lens_skip = 0;
     if (tn.lens_dist_grid == 0 && p.scene.lens_skip == 3) p.scene.lens_skip = 1;  // (A/B: the per-flight bookkeeping)
     p.steps_per_turn = std::max(1u, knob(tn.steps_per_turn, long_flights ? 3 : 2));

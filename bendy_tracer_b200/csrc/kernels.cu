@@ -895,6 +895,7 @@ size_t render_smem_bytes(const RenderParams& p, unsigned threads) {
         const bool exact_ = p.scene.lens_exact != 0, bvh_ = p.scene.n_bvh != 0;                        \
         if (p.scene.n_lens == 0 && !bvh_) BT_LAUNCH_(KERNEL, false, false, 0, false, TAIL, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);      \
         else if (p.scene.n_lens == 0) BT_LAUNCH_(KERNEL, false, false, 0, true, TAIL, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);           \
+        else if (bvh_ && exact_) BT_LAUNCH_(KERNEL, true, true, 0, true, TAIL, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);                   \
         else if (bvh_) BT_LAUNCH_(KERNEL, true, false, 0, true, TAIL, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);                            \
         else if (p.scene.n_lens == 1 && !exact_) BT_LAUNCH_(KERNEL, true, false, 1, false, TAIL, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__); \
         else if (!exact_) BT_LAUNCH_(KERNEL, true, false, 0, false, TAIL, GRID, BLOCK, SMEM, STREAM, __VA_ARGS__);                        \
@@ -943,6 +944,8 @@ cudaError_t BT_SFX(launch_render)(const RenderParams& p, cudaStream_t stream, ui
         else if (ok && !lensed && BT_FITS_(CT_SPHERES | CT_METAL | CT_GLASS)) BT_POOL_(false, false, 0, CT_SPHERES | CT_METAL | CT_GLASS);
         else if (ok && lensed && BT_FITS_(CT_SPHERES | CT_METAL | CT_GLASS)) BT_POOL_(true, false, 1, CT_SPHERES | CT_METAL | CT_GLASS);
         else if (ok && lensed && BT_FITS_(CT_SPHERES | CT_VOLUMES)) BT_POOL_(true, false, 1, CT_SPHERES | CT_VOLUMES);
+        else if (p.output == 0 && lensed && p.scene.n_lens == 1 && p.scene.lens_exact && BT_FITS_(CT_SPHERES | CT_VOLUMES))
+            BT_POOL_(true, true, 1, CT_SPHERES | CT_VOLUMES);
 #undef BT_POOL_
 #undef BT_FITS_
         ++*launches;
@@ -962,6 +965,7 @@ cudaError_t BT_SFX(launch_render)(const RenderParams& p, cudaStream_t stream, ui
         else if (special && !lensed && BT_FITS_(CT_SPHERES | CT_METAL | CT_GLASS)) BT_POOL_(false, false, 0, CT_SPHERES | CT_METAL | CT_GLASS);
         else if (special && lensed && BT_FITS_(CT_SPHERES | CT_METAL | CT_GLASS)) BT_POOL_(true, false, 1, CT_SPHERES | CT_METAL | CT_GLASS);
         else if (special && lensed && BT_FITS_(CT_SPHERES | CT_VOLUMES)) BT_POOL_(true, false, 1, CT_SPHERES | CT_VOLUMES);
+        else if (lensed && one && exact && BT_FITS_(CT_SPHERES | CT_VOLUMES)) BT_POOL_(true, true, 1, CT_SPHERES | CT_VOLUMES);  // cloud / volume + one mass, exact stepper
         else if (ct & CT_CUBOID_LIGHT) {
             if (!lensed) BT_POOL_(false, false, 0, CT_ALL);
             else if (exact) BT_POOL_(true, true, 0, CT_ALL);

@@ -171,7 +171,8 @@ int bt_scene_set_accel(bt_scene* scene, int accel);
  * bit-identical to the CPU oracle up to libm's sin/cos/pow).  FAST: MUFU reciprocal / square
  * roots and FMA-contracted rect tests, each within ~1 ulp (image MAE vs the oracle 1e-8 .. 1e-5 on
  * surface scenes).  AUTO (default): EXACT for scenes with volumetric spheres -- their steep density
- * gradients turn ulp-level differences into flipped scatter decisions -- FAST otherwise.
+ * gradients turn ulp-level differences into flipped scatter decisions -- FAST otherwise.  Under a lens
+ * field EXACT implies BT_LENS_EXACT_RSQRT (the whole path is then bit-identical to the oracle).
  * Environment override for new scenes: BT_PRECISION=fast|exact|auto. */
 enum { BT_PRECISION_AUTO = 0, BT_PRECISION_FAST = 1, BT_PRECISION_EXACT = 2 };
 int bt_scene_set_precision(bt_scene* scene, int precision);

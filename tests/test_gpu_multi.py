@@ -106,3 +106,22 @@ def test_multi_engine_on_real_peers():
 def lib_count(engine):
     from bendy_tracer_b200._ffi import lib
     return lib.bt_engine_device_count(engine.handle)
+
+
+def test_render_sharded_nccl_ranks():
+    """one process per GPU (torch.distributed, NCCL): every rank renders its pass slice, one reduce -- the sum equals the
+    one-GPU frame (tools/check_multi_gpu.py under torchrun on every GPU of the box)"""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two CUDA devices")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tools", "check_multi_gpu.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "OK" in out.stdout

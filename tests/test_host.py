@@ -69,6 +69,29 @@ def test_scene_round_trip(name):
     assert scene.find_by_tag("camera") == 0 and scene.find_by_tag("no such tag") is None
 
 
+UPSTREAM_DIR = os.path.join(ROOT, "tests", "golden", "scenes_upstream")
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_upstream_scene_bytes(name):
+    """the reference's shipped files, byte for byte (hash-ordered keys, the reference's own gzip stream): they load, round-trip
+    to the same JSON value, and flatten to exactly what the re-serialised copy flattens to"""
+    import hashlib
+    path = os.path.join(UPSTREAM_DIR, name + ".json.gz")
+    sums = dict(reversed(l.split()) for l in open(os.path.join(UPSTREAM_DIR, "SHA256SUMS")))
+    raw = open(path, "rb").read()
+    assert hashlib.sha256(raw).hexdigest() == sums[name + ".json.gz"]
+    if os.path.exists(f"/root/reference/{name}.json.gz"):       # (not on the GPU box)
+        assert raw == open(f"/root/reference/{name}.json.gz", "rb").read()
+    up, ours = bt.Scene(raw), bt.Scene.load(O.scene_path(name))
+    original = json.loads(gzip.decompress(raw))
+    assert list(original["objects"]["collection"]) != sorted(original["objects"]["collection"], key=int) or name != "cornell"
+    assert json.loads(up.to_json()) == original
+    assert up.to_json() == ours.to_json()                       # canonical (ascending ObjectRef) order either way
+    assert up.info() == ours.info()
+    assert up.find_by_tag("camera") == ours.find_by_tag("camera") == 0
+
+
 def test_scene_plain_json_and_gzip(tmp_path):
     text = gzip.open(O.scene_path("scene")).read()
     a, b = bt.Scene(text), bt.Scene.load(O.scene_path("scene"))
