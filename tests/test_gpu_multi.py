@@ -124,4 +124,4 @@ def test_render_sharded_nccl_ranks():
            "--master-port", "29533", os.path.join(root, "tools", "check_multi_gpu.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "OK" in out.stdout
+    assert "ALL OK" in out.stdout

@@ -34,6 +34,8 @@ for name, lens in (("cornell", None), ("cloud", None), ("scene", (1.362, 1.577, 
     ok &= good
     if rank == 0:
         print(f"{name}: world {world} max|sharded - single| = {diff:.3e} (scale {scale:.3e}) samples {sharded.samples()} -> {'ok' if good else 'FAIL'}")
+if rank == 0:
+    print("ALL OK" if ok else "FAILED")
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
