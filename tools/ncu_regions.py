@@ -4,8 +4,8 @@ ncu report captured with --import-source on (kernels compiled -lineinfo).
 
     python tools/ncu_regions.py REPORT.ncu-rep KERNEL_REGEX [LAUNCH_INDEX]
 
-Regions: every function of csrc/device.cuh (found by its BT_DEV / template header) and the phases of
-render_body in csrc/kernels.cu (found by their comment markers).  Inlined code is attributed to the
+Regions: every function of csrc/device.cuh (found by its BT_DEV / template header), the functions of
+csrc/kernels.cu and the phases of the pooled kernel in csrc/render_pool.cuh (found by marker lines).  Inlined code is attributed to the
 line it was written on, i.e. to the helper, not to its caller.
 """
 import csv
@@ -36,17 +36,26 @@ GROUPS = [  # (region label, function-name regex) for device.cuh
 ]
 KERNEL_MARKS = [  # (first line matching -> region label) for kernels.cu, in file order
     (r"struct SceneView", "scene staging"),
-    (r"struct Traced", "flight functions (geodesic_step / scan bookkeeping)"),
-    (r"BT_DEV void render_body", "render_body prologue"),
-    (r"Regeneration phase", "regeneration control + path seeding"),
-    (r"---- 1\. trace one segment", "trace dispatch"),
-    (r"if \(LENS\) \{", "flight loop control (ballots)"),
-    (r"if \(alive && has_event\)", "classify / material"),
-    (r"---- 2\. the shared direction sampler", "direction sampler"),
-    (r"---- 3\. the scattered ray", "scatter / pdf / throughput"),
-    (r"if \(finish\) \{", "finish / accumulate"),
-    (r"if \(valid\) \{  // Buffer::write_color", "epilogue"),
+    (r"struct Traced", "trace_straight / flight state"),
+    (r"struct GridFetch", "free-distance grid lookup"),
+    (r"BT_DEV int geodesic_step", "geodesic_step bookkeeping (capture / far / chord length / skip test)"),
+    (r"BT_DEV int geodesic_scan", "geodesic_scan bookkeeping"),
+    (r"BT_DEV Traced flight_result", "flight_result / trace_ray"),
+    (r"struct PathQ", "path state"),
+    (r"BT_DEV bool shade_event", "shade_event: classify / material"),
+    (r"---- 2\. the shared direction sampler", "shade_event: direction sampler"),
+    (r"---- 3\. the scattered ray", "shade_event: scatter / pdf / throughput"),
+    (r"    if \(finish\) \{", "shade_event: finish"),
+    (r"BT_DEV void render_body", "render_body (lane kernel) control"),
     (r"__global__ void", "other kernels"),
+]
+POOL_MARKS = [  # render_pool.cuh
+    (r"^enum \{", "pool: layout / collect"),
+    (r"BT_DEV void render_pool_body", "pool: prologue + phase selection"),
+    (r"=+ STEP =+", "pool: STEP loop control + refill rounds"),
+    (r"=+ SCAN =+", "pool: SCAN pass (state load / store, queues)"),
+    (r"=+ SHADE =+", "pool: SHADE pass (state load / store, queues)"),
+    (r"=+ REGEN =+", "pool: REGEN pass (retire, pixel stream, issue)"),
 ]
 
 
@@ -68,12 +77,13 @@ def device_regions():
     return regions
 
 
-def kernel_regions():
-    lines = open(os.path.join(CSRC, "kernels.cu")).read().splitlines()
+def kernel_regions(fname="kernels.cu", table=None):
+    table = table or KERNEL_MARKS
+    lines = open(os.path.join(CSRC, fname)).read().splitlines()
     marks, k = [], 0
     for i, l in enumerate(lines, 1):
-        if k < len(KERNEL_MARKS) and re.search(KERNEL_MARKS[k][0], l):
-            marks.append((i, KERNEL_MARKS[k][1]))
+        if k < len(table) and re.search(table[k][0], l):
+            marks.append((i, table[k][1]))
             k += 1
     return [(ln, nxt[0] - 1, label) for (ln, label), nxt in zip(marks, marks[1:] + [(len(lines) + 1, None)])]
 
@@ -84,7 +94,7 @@ def main():
     cmd = ["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv", "--kernel-name", "regex:" + kern,
            "--launch-skip", skip, "--launch-count", "1"]
     rows = list(csv.reader(io.StringIO(subprocess.run(cmd, capture_output=True, text=True, check=True).stdout)))
-    regions = {"device.cuh": device_regions(), "kernels.cu": kernel_regions()}
+    regions = {"device.cuh": device_regions(), "kernels.cu": kernel_regions(), "render_pool.cuh": kernel_regions("render_pool.cuh", POOL_MARKS)}
     agg, cur, hdr, name = {}, None, None, ""
     for r in rows:
         if not r:
