@@ -256,6 +256,11 @@ class Scene:
         a = (C.c_float * 12)(*[float(x) for x in np.asarray(affine, np.float32).reshape(12)])
         check(lib.bt_scene_apply_transform(self.handle, object_ref, a))
 
+    def commit(self):
+        """UpdateQueue::commit (src/scene/mod.rs:204-213): apply the queued edits to the flattened scene now (transform edits in
+        place: records rewritten, BVH refit); otherwise the next render does it"""
+        check(lib.bt_scene_commit(self.handle))
+
     def set_lenses(self, xyzr, lens_config=None):
         xyzr = np.ascontiguousarray(xyzr, np.float32).reshape(-1, 4)
         cfg = (lens_config or LensConfig())._c()

@@ -109,7 +109,15 @@ struct bt_scene {
     uint64_t flat_version;  // bumped by every re-flatten
     int accel;          // ACCEL_AUTO / ACCEL_LINEAR / ACCEL_BVH
     int precision;      // BT_PRECISION_AUTO / _FAST / _EXACT
-    bool flat_dirty;    // host flattening out of date
+    bool flat_dirty;    // host flattening out of date: flatten from scratch
+    // transform edits not yet applied to `flat` (bt_scene_apply_transform; applied by bt_scene_commit or the next render):
+    // the objects whose world transform changed (the edited object and its descendants)
+    std::vector<uint64_t> pending;
+    // blob ranges (float4 offset, count) rewritten in place since the flattening of version patch_base: a device copy that is
+    // at least that recent is brought up to date by uploading just these
+    std::vector<std::pair<uint32_t, uint32_t> > patch;
+    uint64_t patch_base;
+    bool patch_dist;    // ... and the free-distance grid too
     std::vector<SceneDev> devs;
 };
 
@@ -135,12 +143,39 @@ int ensure_scratch(bt_engine* e, size_t bytes) {
 }
 
 // Brings the scene's copy on the CURRENT device (cudaSetDevice done by the caller) up to date; *out = that copy.
-int refresh_scene(bt_scene* s, int device, cudaStream_t stream, SceneDev** out) {
+// the host half of a scene update: from scratch, or -- for transform edits -- in place (update_flat: records rewritten, BVH refit)
+void commit_scene(bt_scene* s) {
+    if (!s->flat_dirty && !s->pending.empty()) {
+        std::sort(s->pending.begin(), s->pending.end());
+        s->pending.erase(std::unique(s->pending.begin(), s->pending.end()), s->pending.end());
+        bool dist = false;
+        std::vector<std::pair<uint32_t, uint32_t> > dirty;
+        if (update_flat(s->flat, s->scene, s->pending, &dirty, &dist)) {
+            s->patch.insert(s->patch.end(), dirty.begin(), dirty.end());
+            s->patch_dist |= dist;
+            ++s->flat_version;
+            if (s->patch.size() > 4096) {  // so many small ranges that a full upload is cheaper: older copies take that path
+                s->patch.clear();
+                s->patch_base = s->flat_version;
+            }
+        } else {
+            s->flat_dirty = true;
+        }
+    }
+    s->pending.clear();
     if (s->flat_dirty) {
         s->flat = flatten(s->scene, s->accel);
         s->flat_dirty = false;
         ++s->flat_version;
+        s->patch.clear();
+        s->patch_dist = false;
+        s->patch_base = s->flat_version;
     }
+}
+
+// Brings the scene's copy on the CURRENT device (cudaSetDevice done by the caller) up to date; *out = that copy.
+int refresh_scene(bt_scene* s, int device, cudaStream_t stream, SceneDev** out) {
+    commit_scene(s);
     SceneDev* d = 0;
     for (SceneDev& c : s->devs)
         if (c.device == device) d = &c;
@@ -150,6 +185,26 @@ int refresh_scene(bt_scene* s, int device, cudaStream_t stream, SceneDev** out) 
         c.device = device;
         s->devs.push_back(c);
         d = &s->devs.back();
+    }
+    if (d->version != s->flat_version && d->version >= s->patch_base && d->version != 0) {
+        // only in-place edits since this copy was made: upload the rewritten ranges (a moved object's records, the refitted
+        // BVH nodes) instead of the whole scene
+        if (d->ev_use) CK(cudaEventSynchronize(d->ev_use));
+        for (const std::pair<uint32_t, uint32_t>& r : s->patch)
+            CK(cudaMemcpyAsync(d->d_blob + r.first, s->flat.blob.data() + r.first, (size_t)r.second * sizeof(float4), cudaMemcpyHostToDevice, stream));
+        if (s->patch_dist) {
+            const size_t db = s->flat.dist.size();
+            if (db > d->dist_cap) {
+                if (d->d_dist) cudaFree(d->d_dist);
+                d->d_dist = 0;
+                d->dist_cap = 0;
+                CK(cudaMalloc((void**)&d->d_dist, db));
+                d->dist_cap = db;
+            }
+            if (db) CK(cudaMemcpyAsync(d->d_dist, s->flat.dist.data(), db, cudaMemcpyHostToDevice, stream));
+        }
+        CK(cudaStreamSynchronize(stream));
+        d->version = s->flat_version;
     }
     if (d->version != s->flat_version) {
         // a render enqueued without synchronising (bt_render_async) may still be reading the old copy
@@ -452,6 +507,8 @@ int bt_scene_create_json(bt_engine* engine, const void* bytes, size_t n, bt_scen
     bt_scene* s = new bt_scene();
     s->engine = engine;
     s->flat_version = 1;
+    s->patch_base = 1;
+    s->patch_dist = false;
     try {
         s->accel = ACCEL_AUTO;
         s->precision = BT_PRECISION_AUTO;
@@ -522,7 +579,23 @@ int bt_scene_apply_transform(bt_scene* scene, uint64_t object_ref, const float a
     Affine a;
     std::memcpy(a.f, affine, sizeof a.f);
     scene->scene.apply_transform(object_ref, a);
-    scene->flat_dirty = true;
+    // the edited object and every descendant get a new world transform (object/mod.rs:212-223)
+    std::vector<uint64_t> todo(1, object_ref);
+    while (!todo.empty()) {
+        const uint64_t r = todo.back();
+        todo.pop_back();
+        scene->pending.push_back(r);
+        const Object& o = scene->scene.get_object(r);
+        todo.insert(todo.end(), o.children.begin(), o.children.end());
+    }
+    return BT_OK;
+    GUARD_END
+}
+
+int bt_scene_commit(bt_scene* scene) {
+    if (!scene) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    GUARD_BEGIN
+    commit_scene(scene);
     return BT_OK;
     GUARD_END
 }

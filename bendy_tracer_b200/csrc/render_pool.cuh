@@ -133,13 +133,19 @@ BT_DEV void render_pool_body(const RenderParams& p) {
     __syncwarp();
 
     // ---- this lane's pixel stream: pixel (lane & 7, lane >> 3) of the warp's tile number `seq` ---------------------
+    // Up to TWO pixels are open per lane: A, the older one, whose paths are being retired (they retire in issue order, so every
+    // finished path belongs to A until A is complete), and B, which the lane starts issuing as soon as A's last path is out --
+    // a lane never waits for the slowest path of a pixel before it starts the next one (calls of a few paths per pixel: the
+    // reference's progressive loop renders ONE pass per call, and a frame split over 8 GPUs leaves 8 spp per call).
     // (everything that is only needed when a pixel starts or ends is recomputed there: the STEP loop is short of registers)
-    uint32_t seq = 0;       // the next tile of the warp's stream this lane will work on
+    uint32_t seq = 0;       // the next tile of the warp's stream this lane will take a pixel from
     uint32_t fetched = 0;   // tiles the warp has drawn from the global counter so far (warp-uniform)
-    bool have_pixel = false, exhausted = false;
-    uint32_t px = 0, py = 0;
-    V3 acc = v3(0.0f, 0.0f, 0.0f);
-    uint32_t issued = 0, retired = 0, sub_i = 0, sub_j = 0;
+    bool exhausted = false;
+    uint32_t n_pix = 0;     // open pixels: 0, 1 (A) or 2 (A and B)
+    uint32_t ax = 0, ay = 0, a_issued = 0, a_retired = 0, bx = 0, by = 0, b_issued = 0;
+    uint32_t tot_issued = 0, tot_retired = 0;   // running path counters of this lane (the ring of in-flight paths is indexed by them)
+    V3 acc = v3(0.0f, 0.0f, 0.0f);              // the sum of A's retired paths
+    uint32_t sub_i = 0, sub_j = 0;              // sub-pixel of the next path of the pixel being issued
 
     // warp-uniform queue sizes
     uint32_t n_fly = 0 /* parked on pl.stack */, n_pend = 0, n_res = 0, n_done = 0, n_free = P;
@@ -398,41 +404,45 @@ BT_DEV void render_pool_body(const RenderParams& p) {
             __syncwarp();
         } else {
             // ================================ REGEN ===============================
-            // 1. retire this pixel's finished paths in path order (Chunk::write_*: rgb += value)
+            // 1. retire finished paths in issue order (Chunk::write_*: rgb += value); a completed pixel goes back to the frame
             uint32_t r_cnt = 0;
-            if (have_pixel) {
-                while (retired < issued) {
-                    const uint32_t s = pl.ring[(retired & (POOL_RING - 1)) * 32 + lane];
-                    if (pl.st[s] != ST_DONE) break;
-                    const float4 c = pl.qc[s];
-                    acc = v3(__fadd_rn(acc.x, c.x), __fadd_rn(acc.y, c.y), __fadd_rn(acc.z, c.z));
-                    pl.st[s] = ST_IDLE;
-                    ++retired;
-                    ++r_cnt;
-                }
-                if (retired == p.paths_per_pixel) {  // Buffer::write_color: rgb += value, alpha untouched (buffer.rs:159-178)
-                    float4* dst = p.fb + ((uint64_t)py * p.width + px);
+            while (tot_retired != tot_issued) {
+                const uint32_t s = pl.ring[(tot_retired & (POOL_RING - 1)) * 32 + lane];
+                if (pl.st[s] != ST_DONE) break;
+                const float4 c = pl.qc[s];
+                acc = v3(__fadd_rn(acc.x, c.x), __fadd_rn(acc.y, c.y), __fadd_rn(acc.z, c.z));
+                pl.st[s] = ST_IDLE;
+                ++tot_retired;
+                ++r_cnt;
+                if (++a_retired == p.paths_per_pixel) {  // Buffer::write_color: rgb += value, alpha untouched (buffer.rs:159-178)
+                    float4* dst = p.fb + ((uint64_t)ay * p.width + ax);
                     float4 fbv = *dst;
                     fbv.x += acc.x;
                     fbv.y += acc.y;
                     fbv.z += acc.z;
                     *dst = fbv;
-                    have_pixel = false;
+                    acc = v3(0.0f, 0.0f, 0.0f);
+                    ax = bx;  // B (if open) becomes A
+                    ay = by;
+                    a_issued = b_issued;
+                    a_retired = 0;
+                    --n_pix;
                 }
             }
             const uint32_t n_ret = __reduce_add_sync(0xffffffffu, r_cnt);
             n_done -= n_ret;
             n_free += n_ret;
-            // 2. the next pixel of this lane's stream: pixel `lane` of the warp's tile number seq.  The warp draws tiles from
-            //    the grid-wide counter as its lanes reach them; a lane may run at most POOL_TILES tiles ahead of the slowest one.
+            // 2. open the next pixel of this lane's stream -- pixel `lane` of the warp's tile number seq -- once every path of the
+            //    newest open pixel is issued.  The warp draws tiles from the grid-wide counter as its lanes reach them; a lane may
+            //    run at most POOL_TILES tiles ahead of the slowest one (the window the tile indices are kept in).
             {
                 const uint32_t tiles_x = (p.width + 7) / 8, tiles_y = (p.row_end - p.row0 + 3) / 4;
                 const unsigned long long n_tiles = (unsigned long long)tiles_x * tiles_y;
 #pragma unroll 1
                 for (;;) {
-                    const uint32_t at = exhausted ? 0xffffffffu : (have_pixel ? seq - 1 : seq);
-                    const uint32_t lo = __reduce_min_sync(0xffffffffu, at);
-                    const bool want = !have_pixel && !exhausted && seq - lo < POOL_TILES;
+                    const uint32_t lo = __reduce_min_sync(0xffffffffu, exhausted ? 0xffffffffu : seq);
+                    const bool room = n_pix == 0 || (n_pix == 1 && a_issued == p.paths_per_pixel);
+                    const bool want = room && !exhausted && seq - lo < POOL_TILES;
                     const uint32_t upto = __reduce_max_sync(0xffffffffu, want ? seq + 1 : 0u);
                     if (upto == 0) break;  // nobody can take a pixel now
                     while (fetched < upto) {
@@ -448,13 +458,19 @@ BT_DEV void render_pool_body(const RenderParams& p) {
                             exhausted = true;
                         } else {
                             const uint32_t ty = (uint32_t)(t / tiles_x), tx = (uint32_t)(t - (unsigned long long)ty * tiles_x);
-                            px = tx * 8 + (lane & 7);
-                            py = p.row0 + ty * 4 + (lane >> 3);
+                            const uint32_t px = tx * 8 + (lane & 7), py = p.row0 + ty * 4 + (lane >> 3);
                             if (px < p.width && py < p.row_end) {
-                                acc = v3(0.0f, 0.0f, 0.0f);
-                                issued = retired = 0;
+                                if (n_pix == 0) {
+                                    ax = px;
+                                    ay = py;
+                                    a_issued = a_retired = 0;
+                                } else {
+                                    bx = px;
+                                    by = py;
+                                    b_issued = 0;
+                                }
+                                ++n_pix;
                                 sub_i = sub_j = 0;  // path_base is a multiple of sub_count: a call starts at sub-pixel (0, 0)
-                                have_pixel = true;
                             } else {
                                 skipped = true;  // a tile that hangs over the frame's edge: on to the next one
                             }
@@ -464,8 +480,10 @@ BT_DEV void render_pool_body(const RenderParams& p) {
                     if (!__any_sync(0xffffffffu, skipped)) break;
                 }
             }
-            // 3. start new camera paths in idle slots
-            const bool can_issue = have_pixel && issued < p.paths_per_pixel && issued - retired < POOL_RING;
+            // 3. start new camera paths in idle slots: the next path of the newest open pixel
+            const bool on_b = n_pix == 2;
+            const uint32_t issued = on_b ? b_issued : a_issued, px = on_b ? bx : ax, py = on_b ? by : ay;
+            const bool can_issue = n_pix != 0 && issued < p.paths_per_pixel && tot_issued - tot_retired < POOL_RING;
             const uint32_t rot = turn & 31u;
             const unsigned m_issue = __ballot_sync(0xffffffffu, can_issue);
             uint32_t take = 0;
@@ -487,7 +505,7 @@ BT_DEV void render_pool_body(const RenderParams& p) {
                     }
                     pl.qa[slot] = make_uint4((uint32_t)rng.s0, (uint32_t)(rng.s0 >> 32), (uint32_t)rng.s1, (uint32_t)(rng.s1 >> 32));
                     pl.qb[slot] = make_uint4((uint32_t)rng.s2, (uint32_t)(rng.s2 >> 32), (uint32_t)rng.s3, (uint32_t)(rng.s3 >> 32));
-                    const uint32_t ri = issued & (POOL_RING - 1);
+                    const uint32_t ri = tot_issued & (POOL_RING - 1);
                     pl.qc[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pack_misc(ri, false, -1, 0u, 0u)));
                     if (AOV) {
                         pl.qe[slot] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0x7f800000));
@@ -501,7 +519,8 @@ BT_DEV void render_pool_body(const RenderParams& p) {
                     }
                     pl.st[slot] = LENS ? ST_FLY : ST_PEND_STRAIGHT;
                     pl.ring[ri * 32 + lane] = (uint8_t)slot;
-                    ++issued;
+                    ++tot_issued;
+                    if (on_b) ++b_issued; else ++a_issued;
                 }
                 if (LENS) n_fly += take; else n_pend += take;
                 n_free -= take;

@@ -770,9 +770,7 @@ void Scene::apply_transform(uint64_t object_ref, const Affine& affine) {  // obj
 // ------------------------------------------------------------------------------------------
 namespace {
 
-struct Bounds {
-    float lo[3], hi[3];
-};
+typedef AABB Bounds;
 // LIGHT_RECT fields l1..l6 of a light record (layout.h): Rect::random_point, rect.rs:82-86
 void fill_rect_light(float4* l, const Rect& r, const Affine& tf) {
     l[1] = f4(r.x[0], r.x[1], r.x[2], -r.half_width);
@@ -1037,6 +1035,122 @@ struct BvhBuild {
     }
 };
 
+// ---- the records of ONE object (flatten() appends them; update_flat() overwrites them in place after a transform edit) ----
+struct EmitCtx {
+    const Scene& scene;
+    const std::map<uint64_t, uint32_t>& mat_index;
+    const std::map<uint64_t, uint32_t>& vol_index;
+    bool aa_rects;
+    uint32_t material(uint64_t r) const {
+        const Data& d = scene.get_data(r);
+        if (d.kind != DATA_MATERIAL) throw SceneError("expected material data");
+        return mat_index.find(r)->second;
+    }
+};
+struct ObjRecords {
+    std::vector<float4> prims;        // PRIM_STRIDE per primitive, canonical indices first_prim ..
+    std::vector<Bounds> bounds;
+    bool any_diffuse = false, has_volume = false;
+    bool has_box = false;             // a Cuboid whose faces form one rectangular box
+    float4 box[BOX_STRIDE];
+    bool is_light = false, zero_area = false;
+    std::vector<float4> light;        // LIGHT_STRIDE (l0.y = first_prim, canonical)
+    std::vector<float4> face_lights;  // 6 x LIGHT_STRIDE for a LIGHT Cuboid
+};
+ObjRecords emit_object(const EmitCtx& ctx, const Object& o, uint32_t obj, uint32_t first_prim) {
+    ObjRecords rec;
+    const Scene& scene = ctx.scene;
+    std::vector<float4>& prims = rec.prims;
+    uint32_t n_prims = 0;
+    const Affine& tf = o.transform_world;
+    if (o.kind == OBJ_SPHERE) {
+        uint32_t mat = ctx.material(o.material);
+        uint32_t vol = 0xffffffffu;
+        if (o.has_volume) {
+            const Data& d = scene.get_data(o.volume);
+            if (d.kind != DATA_VOLUME) throw SceneError("expected volume data");
+            vol = ctx.vol_index.find(o.volume)->second;
+            rec.has_volume = true;
+        }
+        float r = o.radius;
+        prims.push_back(f4(tf.f[9], tf.f[10], tf.f[11], r));
+        prims.push_back(f4(r * r, 3.14159265358979323846f * r * r, r > 0.0f ? 2e-5f / r : 3.0e38f, 0.0f));
+        prims.push_back(f4(0, 0, 0, 0));
+        prims.push_back(f4(0, 0, 0, 0));
+        prims.push_back(f4(as_f((uint32_t)PRIM_SPHERE), as_f(mat), as_f(vol), as_f(obj)));
+        {
+            Bounds b;
+            for (int k = 0; k < 3; ++k) { b.lo[k] = tf.f[9 + k] - r; b.hi[k] = tf.f[9 + k] + r; }
+            rec.bounds.push_back(b);
+        }
+        n_prims = 1;
+        rec.any_diffuse |= scene.get_data(o.material).mat_kind == MAT_DIFFUSE;
+    } else if (o.kind == OBJ_RECT) {
+        push_rect(prims, rec.bounds, o.rect, tf, PRIM_RECT, ctx.material(o.rect.material), obj, ctx.aa_rects);
+        n_prims = 1;
+        rec.any_diffuse |= scene.get_data(o.rect.material).mat_kind == MAT_DIFFUSE;
+    } else if (o.kind == OBJ_CUBOID) {
+        for (int i = 0; i < 6; ++i) {
+            // transform * Affine3A::from_translation(offset), cuboid.rs:95
+            Affine ftf = tf;
+            float t[3];
+            mat_vec(tf, o.face_offset[i], t);
+            for (int k = 0; k < 3; ++k) ftf.f[9 + k] = t[k] + tf.f[9 + k];
+            push_rect(prims, rec.bounds, o.faces[i], ftf, PRIM_CUBOID_FACE, ctx.material(o.faces[i].material), obj);
+            rec.any_diffuse |= scene.get_data(o.faces[i].material).mat_kind == MAT_DIFFUSE;
+        }
+        rec.has_box = make_box(o, tf, rec.box);
+        n_prims = 6;
+    }
+    // the canonical primitive index lives in the high bits of q4.x (layout.h: PRIM_CANON_SHIFT)
+    for (uint32_t i = 0; i < n_prims; ++i) {
+        float4& meta = prims[(size_t)i * PRIM_STRIDE + 4];
+        meta.x = as_f((as_u(meta.x) & ((1u << PRIM_CANON_SHIFT) - 1u)) | ((first_prim + i) << PRIM_CANON_SHIFT));
+    }
+    if (o.flags & 1u) {  // ObjectFlags::LIGHT
+        rec.is_light = true;
+        std::vector<float4>& lights = rec.light;
+        lights.assign(LIGHT_STRIDE, f4(0, 0, 0, 0));
+        if (o.kind == OBJ_SPHERE) {
+            lights[0] = f4(as_f(LIGHT_SPHERE), as_f(first_prim), as_f(n_prims), as_f(obj));
+            lights[1] = f4(tf.f[9], tf.f[10], tf.f[11], o.radius);
+        } else if (o.kind == OBJ_RECT) {
+            lights[0] = f4(as_f(LIGHT_RECT), as_f(first_prim), as_f(n_prims), as_f(obj));
+            fill_rect_light(&lights[0], o.rect, tf);
+        } else if (o.kind == OBJ_CUBOID) {
+            // Cuboid::random_point, cuboid.rs:48-54: WeightedIndex over the face areas (rand 0.8.5:
+            // cumulative sums without the last weight, Uniform::new(0, total)), then the face's
+            // Rect::random_point.  The six faces become LIGHT_RECT sub-records behind the object
+            // lights (appended by flatten); l2.z holds the first one's index.
+            float cumulative[5];
+            float total = 4.0f * o.faces[0].half_width * o.faces[0].half_height;
+            for (int i = 1; i < 6; ++i) {
+                cumulative[i - 1] = total;
+                total += 4.0f * o.faces[i].half_width * o.faces[i].half_height;
+            }
+            if (!(total > 0.0f)) rec.zero_area = true;
+            lights[0] = f4(as_f(LIGHT_CUBOID), as_f(first_prim), as_f(n_prims), as_f(obj));
+            lights[1] = f4(cumulative[0], cumulative[1], cumulative[2], cumulative[3]);
+            lights[2] = f4(cumulative[4], total > 0.0f ? uniform_scale(0.0f, total) : 0.0f, as_f(0u), 0.0f);
+            for (int i = 0; i < 6; ++i) {
+                Affine ftf = tf;
+                float t[3];
+                mat_vec(tf, o.face_offset[i], t);
+                for (int k = 0; k < 3; ++k) ftf.f[9 + k] = t[k] + tf.f[9 + k];
+                size_t fb = rec.face_lights.size();
+                rec.face_lights.resize(fb + LIGHT_STRIDE, f4(0, 0, 0, 0));
+                rec.face_lights[fb] = f4(as_f(LIGHT_RECT), as_f(first_prim + (uint32_t)i), as_f(1u), as_f(obj));
+                fill_rect_light(&rec.face_lights[fb], o.faces[i], ftf);
+                rec.face_lights[fb + 5].w = 4.0f * o.faces[i].half_width * o.faces[i].half_height;  // Rect::area (rect.rs:98)
+            }
+        } else {
+            lights[0] = f4(as_f(LIGHT_POINT), as_f(0), as_f(0), as_f(obj));
+            lights[1] = f4(tf.f[9], tf.f[10], tf.f[11], 0.0f);
+        }
+    }
+    return rec;
+}
+
 // The free-distance grid of a lensed linear-scan scene (SceneHeader::dist_*).  A geodesic chord shorter than the distance
 // from its start to the nearest primitive surface cannot hit anything and is not intersected ("Geodesic
 // flights"); the grid makes that distance one byte load per RK4 step instead of per-flight bookkeeping that decays and is
@@ -1171,16 +1285,6 @@ FlatScene flatten(const Scene& scene, int accel) {
             fs.grids.insert(fs.grids.end(), d.buffer.begin(), d.buffer.end());
         }
     }
-    struct Resolve {
-        const Scene& s;
-        std::map<uint64_t, uint32_t>& mi;
-        uint32_t material(uint64_t r) const {
-            const Data& d = s.get_data(r);
-            if (d.kind != DATA_MATERIAL) throw SceneError("expected material data");
-            return mi[r];
-        }
-    } resolve = {scene, mat_index};
-
     // root material folded to the ColorData sample_root returns (src/tracer/mod.rs:429-452)
     {
         const Data& d = scene.get_data(scene.root_material);
@@ -1198,104 +1302,40 @@ FlatScene flatten(const Scene& scene, int accel) {
 
     // BT_ACCEL_LINEAR_FACES keeps the literal tests: six Rect::hit per cuboid, the general rect test everywhere
     const bool aa_rects = accel != ACCEL_LINEAR_FACES && !std::getenv("BT_NO_AA_RECTS");
+    const EmitCtx ctx = {scene, mat_index, vol_index, aa_rects};
     std::vector<float4> prims, lights, face_lights, boxes;
     std::vector<size_t> cuboid_lights;  // offsets of the LIGHT_CUBOID records in `lights`
     std::vector<std::pair<uint32_t, uint32_t> > box_of_prim;  // (first face record, box index)
     std::vector<Bounds> bounds;
     bool any_diffuse = false;
     for (std::map<uint64_t, Object>::const_iterator it = scene.objects.begin(); it != scene.objects.end(); ++it) {
-        const Object& o = it->second;
-        uint32_t obj = (uint32_t)fs.object_refs.size();
+        const uint32_t obj = (uint32_t)fs.object_refs.size(), first_prim = (uint32_t)(prims.size() / PRIM_STRIDE);
         fs.object_refs.push_back(it->first);
-        uint32_t first_prim = (uint32_t)(prims.size() / PRIM_STRIDE);
-        uint32_t n_prims = 0;
-        const Affine& tf = o.transform_world;
-        if (o.kind == OBJ_SPHERE) {
-            uint32_t mat = resolve.material(o.material);
-            uint32_t vol = 0xffffffffu;
-            if (o.has_volume) {
-                const Data& d = scene.get_data(o.volume);
-                if (d.kind != DATA_VOLUME) throw SceneError("expected volume data");
-                vol = vol_index[o.volume];
-                fs.header.has_volume_prims = 1;
-            }
-            float r = o.radius;
-            prims.push_back(f4(tf.f[9], tf.f[10], tf.f[11], r));
-            prims.push_back(f4(r * r, 3.14159265358979323846f * r * r, r > 0.0f ? 2e-5f / r : 3.0e38f, 0.0f));
-            prims.push_back(f4(0, 0, 0, 0));
-            prims.push_back(f4(0, 0, 0, 0));
-            prims.push_back(f4(as_f(PRIM_SPHERE | ((uint32_t)(prims.size() / PRIM_STRIDE) << PRIM_CANON_SHIFT)), as_f(mat), as_f(vol), as_f(obj)));
-            {
-                Bounds b;
-                for (int k = 0; k < 3; ++k) { b.lo[k] = tf.f[9 + k] - r; b.hi[k] = tf.f[9 + k] + r; }
-                bounds.push_back(b);
-            }
-            n_prims = 1;
-            any_diffuse |= scene.get_data(o.material).mat_kind == MAT_DIFFUSE;
-        } else if (o.kind == OBJ_RECT) {
-            push_rect(prims, bounds, o.rect, tf, PRIM_RECT, resolve.material(o.rect.material), obj, aa_rects);
-            n_prims = 1;
-            any_diffuse |= scene.get_data(o.rect.material).mat_kind == MAT_DIFFUSE;
-        } else if (o.kind == OBJ_CUBOID) {
-            for (int i = 0; i < 6; ++i) {
-                // transform * Affine3A::from_translation(offset), cuboid.rs:95
-                Affine ftf = tf;
-                float t[3];
-                mat_vec(tf, o.face_offset[i], t);
-                for (int k = 0; k < 3; ++k) ftf.f[9 + k] = t[k] + tf.f[9 + k];
-                push_rect(prims, bounds, o.faces[i], ftf, PRIM_CUBOID_FACE, resolve.material(o.faces[i].material), obj);
-                any_diffuse |= scene.get_data(o.faces[i].material).mat_kind == MAT_DIFFUSE;
-            }
-            float4 box[BOX_STRIDE];
-            if (make_box(o, tf, box)) {  // q4.z of the first face: 1 + box index (cuboid faces carry no area)
-                box_of_prim.push_back(std::make_pair((uint32_t)(prims.size() / PRIM_STRIDE) - 6u, (uint32_t)(boxes.size() / BOX_STRIDE)));
-                boxes.insert(boxes.end(), box, box + BOX_STRIDE);
-            }
-            n_prims = 6;
+        const ObjRecords rec = emit_object(ctx, it->second, obj, first_prim);
+        ObjSpan span = {first_prim, (uint32_t)(rec.prims.size() / PRIM_STRIDE), -1, -1, false};
+        prims.insert(prims.end(), rec.prims.begin(), rec.prims.end());
+        bounds.insert(bounds.end(), rec.bounds.begin(), rec.bounds.end());
+        any_diffuse |= rec.any_diffuse;
+        if (rec.has_volume) fs.header.has_volume_prims = 1;
+        if (rec.has_box) {  // q4.z of the first face: 1 + box index (cuboid faces carry no area)
+            span.box = (int32_t)(boxes.size() / BOX_STRIDE);
+            box_of_prim.push_back(std::make_pair(first_prim, (uint32_t)span.box));
+            boxes.insert(boxes.end(), rec.box, rec.box + BOX_STRIDE);
         }
-        if (o.flags & 1u) {  // ObjectFlags::LIGHT
-            size_t base = lights.size();
-            lights.resize(base + LIGHT_STRIDE, f4(0, 0, 0, 0));
-            if (o.kind == OBJ_SPHERE) {
-                lights[base] = f4(as_f(LIGHT_SPHERE), as_f(first_prim), as_f(n_prims), as_f(obj));
-                lights[base + 1] = f4(tf.f[9], tf.f[10], tf.f[11], o.radius);
-            } else if (o.kind == OBJ_RECT) {
-                lights[base] = f4(as_f(LIGHT_RECT), as_f(first_prim), as_f(n_prims), as_f(obj));
-                fill_rect_light(&lights[base], o.rect, tf);
-            } else if (o.kind == OBJ_CUBOID) {
-                // Cuboid::random_point, cuboid.rs:48-54: WeightedIndex over the face areas (rand 0.8.5:
-                // cumulative sums without the last weight, Uniform::new(0, total)), then the face's
-                // Rect::random_point.  The six faces become LIGHT_RECT sub-records behind the object
-                // lights (face_lights, appended below); l2.z holds the first one's index.
-                float cumulative[5];
-                float total = 4.0f * o.faces[0].half_width * o.faces[0].half_height;
-                for (int i = 1; i < 6; ++i) {
-                    cumulative[i - 1] = total;
-                    total += 4.0f * o.faces[i].half_width * o.faces[i].half_height;
-                }
-                if (!(total > 0.0f)) fs.cuboid_light_without_area = true;  // WeightedIndex::new(..).unwrap() panics
-                lights[base] = f4(as_f(LIGHT_CUBOID), as_f(first_prim), as_f(n_prims), as_f(obj));
-                lights[base + 1] = f4(cumulative[0], cumulative[1], cumulative[2], cumulative[3]);
-                lights[base + 2] = f4(cumulative[4], total > 0.0f ? uniform_scale(0.0f, total) : 0.0f,
-                                      as_f((uint32_t)(face_lights.size() / LIGHT_STRIDE)), 0.0f);
+        if (rec.is_light) {
+            const size_t base = lights.size();
+            span.light = (int32_t)(base / LIGHT_STRIDE);
+            lights.insert(lights.end(), rec.light.begin(), rec.light.end());
+            if (!rec.face_lights.empty()) {  // a LIGHT Cuboid: l2.z = index of its first face sub-record (made absolute below)
+                span.cuboid_light = true;
+                lights[base + 2].z = as_f((uint32_t)(face_lights.size() / LIGHT_STRIDE));
                 cuboid_lights.push_back(base);
-                for (int i = 0; i < 6; ++i) {
-                    Affine ftf = tf;
-                    float t[3];
-                    mat_vec(tf, o.face_offset[i], t);
-                    for (int k = 0; k < 3; ++k) ftf.f[9 + k] = t[k] + tf.f[9 + k];
-                    size_t fb = face_lights.size();
-                    face_lights.resize(fb + LIGHT_STRIDE, f4(0, 0, 0, 0));
-                    face_lights[fb] = f4(as_f(LIGHT_RECT), as_f(first_prim + (uint32_t)i), as_f(1u), as_f(obj));
-                    fill_rect_light(&face_lights[fb], o.faces[i], ftf);
-                    face_lights[fb + 5].w = 4.0f * o.faces[i].half_width * o.faces[i].half_height;  // Rect::area (rect.rs:98)
-                }
+                face_lights.insert(face_lights.end(), rec.face_lights.begin(), rec.face_lights.end());
                 fs.header.content |= 64u;  // CT_CUBOID_LIGHT
-            } else {
-                lights[base] = f4(as_f(LIGHT_POINT), as_f(0), as_f(0), as_f(obj));
-                lights[base + 1] = f4(tf.f[9], tf.f[10], tf.f[11], 0.0f);
+                if (rec.zero_area) fs.cuboid_light_without_area = true;  // WeightedIndex::new(..).unwrap() panics
             }
         }
+        fs.spans.push_back(span);
     }
     // object lights first (Uniform::new(0, count) indexes them), the cuboid face sub-records behind
     const uint32_t n_object_lights = (uint32_t)(lights.size() / LIGHT_STRIDE);
@@ -1428,9 +1468,121 @@ FlatScene flatten(const Scene& scene, int accel) {
     h.max_steps = scene.lens_config.max_steps;
     h.lens_exact = scene.lens_config.flags & 1u;
     fs.diffuse_without_light = any_diffuse && h.n_lights == 0;
+    fs.where.assign(h.n_prims, 0);
+    for (uint32_t pos = 0; pos < h.n_prims; ++pos) fs.where[fs.prim_order[pos]] = pos;
+    fs.prim_bounds = bounds;
+    fs.accel = accel;
     if (fs.blob.empty()) fs.blob.push_back(f4(0, 0, 0, 0));
     if (fs.grids.empty()) fs.grids.push_back(0.0f);
     return fs;
+}
+
+namespace {
+// Recompute every node box of the BVH from the primitives' current bounds: same topology, same leaves.  Children are
+// stored behind their parent (BvhBuild::build reserves the parent's slot first), so one backward sweep sees every
+// child before its parent.
+void refit_bvh(FlatScene& fs) {
+    const SceneHeader& h = fs.header;
+    float4* nodes = &fs.blob[h.bvh_off];
+    std::vector<Bounds> own(h.n_bvh, BvhBuild::empty());  // unpadded box of each inner node
+    auto child_box = [&](uint32_t ref) {
+        if (!(ref & BVH_LEAF)) return own[ref];
+        Bounds b = BvhBuild::empty();
+        const uint32_t first = ref & 0x00ffffffu, count = (ref >> 24) & 0x7fu;
+        for (uint32_t pos = first; pos < first + count; ++pos) BvhBuild::grow(b, fs.prim_bounds[fs.prim_order[pos]]);
+        return b;
+    };
+    for (uint32_t n = h.n_bvh; n-- > 0;) {
+        float4* q = nodes + (size_t)n * BVH_STRIDE;
+        const uint32_t left = as_u(q[3].x), right = as_u(q[3].y);
+        const Bounds lb = child_box(left), rb = child_box(right);
+        own[n] = lb;
+        BvhBuild::grow(own[n], rb);
+        const Bounds l = BvhBuild::padded(lb), r = BvhBuild::padded(rb);
+        q[0] = f4(l.lo[0], l.lo[1], l.lo[2], l.hi[0]);
+        q[1] = f4(l.hi[1], l.hi[2], r.lo[0], r.lo[1]);
+        q[2] = f4(r.lo[2], r.hi[0], r.hi[1], r.hi[2]);
+    }
+}
+}  // namespace
+
+bool update_flat(FlatScene& fs, const Scene& scene, const std::vector<uint64_t>& refs, std::vector<std::pair<uint32_t, uint32_t> >* dirty,
+                 bool* dist_changed) {
+    *dist_changed = false;
+    SceneHeader& h = fs.header;
+    // the data tables in the order flatten() numbers them
+    std::map<uint64_t, uint32_t> mat_index, vol_index;
+    {
+        uint32_t nm = 0, nv = 0;
+        for (std::map<uint64_t, Data>::const_iterator it = scene.data.begin(); it != scene.data.end(); ++it)
+            if (it->second.kind == DATA_MATERIAL) mat_index[it->first] = nm++; else vol_index[it->first] = nv++;
+    }
+    const EmitCtx ctx = {scene, mat_index, vol_index, fs.accel != ACCEL_LINEAR_FACES && !std::getenv("BT_NO_AA_RECTS")};
+    std::map<uint64_t, uint32_t> index_of;
+    for (uint32_t i = 0; i < fs.object_refs.size(); ++i) index_of[fs.object_refs[i]] = i;
+    if (index_of.size() != scene.objects.size()) return false;
+    // first pass: everything must keep its shape
+    std::vector<std::pair<uint32_t, ObjRecords> > recs;
+    for (size_t k = 0; k < refs.size(); ++k) {
+        std::map<uint64_t, uint32_t>::const_iterator it = index_of.find(refs[k]);
+        if (it == index_of.end()) return false;
+        const uint32_t obj = it->second;
+        const ObjSpan& sp = fs.spans[obj];
+        ObjRecords rec = emit_object(ctx, scene.get_object(refs[k]), obj, sp.first_prim);
+        const bool boxes_used = h.n_bvh == 0 && fs.accel != ACCEL_LINEAR_FACES;
+        if (rec.prims.size() / PRIM_STRIDE != sp.n_prims || rec.is_light != (sp.light >= 0) || sp.cuboid_light || !rec.face_lights.empty() ||
+            (boxes_used && rec.has_box != (sp.box >= 0)))
+            return false;
+        for (uint32_t i = 0; i < sp.n_prims; ++i) {  // a rect that stops (or starts) being axis-aligned changes its record type only
+            const uint32_t pos = fs.where[sp.first_prim + i];
+            const uint32_t was = as_u(fs.blob[h.prim_off + (size_t)pos * PRIM_STRIDE + 4].x) & 3u, is = as_u(rec.prims[(size_t)i * PRIM_STRIDE + 4].x) & 3u;
+            if ((was == PRIM_SPHERE) != (is == PRIM_SPHERE)) return false;
+        }
+        recs.push_back(std::make_pair(obj, rec));
+    }
+    // second pass: overwrite in place
+    for (size_t k = 0; k < recs.size(); ++k) {
+        const uint32_t obj = recs[k].first;
+        const ObjRecords& rec = recs[k].second;
+        const ObjSpan& sp = fs.spans[obj];
+        for (uint32_t i = 0; i < sp.n_prims; ++i) {
+            const uint32_t canon = sp.first_prim + i, pos = fs.where[canon];
+            const size_t at = h.prim_off + (size_t)pos * PRIM_STRIDE;
+            for (int j = 0; j < PRIM_STRIDE; ++j) fs.blob[at + j] = rec.prims[(size_t)i * PRIM_STRIDE + j];
+            if (i == 0 && sp.box >= 0 && h.n_boxes) fs.blob[at + 4].z = as_f((uint32_t)sp.box + 1u);
+            dirty->push_back(std::make_pair((uint32_t)at, (uint32_t)PRIM_STRIDE));
+            fs.prim_bounds[canon] = rec.bounds[i];
+            if (h.lens_skip) {
+                const size_t b = h.bound_off + (size_t)canon * BOUND_STRIDE;
+                fs.blob[b] = f4(rec.bounds[i].lo[0], rec.bounds[i].lo[1], rec.bounds[i].lo[2], 0.0f);
+                fs.blob[b + 1] = f4(rec.bounds[i].hi[0], rec.bounds[i].hi[1], rec.bounds[i].hi[2], 0.0f);
+                dirty->push_back(std::make_pair((uint32_t)b, (uint32_t)BOUND_STRIDE));
+            }
+        }
+        if (sp.box >= 0 && h.n_boxes) {
+            const size_t b = h.box_off + (size_t)sp.box * BOX_STRIDE;
+            for (int j = 0; j < BOX_STRIDE; ++j) fs.blob[b + j] = rec.box[j];
+            dirty->push_back(std::make_pair((uint32_t)b, (uint32_t)BOX_STRIDE));
+        }
+        if (sp.light >= 0) {
+            const size_t l = h.light_off + (size_t)sp.light * LIGHT_STRIDE;
+            for (int j = 0; j < LIGHT_STRIDE; ++j) fs.blob[l + j] = rec.light[j];
+            if (as_u(rec.light[0].z)) fs.blob[l].y = as_f(fs.where[sp.first_prim]);  // lights point at their primitive RECORD
+            dirty->push_back(std::make_pair((uint32_t)l, (uint32_t)LIGHT_STRIDE));
+        }
+    }
+    if (h.n_bvh) {
+        refit_bvh(fs);
+        dirty->push_back(std::make_pair(h.bvh_off, h.n_bvh * (uint32_t)BVH_STRIDE));
+    }
+    if (h.lens_skip == 3) {  // the free-distance grid describes the old geometry: rebuilt (host, tens of ms -- see DESIGN.md)
+        std::vector<float4> canon_prims((size_t)h.n_prims * PRIM_STRIDE);
+        for (uint32_t c = 0; c < h.n_prims; ++c)
+            for (int j = 0; j < PRIM_STRIDE; ++j) canon_prims[(size_t)c * PRIM_STRIDE + j] = fs.blob[h.prim_off + (size_t)fs.where[c] * PRIM_STRIDE + j];
+        if (!build_dist_grid(canon_prims, fs.prim_bounds, h, &fs.dist)) h.lens_skip = 1;
+        *dist_changed = true;
+    }
+    return true;
 }
 
 CameraBlock make_camera_block(const Scene& scene, uint64_t camera_ref, uint32_t width, uint32_t height, uint32_t subsample) {

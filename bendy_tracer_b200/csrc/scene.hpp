@@ -108,6 +108,17 @@ struct Scene {  // reference src/scene/mod.rs:84-90
     void apply_transform(uint64_t object_ref, const Affine& affine);
 };
 
+// where the records of one object live in the flattened scene (update_flat rewrites them in place)
+struct ObjSpan {
+    uint32_t first_prim, n_prims;   // canonical primitive indices
+    int32_t light;                  // index of its record in the light table (-1: not a LIGHT object)
+    int32_t box;                    // index of its BOX record (-1: none)
+    bool cuboid_light;              // a LIGHT Cuboid (face sub-records: not updated in place)
+};
+struct AABB {
+    float lo[3], hi[3];
+};
+
 // The flattened scene: the blob of layout.h + the tables the host keeps.
 struct FlatScene {
     SceneHeader header;
@@ -116,12 +127,22 @@ struct FlatScene {
     std::vector<uint8_t> dist;          // free-distance grid (SceneHeader::dist_*); empty unless header.lens_skip == 3
     std::vector<uint64_t> object_refs;  // object index -> ObjectRef
     std::vector<uint32_t> prim_order;   // record position -> canonical primitive index (identity without a BVH)
+    std::vector<uint32_t> where;        // canonical primitive index -> record position
+    std::vector<ObjSpan> spans;         // per object index
+    std::vector<AABB> prim_bounds;      // world AABB per canonical primitive (BVH refit, free-distance grid)
+    int accel;                          // the mode it was flattened with
     bool diffuse_without_light;         // a Diffuse material is reachable but no LIGHT exists
     bool cuboid_light_without_area;     // a LIGHT Cuboid whose face areas sum to 0: WeightedIndex::new(..).unwrap() panics (cuboid.rs:49)
 };
 // accel: 0 = automatic (BVH above BVH_AUTO_PRIMS primitives), 1 = linear scan, 2 = BVH
 enum { ACCEL_AUTO = 0, ACCEL_LINEAR = 1, ACCEL_BVH = 2, ACCEL_LINEAR_FACES = 3, BVH_AUTO_PRIMS = 64 };
 FlatScene flatten(const Scene& scene, int accel = ACCEL_AUTO);
+// Transform-only edits (Object::apply_transform, UpdateQueue::commit -- reference src/scene/mod.rs:154-239): rewrite the records
+// of the objects `refs` in place, REFIT the BVH (same topology, new boxes) and list the blob ranges that changed
+// (float4 offset, count).  Returns false -- and leaves `fs` untouched -- when the edit changes the layout (a cuboid that stops
+// being a box, a LIGHT Cuboid, ...): the caller flattens from scratch.  `dist_changed`: the free-distance grid was rebuilt.
+bool update_flat(FlatScene& fs, const Scene& scene, const std::vector<uint64_t>& refs, std::vector<std::pair<uint32_t, uint32_t> >* dirty,
+                 bool* dist_changed);
 
 // Uniform<f32>::new / new_inclusive scale (rand 0.8.5 UniformFloat) -- host-side constants
 float uniform_scale(float low, float high);

@@ -154,6 +154,11 @@ int bt_scene_set_camera_aspect(bt_scene* scene, uint64_t camera_ref, float aspec
  * src/scene/object/mod.rs:212-223, src/scene/mod.rs:204-213): local = local * affine, world and
  * the children's parent transforms are re-derived, device buffers are re-flattened lazily. */
 int bt_scene_apply_transform(bt_scene* scene, uint64_t object_ref, const float affine[12]);
+/* UpdateQueue::commit (reference src/scene/mod.rs:204-213): applies the edits queued since the last render to the flattened
+ * scene on the host.  Transform edits are applied IN PLACE -- the records of the moved objects are rewritten, the BVH is refit
+ * (same topology, new boxes), and the next render uploads only those ranges -- unless an edit changes the layout (then, as for
+ * every other kind of edit, the scene is flattened from scratch).  Optional: the next render call commits what is pending. */
+int bt_scene_commit(bt_scene* scene);
 /* lens field: n point masses (x, y, z, r_s); cfg may be NULL for the defaults */
 int bt_scene_set_lenses(bt_scene* scene, const float* xyzr, uint32_t n, const bt_lens_config* cfg);
 void bt_lens_config_default(bt_lens_config* cfg);
