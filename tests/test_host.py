@@ -390,3 +390,42 @@ def test_reference_patch_is_well_formed():
             r = subprocess.run(["patch", "-p1", "--dry-run", "-i", os.path.join(ROOT, "patches", "bendy_tracer_b200.patch")],
                                cwd=tmp, capture_output=True, text=True)
             assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_json_nesting_limit_is_an_error_not_a_crash():
+    """serde_json stops at 128 nested arrays / objects with an error; so does the loader (a scene file is untrusted input:
+    100 000 '[' must not overflow the host stack)"""
+    for text in ("[" * 100000, "{\"a\":" * 5000 + "1" + "}" * 5000, "[" * 129 + "]" * 129):
+        with pytest.raises(bt.BendyError) as e:
+            bt.Scene.from_json(text)
+        assert e.value.code == _ffi.ERR_PARSE
+    ok = "[" * 100 + "]" * 100          # within the limit: parses (and is then rejected as a scene, not as JSON)
+    with pytest.raises(bt.BendyError) as e:
+        bt.Scene.from_json(ok)
+    assert "recursion" not in str(e.value)
+
+
+def test_bvh_build_survives_skewed_and_coincident_primitives():
+    """200 spheres on one spot and a geometric cluster that makes every SAH split lopsided: the builder falls back to
+    median splits near its depth budget instead of rejecting the scene (flattening happens at load: no GPU needed)"""
+    from common import synthetic_scene
+    doc = synthetic_scene(0, 0, 0, seed=3)
+    objs = doc["objects"]["collection"]
+    key = doc["objects"]["next_key"]
+    proto = objs["2"]
+    for i in range(400):
+        o = json.loads(json.dumps(proto))
+        o["object_ref"] = key
+        o["flags"] = {"bits": 0}
+        o["inner"]["Sphere"]["radius"] = 0.01
+        t = o["transform"]["transform_world"]
+        x = 0.0 if i < 200 else float(np.float32(2.0 ** -(i - 200) * 8.0))      # coincident, then geometrically spaced
+        t[9:12] = [x, 0.5, 0.0]
+        o["transform"]["transform_local"] = list(t)
+        objs[str(key)] = o
+        key += 1
+    doc["objects"]["next_key"] = key
+    sc = bt.Scene.from_json(json.dumps(doc))
+    sc.set_accel("bvh")
+    info = sc.info()
+    assert info["n_primitives"] == 402 and info["n_bvh_nodes"] > 10

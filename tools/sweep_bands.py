@@ -1,4 +1,4 @@
-"""Host-buffer render (bt_render, BT_MEM_HOST) against the number of pipeline bands (env BT_HOST_BANDS)."""
+"""Host-buffer render (bt_render, BT_MEM_HOST) against the number of pipeline bands (tuning knob host_bands)."""
 import os, sys, time
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
@@ -20,10 +20,7 @@ for name, w, h, passes in (("cornell2", 1920, 1080, 64), ("cornell", 512, 512, 4
     e0.record(); tracer.render(scene, cam, rc, dev, sync=False); e1.record(); torch.cuda.synchronize()
     line = [f"{name} {w}x{h}x{passes * 4}: device {e0.elapsed_time(e1):7.2f} ms"]
     for bands in ("1", "2", "4", "8", "16", ""):
-        if bands:
-            os.environ["BT_HOST_BANDS"] = bands
-        else:
-            os.environ.pop("BT_HOST_BANDS", None)
+        bt.Engine.default(0).set_tuning(host_bands=int(bands) if bands else None)   # (knobs are read per engine, not per call)
         tracer.render(scene, cam, rc, hb)
         best = 1e9
         for i in range(3):
