@@ -130,6 +130,46 @@ static bool use_exact(const bt_engine*, const bt_scene* s) {
     return s->precision == BT_PRECISION_EXACT;
 }
 
+// The cells of the free-distance grid (layout.h: SceneHeader::dist_*; scene.cpp: build_dist_grid lays the grid out and holds
+// the host version of exactly this arithmetic -- this file is compiled -fmad=false, so the two agree bit for bit).  One thread
+// per cell: the lower bound, over all points of the cell, of the distance to the nearest primitive surface (spheres exactly,
+// everything else through its world AABB -- the bound records of the blob), minus the rounding margins of the hit tests,
+// in quanta of dist_q, rounded down.
+__global__ void __launch_bounds__(256) dist_grid_kernel(const float4* __restrict__ blob, const SceneHeader h, uint8_t* __restrict__ out) {
+    const uint64_t n_cells = (uint64_t)h.dist_nx * h.dist_ny * h.dist_nz;
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_cells) return;
+    const uint32_t x = (uint32_t)(idx % h.dist_nx), y = (uint32_t)((idx / h.dist_nx) % h.dist_ny), z = (uint32_t)(idx / ((uint64_t)h.dist_nx * h.dist_ny));
+    const double cell = (double)h.dist_cell;
+    const double half_diag = 0.5 * sqrt(3.0) * cell * 1.01 + 1e-5;
+    const double c[3] = {h.dist_lo[0] + (x + 0.5) * cell, h.dist_lo[1] + (y + 0.5) * cell, h.dist_lo[2] + (z + 0.5) * cell};
+    const double l1 = fabs(c[0]) + fabs(c[1]) + fabs(c[2]) + 3.0 * half_diag;
+    double best = 1e30;
+    for (uint32_t i = 0; i < h.n_prims; ++i) {
+        const float4* rec = blob + h.prim_off + (size_t)i * PRIM_STRIDE;
+        double b;
+        if ((__float_as_uint(rec[4].x) & 3u) == PRIM_SPHERE) {
+            const float4 q0 = rec[0];
+            const double dx = c[0] - q0.x, dy = c[1] - q0.y, dz = c[2] - q0.z, r = q0.w;
+            const double dc = sqrt(dx * dx + dy * dy + dz * dz), dmax = dc + half_diag;
+            b = fabs(dc - r) - (dmax * dmax * (double)rec[1].z + 2e-5 * (dmax + r) + 1e-6);
+        } else {
+            const float4 lo = blob[h.bound_off + (size_t)i * BOUND_STRIDE], hi = blob[h.bound_off + (size_t)i * BOUND_STRIDE + 1];
+            const float blo[3] = {lo.x, lo.y, lo.z}, bhi[3] = {hi.x, hi.y, hi.z};
+            double d2 = 0.0, ext = 0.0;
+            for (int k = 0; k < 3; ++k) {
+                const double d = fmax(fmax((double)blo[k] - c[k], c[k] - (double)bhi[k]), 0.0);
+                d2 += d * d;
+                ext += fabs((double)bhi[k] - (double)blo[k]);
+            }
+            b = sqrt(d2) - (1e-4 * (l1 + ext + sqrt(d2)) + 1e-4);
+        }
+        best = fmin(best, b);
+    }
+    const double v = floor((best - half_diag) / (double)h.dist_q);
+    out[idx] = (uint8_t)fmin(fmax(v, 0.0), 255.0);
+}
+
 namespace {
 
 int ensure_scratch(bt_engine* e, size_t bytes) {
@@ -143,6 +183,28 @@ int ensure_scratch(bt_engine* e, size_t bytes) {
 }
 
 // Brings the scene's copy on the CURRENT device (cudaSetDevice done by the caller) up to date; *out = that copy.
+// the free-distance grid of this device copy: filled by dist_grid_kernel from the blob just uploaded (or copied, when the host
+// filled it: BT_DIST_GRID_HOST)
+int upload_dist_grid(bt_scene* s, SceneDev* d, cudaStream_t stream) {
+    const SceneHeader& h = s->flat.header;
+    if (h.lens_skip != 3) return BT_OK;
+    const size_t db = (size_t)h.dist_nx * h.dist_ny * h.dist_nz;
+    if (db > d->dist_cap) {
+        if (d->d_dist) cudaFree(d->d_dist);
+        d->d_dist = 0;
+        d->dist_cap = 0;
+        CK(cudaMalloc((void**)&d->d_dist, db));
+        d->dist_cap = db;
+    }
+    if (!s->flat.dist.empty()) {
+        CK(cudaMemcpyAsync(d->d_dist, s->flat.dist.data(), db, cudaMemcpyHostToDevice, stream));
+    } else {
+        dist_grid_kernel<<<(unsigned)((db + 255) / 256), 256, 0, stream>>>(d->d_blob, h, d->d_dist);
+        CK(cudaGetLastError());
+    }
+    return BT_OK;
+}
+
 // the host half of a scene update: from scratch, or -- for transform edits -- in place (update_flat: records rewritten, BVH refit)
 void commit_scene(bt_scene* s) {
     if (!s->flat_dirty && !s->pending.empty()) {
@@ -193,15 +255,8 @@ int refresh_scene(bt_scene* s, int device, cudaStream_t stream, SceneDev** out) 
         for (const std::pair<uint32_t, uint32_t>& r : s->patch)
             CK(cudaMemcpyAsync(d->d_blob + r.first, s->flat.blob.data() + r.first, (size_t)r.second * sizeof(float4), cudaMemcpyHostToDevice, stream));
         if (s->patch_dist) {
-            const size_t db = s->flat.dist.size();
-            if (db > d->dist_cap) {
-                if (d->d_dist) cudaFree(d->d_dist);
-                d->d_dist = 0;
-                d->dist_cap = 0;
-                CK(cudaMalloc((void**)&d->d_dist, db));
-                d->dist_cap = db;
-            }
-            if (db) CK(cudaMemcpyAsync(d->d_dist, s->flat.dist.data(), db, cudaMemcpyHostToDevice, stream));
+            int rc = upload_dist_grid(s, d, stream);
+            if (rc != BT_OK) return rc;
         }
         CK(cudaStreamSynchronize(stream));
         d->version = s->flat_version;
@@ -226,15 +281,10 @@ int refresh_scene(bt_scene* s, int device, cudaStream_t stream, SceneDev** out) 
         }
         CK(cudaMemcpyAsync(d->d_blob, s->flat.blob.data(), bb, cudaMemcpyHostToDevice, stream));
         CK(cudaMemcpyAsync(d->d_grids, s->flat.grids.data(), gb, cudaMemcpyHostToDevice, stream));
-        const size_t db = s->flat.dist.size();
-        if (db > d->dist_cap) {
-            if (d->d_dist) cudaFree(d->d_dist);
-            d->d_dist = 0;
-            d->dist_cap = 0;
-            CK(cudaMalloc((void**)&d->d_dist, db));
-            d->dist_cap = db;
+        {
+            int rc = upload_dist_grid(s, d, stream);
+            if (rc != BT_OK) return rc;
         }
-        if (db) CK(cudaMemcpyAsync(d->d_dist, s->flat.dist.data(), db, cudaMemcpyHostToDevice, stream));
         CK(cudaStreamSynchronize(stream));  // the host vectors may change after we return
         d->version = s->flat_version;
     }

@@ -97,7 +97,7 @@ struct SceneHeader {
     // tests.  The box spans every primitive but the `n_far` scene-spanning spheres listed in far_prim, with dist_pad to spare:
     // outside it the bound is min(distance to the box + dist_pad, exact distance to those spheres).
     float dist_lo[3], dist_hi[3];
-    float dist_inv_cell, dist_q, dist_pad;
+    float dist_cell, dist_inv_cell, dist_q, dist_pad;
     uint32_t dist_nx, dist_ny, dist_nz;
     uint32_t n_far;
     int32_t far_prim[2];

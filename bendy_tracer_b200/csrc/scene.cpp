@@ -1161,7 +1161,7 @@ ObjRecords emit_object(const EmitCtx& ctx, const Object& o, uint32_t obj, uint32
 // left out of the BOX (the cells inside it account for them like for every other primitive) and evaluated exactly for
 // points outside it.  Returns false (the per-flight scheme stays) when there are
 // more, or nothing to put in a grid.
-bool build_dist_grid(const std::vector<float4>& prims, const std::vector<Bounds>& bounds, SceneHeader& h, std::vector<uint8_t>* out) {
+bool build_dist_grid(const std::vector<float4>& prims, const std::vector<Bounds>& bounds, SceneHeader& h, std::vector<uint8_t>* out, bool fill) {
     const uint32_t n = h.n_prims;
     if (n == 0 || bounds.size() < n) return false;
     std::vector<float> size(n);
@@ -1210,8 +1210,11 @@ bool build_dist_grid(const std::vector<float4>& prims, const std::vector<Bounds>
     const float q = 0.5f * cell;
     // a point is binned with float arithmetic and may land one ulp into the neighbouring cell: the half diagonal is padded
     const double half_diag = 0.5 * std::sqrt(3.0) * (double)cell * 1.01 + 1e-5;
-    out->assign((size_t)dims[0] * dims[1] * dims[2], 0);
-    for (uint32_t z = 0; z < dims[2]; ++z)
+    // The cells are normally filled ON THE DEVICE (engine.cu: dist_grid_kernel, the same arithmetic in the same order, one thread
+    // per cell: a 2M-cell grid takes 65 - 140 ms here and well under a millisecond there); BT_DIST_GRID_HOST=1 fills them here.
+    out->clear();
+    if (fill) out->assign((size_t)dims[0] * dims[1] * dims[2], 0);
+    for (uint32_t z = 0; fill && z < dims[2]; ++z)
         for (uint32_t y = 0; y < dims[1]; ++y)
             for (uint32_t x = 0; x < dims[0]; ++x) {
                 const double c[3] = {box.lo[0] + (x + 0.5) * (double)cell, box.lo[1] + (y + 0.5) * (double)cell, box.lo[2] + (z + 0.5) * (double)cell};
@@ -1244,6 +1247,7 @@ bool build_dist_grid(const std::vector<float4>& prims, const std::vector<Bounds>
         h.dist_lo[k] = box.lo[k];
         h.dist_hi[k] = box.lo[k] + (float)dims[k] * cell;
     }
+    h.dist_cell = cell;
     h.dist_inv_cell = 1.0f / cell;
     h.dist_q = q;
     h.dist_pad = pad;
@@ -1452,7 +1456,7 @@ FlatScene flatten(const Scene& scene, int accel) {
             fs.blob.push_back(f4(bounds[i].lo[0], bounds[i].lo[1], bounds[i].lo[2], 0.0f));
             fs.blob.push_back(f4(bounds[i].hi[0], bounds[i].hi[1], bounds[i].hi[2], 0.0f));
         }
-        if (!std::getenv("BT_NO_DIST_GRID") && build_dist_grid(prims, bounds, h, &fs.dist)) h.lens_skip = 3;
+        if (!std::getenv("BT_NO_DIST_GRID") && build_dist_grid(prims, bounds, h, &fs.dist, std::getenv("BT_DIST_GRID_HOST") != 0)) h.lens_skip = 3;
     }
     h.bvh_off = (uint32_t)fs.blob.size();
     h.n_bvh = (uint32_t)(nodes.size() / BVH_STRIDE);
@@ -1579,7 +1583,7 @@ bool update_flat(FlatScene& fs, const Scene& scene, const std::vector<uint64_t>&
         std::vector<float4> canon_prims((size_t)h.n_prims * PRIM_STRIDE);
         for (uint32_t c = 0; c < h.n_prims; ++c)
             for (int j = 0; j < PRIM_STRIDE; ++j) canon_prims[(size_t)c * PRIM_STRIDE + j] = fs.blob[h.prim_off + (size_t)fs.where[c] * PRIM_STRIDE + j];
-        if (!build_dist_grid(canon_prims, fs.prim_bounds, h, &fs.dist)) h.lens_skip = 1;
+        if (!build_dist_grid(canon_prims, fs.prim_bounds, h, &fs.dist, std::getenv("BT_DIST_GRID_HOST") != 0)) h.lens_skip = 1;
         *dist_changed = true;
     }
     return true;

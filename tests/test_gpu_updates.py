@@ -120,3 +120,38 @@ def test_update_that_changes_the_layout_falls_back():
     assert sc.info()["n_boxes"] == 1
     fresh = _fresh_copy(sc)
     assert np.array_equal(got, _render(fresh, cam, w, h))
+
+
+@pytest.mark.parametrize("name,lens", [("scene", LENS_SCENE), ("cornell2", np.array([[0.3, 2.2, 2.0, 0.1]], np.float32))])
+def test_free_distance_grid_device_build_equals_host_build(name, lens, monkeypatch):
+    """the free-distance grid is filled by a kernel from the uploaded scene (one thread per cell); BT_DIST_GRID_HOST=1 fills it
+    on the host with the same arithmetic.  Same grid => the same chords are skipped: identical work counters (intersection
+    passes, RK4 steps) and identical images -- before and after a transform edit (which re-plans and refills the grid)."""
+    import bendy_tracer_b200 as bt
+    import oracle_ffi as O
+    w, h = 128, 72
+    out = {}
+    for mode in ("device", "host"):
+        if mode == "host":
+            monkeypatch.setenv("BT_DIST_GRID_HOST", "1")
+        else:
+            monkeypatch.delenv("BT_DIST_GRID_HOST", raising=False)
+        sc = bt.Scene.load(O.scene_path(name))
+        cam = sc.find_by_tag("camera")
+        sc.set_camera_aspect(cam, float(np.float32(w) / np.float32(h)))
+        sc.set_lenses(lens)
+        tr = bt.Tracer(bt.Config(), seed=8)
+        rc = bt.RenderConfig.with_samples_subsample(2, bt.Subsample(2))
+        img0, st0 = _render(sc, cam, w, h), tr.render_stats(sc, cam, rc, w, h)
+        sc.apply_transform(2, _translate(0.2, 0.1, -0.3))
+        t0 = time.perf_counter()
+        sc.commit()
+        t_commit = time.perf_counter() - t0
+        img1, st1 = _render(sc, cam, w, h), tr.render_stats(sc, cam, rc, w, h)
+        out[mode] = (img0, st0, img1, st1, t_commit)
+    for k in (0, 2):
+        assert np.array_equal(out["device"][k], out["host"][k])
+    assert out["device"][1] == out["host"][1] and out["device"][3] == out["host"][3]
+    assert out["device"][1]["scans"] < 0.2 * out["device"][1]["rk4_steps"]           # (and the grid does skip chords: most RK4 steps need no intersection pass)
+    print(f"{name}: commit of one moved object under a lens field: grid on the device {out['device'][4] * 1e3:.2f} ms, on the host {out['host'][4] * 1e3:.1f} ms")
+    assert out["device"][4] < 0.2 * out["host"][4]
