@@ -1,20 +1,19 @@
 #!/bin/bash
-# 8-GPU box: multi-GPU correctness check, weak scaling of the C2 step, strong scaling of the C5 frame.
-TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+# Strong scaling of the C5 frame on one 8 x B200 box: C5-64 at N = 1, 2, 4, 8 (torchrun, NCCL), N = 8 in one process through
+# bt_engine_create_multi, and the full BASELINE configs[4] frame (1024 spp) once at N = 8.
 mkdir -p gpurun_out
-$TR --master-port 29511 --nproc-per-node 8 tools/check_multi_gpu.py > gpurun_out/mgpu_check8.log 2>&1
-$TR --master-port 29512 --nproc-per-node 8 bench.py --gpus 8 --steps 3 --warmup 3 --no-extras > gpurun_out/scale_s3_C2_8.json 2> gpurun_out/scale_s3_C2_8.err
-python bench.py --gpus 1 --workload C5-128 --steps 1 --warmup 1 --no-extras > gpurun_out/scale_s3_C5q_1.json 2> gpurun_out/scale_s3_C5q_1.err
-port=29520
-for n in 2 4 8; do
-  port=$((port+1))
-  $TR --master-port $port --nproc-per-node $n bench.py --gpus $n --workload C5-128 --steps 1 --warmup 1 --no-extras > gpurun_out/scale_s3_C5q_$n.json 2> gpurun_out/scale_s3_C5q_$n.err
+for n in 8 4 2; do
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29520 + n)) bench.py --gpus $n --steps 5 --warmup 3 --no-extras > gpurun_out/final_scale_n$n.json 2> gpurun_out/final_scale_n$n.err
 done
-$TR --master-port 29530 --nproc-per-node 8 bench.py --gpus 8 --workload C5 --steps 1 --warmup 1 --no-extras > gpurun_out/scale_s3_C5_8.json 2> gpurun_out/scale_s3_C5_8.err
-cat gpurun_out/mgpu_check8.log | tail -4
-for f in gpurun_out/scale_s3_*.json; do echo $f; python -c "
-import json,sys
-try:
-    d=json.load(open('$f')); print(d['n_gpus'], d['scaling'], round(d['value'],1), 'Ms/s', round(d['ms_per_step'],1), 'ms', d['config']['workload'][:60])
-except Exception as e: print('ERR', e)
-"; done
+python bench.py --workload C5-64 --steps 3 --warmup 3 --no-extras > gpurun_out/final_scale_n1.json 2> gpurun_out/final_scale_n1.err
+python bench.py --gpus 8 --steps 5 --warmup 3 --no-extras > gpurun_out/final_scale_n8_inproc.json 2> gpurun_out/final_scale_n8_inproc.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29540 bench.py --gpus 8 --workload C5 --steps 2 --warmup 1 --no-extras > gpurun_out/final_scale_C5_full_n8.json 2> gpurun_out/final_scale_C5_full_n8.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --impl reference --gpus 8 --steps 2 --warmup 1 > gpurun_out/final_scale_ref_n8.json 2> gpurun_out/final_scale_ref_n8.err
+timeout 300 python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -2
+python - <<PY
+import json
+for f in ("final_scale_n1","final_scale_n2","final_scale_n4","final_scale_n8","final_scale_n8_inproc","final_scale_C5_full_n8","final_scale_ref_n8"):
+    try:
+        d=json.load(open("gpurun_out/%s.json"%f)); print(f, {k:d.get(k) for k in ("value","ms_per_step","n_gpus","reduce_ms")}, "e2e", d["e2e"]["value"], d.get("clocks"))
+    except Exception as e: print(f, "ERR", e)
+PY
