@@ -921,8 +921,12 @@ BT_DEV V3 lens_accel(const L& lens, D0Cache<L>& cache, V3 x, float a, V3 w, V3 v
             if (INFO >= 2) {
                 const float4 e1 = lens.e1(m);  // (r_s, r_far * r_s, -, -)
                 if (r < e1.x) captured = true;
-                float dv = fmaf(dz, v.z, fmaf(dy, v.y, dx * v.x));
-                if (!(r > e1.y && dv > 0.0f)) far = false;
+                if (r > e1.y) {  // beyond r_far of this mass (rare): receding?
+                    const float dv = fmaf(dz, v.z, fmaf(dy, v.y, dx * v.x));
+                    if (!(dv > 0.0f)) far = false;
+                } else {
+                    far = false;
+                }
             }
         }
     }

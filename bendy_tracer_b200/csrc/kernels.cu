@@ -162,7 +162,9 @@ BT_DEV int geodesic_step(const RenderParams& p, const L& lens, const float4* pri
     const V3 k1 = lens_accel<2, EXACT, 0>(lens, cache, x, 0.0f, v, v, rmin, captured, far);
     if (captured) return FL_CAPTURED;
     if (far) return FL_PEND_FAR;
-    const V3 x0 = x;
+    // the chord's start is kept where a pending chord needs it (f.xp): the step writes the new position into x and nothing
+    // is copied afterwards, whatever the chord turns out to be
+    f.xp = x;
     float free = f.free;
     GridFetch gf;
     gf.raw = 0;
@@ -172,16 +174,16 @@ BT_DEV int geodesic_step(const RenderParams& p, const L& lens, const float4* pri
     // wavefronts per warp instruction and made the step L1-bound (C3: -6 %); a quarter of the lanes is not.
     const bool grid = p.scene.lens_skip == 3, refresh = grid && free <= 1.4f * f.rest;
     if (grid) {
-        if (refresh) gf = grid_bound_fetch(p, prims, x0);
+        if (refresh) gf = grid_bound_fetch(p, prims, f.xp);
     } else if ((C & CT_SPHERES) && f.near >= 0) {
         const float4* q = prims + f.near * PRIM_STRIDE;
         const float4 q0 = q[0], q1 = q[1];
-        const V3 oc = x0 - v3(q0);
+        const V3 oc = f.xp - v3(q0);
         free = fminf(sphere_free_bound(q0, q1, fmaf(oc.z, oc.z, fmaf(oc.y, oc.y, oc.x * oc.x))), f.rest);
     }
     rk4_from_k1<EXACT>(lens, cache, x, v, k1, step_size(p.scene.kappa, p.scene.h_min, p.scene.h_max, rmin));
     float len;
-    (void)normalize_fma<EXACT>(x - x0, &len);
+    (void)normalize_fma<EXACT>(x - f.xp, &len);
     if (refresh) free = fmaxf(free, grid_bound_finish(p, gf, len));
     if (len * 1.02f < free) {  // nothing within reach: the chord needs no intersection test
         f.free = free - len;
@@ -190,7 +192,6 @@ BT_DEV int geodesic_step(const RenderParams& p, const L& lens, const float4* pri
         f.steps++;
         return (f.travelled >= tmax || f.steps >= p.scene.max_steps) ? FL_ESCAPED : FL_FLY;
     }
-    f.xp = x0;
     return FL_PEND;
 }
 // INTERSECTION phase: the pending chord (or the final straight segment) against the scene; the
