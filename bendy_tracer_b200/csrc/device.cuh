@@ -538,20 +538,22 @@ BT_DEV Hit scan_prims(const float4* prims, const float4* boxes, int n_prims, V3 
 }
 
 // Closest hit through the BVH (extension; scenes above the linear-scan budget).  Records and
-// nodes are read from global memory (L2 / HBM), the traversal stack lives in shared memory
-// (stack[level * blockDim.x + tid]: conflict-free).  Same per-primitive tests as the scan; an
-// exact-distance tie is decided by the canonical primitive index exactly as the reference's
-// scan order would: the later record wins unless it is a cuboid face (strict '<', cuboid.rs:97).
-BT_DEV float slab(float lx, float ly, float lz, float hx, float hy, float hz, V3 o, V3 inv, float tmin, float tmax, bool& hit) {
+// nodes are read from global memory (L1 / L2), the traversal stack lives in shared memory
+// (stack[level * blockDim.x + tid]: conflict-free; levels >= BVH_STACK_SMEM, rarely reached, in local
+// memory).  Same per-primitive tests as the scan; an exact-distance tie is decided by the canonical
+// primitive index exactly as the reference's scan order would: the later record wins unless it is a
+// cuboid face (strict '<', cuboid.rs:97).
+// entry distance of the ray into one child box of a 4-wide node, +inf when it misses
+BT_DEV float slab(float lx, float hx, float ly, float hy, float lz, float hz, V3 o, V3 inv, float tmin, float tmax) {
     const float tx0 = (lx - o.x) * inv.x, tx1 = (hx - o.x) * inv.x;
     const float ty0 = (ly - o.y) * inv.y, ty1 = (hy - o.y) * inv.y;
     const float tz0 = (lz - o.z) * inv.z, tz1 = (hz - o.z) * inv.z;
     const float tnear = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
     const float tfar = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tmax));
-    hit = tnear <= tfar * 1.00001f + 1e-6f;  // inclusive and slightly generous: never cull a scan hit
-    return tnear;
+    // inclusive and slightly generous: never cull a scan hit
+    return tnear <= tfar * 1.00001f + 1e-6f ? tnear : __int_as_float(0x7f800000);
 }
-// A closest-hit traversal in progress (resumable: the render kernel advances all lanes of a warp one
+// A closest-hit traversal in progress (resumable: the render kernel advances the lanes of a warp one
 // unit at a time and leaves the loop when enough of them are done -- step compaction, as for the
 // geodesic flights).
 struct BvhTrav {
@@ -560,6 +562,26 @@ struct BvhTrav {
     int best_canon;
     bool best_strict;
 };
+// Where one traversal keeps its stack: levels < k in shared memory (entry `level * stride + idx`, the entry
+// distances k * stride words further), the rarely reached rest in `over` (local memory in the lane kernel, a
+// global arena in the pooled one).
+struct BvhStack {
+    uint32_t* base;
+    uint32_t stride, idx, k;
+    uint2* over;
+};
+struct BvhSpill {  // stack levels BVH_STACK_SMEM .. BVH_STACK - 1 of one lane
+    uint2 e[BVH_STACK - BVH_STACK_SMEM];
+};
+BT_DEV BvhStack bvh_lane_stack(uint32_t* stack, BvhSpill& spill) {
+    BvhStack s;
+    s.base = stack;
+    s.stride = blockDim.x;
+    s.idx = threadIdx.x;
+    s.k = BVH_STACK_SMEM;
+    s.over = spill.e;
+    return s;
+}
 enum : uint32_t { BVH_DONE = 0xffffffffu };  // (leaf bit set: ends the descent loop)
 BT_DEV void bvh_begin(BvhTrav& t, float tmax) {
     t.cur = 0;  // node 0 is always an inner node
@@ -570,85 +592,119 @@ BT_DEV void bvh_begin(BvhTrav& t, float tmax) {
     t.best_canon = -1;
     t.best_strict = false;
 }
-// One unit of "while-while" traversal: descend inner nodes until a leaf is held, test the leaf, pop.
-// Inside a warp the two phases never interleave, which keeps it converged for incoherent rays.
-// Returns true when the traversal is complete (t.h is the closest hit).
-template <bool FLIGHT = false>
-BT_DEV bool bvh_unit(BvhTrav& t, const float4* __restrict__ prims, const float4* __restrict__ nodes, uint32_t* stack, V3 o, V3 d,
-                     float tmin) {
-    const V3 inv = v3(m_rcp(d.x), m_rcp(d.y), m_rcp(d.z));
-    const uint32_t lanes = blockDim.x, tid = threadIdx.x;
-    float* stack_t = reinterpret_cast<float*>(stack + BVH_STACK * lanes);
-    uint32_t cur = t.cur, sp = t.sp;
-    // pop, skipping subtrees that start beyond the hit found since they were pushed
-#define BT_BVH_POP()                                         \
-    for (;;) {                                               \
-        if (sp == 0) {                                       \
-            cur = BVH_DONE;                                  \
-            break;                                           \
-        }                                                    \
-        --sp;                                                \
-        cur = stack[sp * lanes + tid];                       \
-        if (stack_t[sp * lanes + tid] <= t.h.t) break;       \
+BT_DEV void bvh_push(BvhTrav& t, const BvhStack& st, uint32_t ref, float tn) {
+    if (t.sp < st.k) {
+        st.base[t.sp * st.stride + st.idx] = ref;
+        st.base[(st.k + t.sp) * st.stride + st.idx] = __float_as_uint(tn);
+    } else {
+        st.over[t.sp - st.k] = make_uint2(ref, __float_as_uint(tn));
     }
-    while (!(cur & BVH_LEAF)) {
-        const float4* n = nodes + cur * BVH_STRIDE;
-        const float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3);
-        bool hl, hr;
-        const float tl = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, tmin, t.h.t, hl);
-        const float tr = slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, tmin, t.h.t, hr);
-        const uint32_t left = __float_as_uint(n3.x), right = __float_as_uint(n3.y);
-        if (hl && hr) {
-            const bool left_first = tl <= tr;
-            stack[sp * lanes + tid] = left_first ? right : left;
-            stack_t[sp * lanes + tid] = left_first ? tr : tl;
-            ++sp;
-            cur = left_first ? left : right;
-        } else if (hl || hr) {
-            cur = hl ? left : right;
+    ++t.sp;
+}
+// pop, skipping subtrees that start beyond the hit found since they were pushed
+BT_DEV uint32_t bvh_pop(BvhTrav& t, const BvhStack& st) {
+    uint32_t sp = t.sp, cur = BVH_DONE;
+    while (sp != 0) {
+        --sp;
+        uint32_t ref, tn;
+        if (sp < st.k) {
+            ref = st.base[sp * st.stride + st.idx];
+            tn = st.base[(st.k + sp) * st.stride + st.idx];
         } else {
-            BT_BVH_POP()
+            const uint2 e = st.over[sp - st.k];
+            ref = e.x;
+            tn = e.y;
+        }
+        if (__uint_as_float(tn) <= t.h.t) {
+            cur = ref;
+            break;
         }
     }
-    if (cur != BVH_DONE) {
-        const uint32_t first = cur & 0x00ffffffu, count = (cur >> 24) & 0x7fu;
-        for (uint32_t i = first; i < first + count; ++i) {
-            const float4* q = prims + i * PRIM_STRIDE;
-            const int meta = __float_as_int(__ldg(q + 4).x);
-            const int type = meta & 3, canon = meta >> PRIM_CANON_SHIFT;
-            const bool strict = type == PRIM_CUBOID_FACE;
-            float tt;
-            bool front = true, ok;
-            if (type == PRIM_SPHERE)
-                ok = sphere_roots<FLIGHT>(__ldg(q), __ldg(q + 1).x, o, d, tmin, t.h.t, tt);
-            else
-                ok = rect_test(q, o, d, tmin, t.h.t, false, tt, front);
-            if (ok) {
-                // tt <= h.t here.  Equal distance: the later canonical index wins unless strict.
-                bool take = tt < t.h.t;
-                if (!take) take = canon > t.best_canon ? !strict : t.best_strict;
-                if (take) {
-                    t.h.t = tt;
-                    t.h.prim = (int)i;
-                    t.h.face = type == PRIM_SPHERE ? 8 : (front ? 0 : 1);
-                    t.best_canon = canon;
-                    t.best_strict = strict;
-                }
+    t.sp = sp;
+    return cur;
+}
+// The traversal in two kinds of unit, so that a warp can run each kind with the lanes that want it
+// (render_body picks the kind more lanes are waiting for; bvh_closest just alternates them):
+// bvh_node visits ONE 4-wide inner node (four slab tests off one 128-byte fetch; descend into the
+// nearest child hit, push the others far-to-near, or pop), bvh_leaf tests the records of the leaf held in
+// t.cur and pops.  t.cur == BVH_DONE when the traversal is complete (t.h is the closest hit).
+#define BT_BVH_CSWAP(ta, ra, tb, rb)            \
+    {                                           \
+        const bool sw = tb < ta;                \
+        const float tlo = sw ? tb : ta;         \
+        const uint32_t rlo = sw ? rb : ra;      \
+        tb = sw ? ta : tb;                      \
+        rb = sw ? ra : rb;                      \
+        ta = tlo;                               \
+        ra = rlo;                               \
+    }
+BT_DEV void bvh_node(BvhTrav& t, const float4* __restrict__ nodes, const BvhStack& st, V3 o, V3 inv, float tmin) {
+    const float inf = __int_as_float(0x7f800000);
+    const float4* n = nodes + t.cur * BVH_STRIDE;
+    const float4 lx = __ldg(n), hx = __ldg(n + 1), ly = __ldg(n + 2), hy = __ldg(n + 3), lz = __ldg(n + 4), hz = __ldg(n + 5);
+    const float4 rf = __ldg(n + 6);
+    uint32_t r0 = __float_as_uint(rf.x), r1 = __float_as_uint(rf.y), r2 = __float_as_uint(rf.z), r3 = __float_as_uint(rf.w);
+    float t0 = slab(lx.x, hx.x, ly.x, hy.x, lz.x, hz.x, o, inv, tmin, t.h.t);
+    float t1 = slab(lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, o, inv, tmin, t.h.t);
+    float t2 = r2 != BVH_EMPTY ? slab(lx.z, hx.z, ly.z, hy.z, lz.z, hz.z, o, inv, tmin, t.h.t) : inf;
+    float t3 = r3 != BVH_EMPTY ? slab(lx.w, hx.w, ly.w, hy.w, lz.w, hz.w, o, inv, tmin, t.h.t) : inf;
+    if (r1 == BVH_EMPTY) t1 = inf;  // (a node has at least one child; empty slots come last)
+    // nearest first (misses, at +inf, sort last)
+    BT_BVH_CSWAP(t0, r0, t1, r1)
+    BT_BVH_CSWAP(t2, r2, t3, r3)
+    BT_BVH_CSWAP(t0, r0, t2, r2)
+    BT_BVH_CSWAP(t1, r1, t3, r3)
+    BT_BVH_CSWAP(t1, r1, t2, r2)
+    if (t0 < inf) {
+        if (t3 < inf) bvh_push(t, st, r3, t3);
+        if (t2 < inf) bvh_push(t, st, r2, t2);
+        if (t1 < inf) bvh_push(t, st, r1, t1);
+        t.cur = r0;
+    } else {
+        t.cur = bvh_pop(t, st);
+    }
+}
+#undef BT_BVH_CSWAP
+template <bool FLIGHT = false>
+BT_DEV void bvh_leaf(BvhTrav& t, const float4* __restrict__ prims, const BvhStack& st, V3 o, V3 d, float tmin) {
+    const uint32_t first = t.cur & 0x00ffffffu, count = (t.cur >> 24) & 0x7fu;
+    for (uint32_t i = first; i < first + count; ++i) {
+        const float4* q = prims + i * PRIM_STRIDE;
+        const int meta = __float_as_int(__ldg(q + 4).x);
+        const int type = meta & 3, canon = meta >> PRIM_CANON_SHIFT;
+        const bool strict = type == PRIM_CUBOID_FACE;
+        float tt;
+        bool front = true, ok;
+        if (type == PRIM_SPHERE)
+            ok = sphere_roots<FLIGHT>(__ldg(q), __ldg(q + 1).x, o, d, tmin, t.h.t, tt);
+        else
+            ok = rect_test(q, o, d, tmin, t.h.t, false, tt, front);
+        if (ok) {
+            // tt <= h.t here.  Equal distance: the later canonical index wins unless strict.
+            bool take = tt < t.h.t;
+            if (!take) take = canon > t.best_canon ? !strict : t.best_strict;
+            if (take) {
+                t.h.t = tt;
+                t.h.prim = (int)i;
+                t.h.face = type == PRIM_SPHERE ? 8 : (front ? 0 : 1);
+                t.best_canon = canon;
+                t.best_strict = strict;
             }
         }
-        BT_BVH_POP()
     }
-#undef BT_BVH_POP
-    t.cur = cur;
-    t.sp = sp;
-    return cur == BVH_DONE;
+    t.cur = bvh_pop(t, st);
 }
 template <bool FLIGHT = false>
 BT_DEV Hit bvh_closest(const float4* __restrict__ prims, const float4* __restrict__ nodes, uint32_t* stack, V3 o, V3 d,
                        float tmin, float tmax) {
     BvhTrav t;
+    BvhSpill spill;
+    const BvhStack st = bvh_lane_stack(stack, spill);
     bvh_begin(t, tmax);
-    while (!bvh_unit<FLIGHT>(t, prims, nodes, stack, o, d, tmin)) {
+    const V3 inv = v3(m_rcp(d.x), m_rcp(d.y), m_rcp(d.z));
+    while (t.cur != BVH_DONE) {  // "while-while": inside a warp the two phases never interleave
+        while (!(t.cur & BVH_LEAF)) bvh_node(t, nodes, st, o, inv, tmin);
+        if (t.cur != BVH_DONE) bvh_leaf<FLIGHT>(t, prims, st, o, d, tmin);
     }
     return t.h;
 }

@@ -355,7 +355,8 @@ int build_params(const bt_engine* en, bt_scene* s, const SceneDev* dev, uint64_t
     // every ~50 turns per lane: small batches keep lanes flying; a marching volume wants larger ones.
     const bool long_flights = p.scene.n_lens != 0 && !p.scene.has_volume_prims;
     p.compact_lanes = knob(tn.compact_lanes, long_flights ? 12 : 16);
-    p.compact_patience = knob(tn.compact_patience, long_flights ? 8 : 16);
+    const bool bvh_rays = p.scene.n_bvh != 0 && p.scene.n_lens == 0;  // (patience counts node / leaf units there, ~7 per old unit)
+    p.compact_patience = knob(tn.compact_patience, long_flights ? 8 : (bvh_rays ? 96 : 16));
     // A scan over a handful of surface primitives costs less than half a ray generation: such a warp
     // is better off collecting more idle lanes first (scene.json.gz: +4.6 %, profiles/r1_sweep_regen2.log).
     const bool cheap_scans = p.scene.n_lens == 0 && !p.scene.has_volume_prims && p.scene.n_bvh == 0 && p.scene.n_prims <= 8;
@@ -744,7 +745,7 @@ namespace {
 // frame with it; bt_render pipelines a host frame through it in bands.
 int ensure_pool_arena(bt_engine* e, int lane, RenderParams* p) {
     if (p->pool_w == 0) return BT_OK;
-    const size_t bytes = render_pool_arena_bytes(p->pool_w, e->sm_count);
+    const size_t bytes = render_pool_arena_bytes(p->pool_w, e->sm_count, p->scene.n_bvh != 0 && p->scene.n_lens == 0);
     if (bytes > e->pool_q_cap[lane]) {
         // (only ever grows; a kernel that may still read the old arena was launched on this lane's stream, and
         // cudaFree synchronises the device)

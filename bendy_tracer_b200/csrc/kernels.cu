@@ -552,6 +552,8 @@ BT_DEV void render_body(const RenderParams& p) {
     flight_reset(fl);
     int fstate = FL_FLY;
     BvhTrav btrav;  // BVH && !LENS: the traversal this lane is in
+    BvhSpill bspill;
+    const BvhStack bstack = bvh_lane_stack(sc.stack, bspill);
     bvh_begin(btrav, 0.0f);
     int bstate = 0;  // 0 none, 1 traversing, 2 done
 
@@ -598,19 +600,30 @@ BT_DEV void render_body(const RenderParams& p) {
         Traced tr;
         bool has_event = false;
         if (BVH && !LENS) {
-            // BVH step compaction: every lane advances its traversal one unit (descend to a leaf, test
-            // it, pop) per turn; the warp leaves to shade once enough lanes are done, the others resume.
+            // BVH phase compaction: a traversal alternates between inner-node visits and leaf tests, and the
+            // lanes of a warp want different ones at any moment.  Every turn runs ONE kind of unit -- the
+            // kind more lanes are waiting for -- so neither runs with a handful of lanes while the rest
+            // idle (one unit = descend-to-leaf + leaf ran the descent at 6.8 lanes: profiles/r2_ncu_bvh.md).
+            // The warp leaves to shade once enough lanes are done, the others resume.
             // (Scenes with volumetric spheres never use the BVH, so every segment here is a full ray.)
             if (alive && bstate == 0) {
                 bvh_begin(btrav, p.clip_max);
                 bstate = 1;
             }
+            const V3 inv = v3(m_rcp(d.x), m_rcp(d.y), m_rcp(d.z));
             uint32_t waited = 0;
 #pragma unroll 1
             for (;;) {
-                if (bstate == 1 && bvh_unit(btrav, sc.prims, sc.nodes, sc.stack, o, d, p.clip_min)) bstate = 2;
-                const unsigned m_trav = __ballot_sync(0xffffffffu, bstate == 1);
-                if (m_trav == 0) break;
+                const bool at_leaf = (btrav.cur & BVH_LEAF) != 0;
+                const unsigned m_node = __ballot_sync(0xffffffffu, bstate == 1 && !at_leaf);
+                const unsigned m_leaf = __ballot_sync(0xffffffffu, bstate == 1 && at_leaf);
+                if ((m_node | m_leaf) == 0) break;
+                if (__popc(m_node) >= __popc(m_leaf)) {
+                    if (bstate == 1 && !at_leaf) bvh_node(btrav, sc.nodes, bstack, o, inv, p.clip_min);
+                } else {
+                    if (bstate == 1 && at_leaf) bvh_leaf(btrav, sc.prims, bstack, o, d, p.clip_min);
+                }
+                if (bstate == 1 && btrav.cur == BVH_DONE) bstate = 2;
                 const unsigned m_done = __ballot_sync(0xffffffffu, bstate == 2);
                 if (m_done != 0 && ((uint32_t)__popc(m_done) >= p.compact_lanes || ++waited >= p.compact_patience)) break;
             }
@@ -699,8 +712,11 @@ BT_DEV void render_body(const RenderParams& p) {
 // Lensed variants carry the flight state on top of the path state: 128-thread CTAs at 5 per SM give
 // them 96 registers (20 warps / SM) instead of 80 with spills (24 warps / SM).  The flat variants keep
 // the 85-register cap of (256, 3) and are launched with 128 threads as well (launch_render).
+#ifndef BT_BVH_CTAS
+#define BT_BVH_CTAS 7  // (measured 4 .. 7: the traversal is latency-bound, every CTA more is +6 .. +15 %)
+#endif
 template <bool LENS, bool EXACT, int NL, bool BVH, int C = CT_ALL>
-__global__ void __launch_bounds__(128, LENS ? 5 : 7) render_kernel(const __grid_constant__ RenderParams p) {
+__global__ void __launch_bounds__(128, LENS ? 5 : (BVH ? BT_BVH_CTAS : 7)) render_kernel(const __grid_constant__ RenderParams p) {
     render_body<false, LENS, EXACT, NL, BVH, C>(p);
 }
 // the same kernel + work counters for bench.py's roofline accounting (never timed)
@@ -716,6 +732,14 @@ __global__ void __launch_bounds__(256, 2) render_kernel_stats(const __grid_const
 template <bool LENS, bool EXACT, int NL, int C = CT_ALL>
 __global__ void BT_POOL_BOUNDS(LENS) render_pool_kernel(const __grid_constant__ RenderParams p) {
     render_pool_body<LENS, EXACT, NL, C>(p);
+}
+// BVH scenes under a flat field: the scan is a pooled traversal (NODE / LEAF phases)
+#ifndef BT_BVH_POOL_CTAS
+#define BT_BVH_POOL_CTAS 6
+#endif
+template <int C>
+__global__ void __launch_bounds__(128, BT_BVH_POOL_CTAS) render_pool_bvh_kernel(const __grid_constant__ RenderParams p) {
+    render_pool_body<false, false, 0, C, false, true>(p);
 }
 // the same kernel + scheduling counters (bt_render_pool_stats; the content-specialised variants only; never timed)
 template <bool LENS, bool EXACT, int NL, int C>
@@ -873,11 +897,11 @@ cudaError_t ensure_smem(K kernel, size_t bytes) {
 }  // namespace
 
 #ifndef BT_EXACT_SCAN
-size_t render_pool_arena_bytes(uint32_t pool_w, int sm_count) {
-    return 256 /* the tile counter */ + (size_t)sm_count * 8 /* CTAs per SM at most */ * 6 /* warps per CTA at most */ * pool_q_bytes(pool_w);
+size_t render_pool_arena_bytes(uint32_t pool_w, int sm_count, bool bvh) {
+    return 256 /* the tile counter */ + (size_t)sm_count * 8 /* CTAs per SM at most */ * (bvh ? 4 : 6) /* warps per CTA at most */ * pool_q_bytes(pool_w, bvh);
 }
 size_t render_smem_bytes(const RenderParams& p, unsigned threads) {
-    return (size_t)p.scene.stage_f4 * sizeof(float4) + (p.scene.n_bvh ? (size_t)BVH_STACK * threads * 2 * sizeof(uint32_t) : 0);
+    return (size_t)p.scene.stage_f4 * sizeof(float4) + (p.scene.n_bvh ? (size_t)BVH_STACK_SMEM * threads * 2 * sizeof(uint32_t) : 0);
 }
 
 #endif
@@ -911,7 +935,8 @@ cudaError_t launch_pool(K kernel, const RenderParams& p, bool lens, bool aov, cu
     const unsigned cap = 128;  // BT_POOL_BOUNDS
     const unsigned threads = p.pool_threads ? std::min(p.pool_threads, cap) : cap, warps = threads / 32;
     (void)aov;
-    const size_t smem = (size_t)p.scene.stage_f4 * sizeof(float4) + warps * pool_warp_bytes(p.pool_w, lens);
+    const bool bvh = p.scene.n_bvh != 0;
+    const size_t smem = (size_t)p.scene.stage_f4 * sizeof(float4) + warps * pool_warp_bytes(p.pool_w, lens, bvh);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0, dev = 0, sms = 0;
@@ -921,7 +946,7 @@ cudaError_t launch_pool(K kernel, const RenderParams& p, bool lens, bool aov, cu
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     const uint64_t tiles = (uint64_t)((p.width + 7) / 8) * ((p.row_end - p.row0 + 3) / 4);
     const uint64_t need = (tiles + warps - 1) / warps, fit = (uint64_t)per_sm * sms;
-    const uint64_t room = p.pool_q_cap / (pool_q_bytes(p.pool_w) * warps);  // CTAs the path-state arena has room for
+    const uint64_t room = p.pool_q_cap / (pool_q_bytes(p.pool_w, bvh) * warps);  // CTAs the path-state arena has room for
     if (room < 1 || !p.pool_q || !p.pool_counter) return cudaErrorMemoryAllocation;
     if ((e = cudaMemsetAsync(p.pool_counter, 0, sizeof(unsigned long long), stream)) != cudaSuccess) return e;
     kernel<<<(unsigned)std::max<uint64_t>(1, std::min(std::min(need, fit), room)), threads, smem, stream>>>(p);
@@ -931,9 +956,18 @@ cudaError_t launch_pool(K kernel, const RenderParams& p, bool lens, bool aov, cu
 
 cudaError_t BT_SFX(launch_render)(const RenderParams& p, cudaStream_t stream, uint64_t* launches) {
     // (the pooled kernel packs a path's counters into 8 bits each and its volume object into 7: render_pool.cuh)
-    const bool pool_ok = p.pool_w != 0 && p.scene.n_bvh == 0 && p.max_bounces <= POOL_MAX_BOUNCES && p.max_volume_bounces <= POOL_MAX_BOUNCES &&
-                         p.scene.n_prims <= POOL_MAX_OBJECTS;
-    if (pool_ok && p.pool_stats) {
+    const bool bvh_pool = p.scene.n_bvh != 0 && p.scene.n_lens == 0;  // (no volumetric spheres under a BVH: nothing to pack)
+    const bool pool_ok = p.pool_w != 0 && (p.scene.n_bvh == 0 || bvh_pool) && p.max_bounces <= POOL_MAX_BOUNCES &&
+                         p.max_volume_bounces <= POOL_MAX_BOUNCES && (p.scene.n_prims <= POOL_MAX_OBJECTS || bvh_pool);
+    if (pool_ok && bvh_pool && !p.stats && !p.pool_stats) {
+        const uint32_t ct = p.scene.content | (p.output != 0 ? (uint32_t)CT_AOV : 0u);
+        cudaError_t e_;
+        if (ct & CT_CUBOID_LIGHT) e_ = launch_pool(render_pool_bvh_kernel<CT_ALL>, p, false, true, stream);
+        else e_ = launch_pool(render_pool_bvh_kernel<CT_ALL & ~CT_CUBOID_LIGHT>, p, false, true, stream);
+        ++*launches;
+        return e_;
+    }
+    if (pool_ok && !bvh_pool && p.pool_stats) {
         const uint32_t ct = p.scene.content;
         const bool lensed = p.scene.n_lens != 0, ok = p.output == 0 && !(lensed && (p.scene.lens_exact || p.scene.n_lens != 1));
 #define BT_FITS_(C) ((ct & ~(uint32_t)(C)) == 0)
@@ -952,7 +986,7 @@ cudaError_t BT_SFX(launch_render)(const RenderParams& p, cudaStream_t stream, ui
         ++*launches;
         return e_;
     }
-    if (pool_ok && !p.stats) {
+    if (pool_ok && !bvh_pool && !p.stats) {
         // the pooled kernel (render_pool.cuh): the same variants as below
         const uint32_t ct = p.scene.content | (p.output != 0 ? (uint32_t)CT_AOV : 0u);
         const bool lensed = p.scene.n_lens != 0, one = p.scene.n_lens == 1, exact = p.scene.lens_exact != 0;

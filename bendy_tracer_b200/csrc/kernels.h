@@ -55,7 +55,7 @@ cudaError_t launch_fp32_peak(float* out, uint32_t iters, int blocks, cudaStream_
 
 size_t render_smem_bytes(const RenderParams& p, unsigned threads = 256);
 // device bytes the pooled render kernel wants for its path-state arena on a GPU of `sm_count` SMs (an upper bound of its grid)
-size_t render_pool_arena_bytes(uint32_t pool_w, int sm_count);
+size_t render_pool_arena_bytes(uint32_t pool_w, int sm_count, bool bvh);
 enum { FP32_PEAK_THREADS = 256, FP32_PEAK_CHAINS = 8, FP32_PEAK_UNROLL = 16 };
 
 }  // namespace bt

@@ -34,8 +34,10 @@ enum {
     ST_IDLE = 0, ST_DONE = 1,
     ST_FLY = FL_FLY + 2, ST_PEND = FL_PEND + 2, ST_PEND_FAR = FL_PEND_FAR + 2, ST_PEND_STRAIGHT = 5,
     ST_HIT = FL_HIT + 2, ST_HIT_FAR = FL_HIT_FAR + 2, ST_ESCAPED = FL_ESCAPED + 2, ST_CAPTURED = FL_CAPTURED + 2,
-    ST_HIT_STRAIGHT = 10
+    ST_HIT_STRAIGHT = 10,
+    ST_NODE = 11, ST_LEAF = 12  // BVH scenes: a traversal waiting at an inner node / holding a leaf
 };
+enum { POOL_BVH_K = 8 };  // traversal stack levels of a slot kept in shared memory (the rest: the arena)
 enum { POOL_RING = 16 };  // paths of one pixel in flight at most (in-order retirement window)
 enum { POOL_TILES = 8 };  // window of tiles a warp's lanes may be spread over
 
@@ -46,6 +48,9 @@ struct Pool {
     uint4 *qa, *qb;             // Q: xoshiro256++ state
     float4* qc;                 //    (T, misc)   misc = ring index | latched << 4 | (vol_obj + 1) << 5 | bounce << 12 | volume bounce << 20
     float4 *qe, *qf;            //    AOV latches (albedo, depth) (normal, -)   [CT_AOV kernels]
+    uint2* tv;                  // BVH: (node reference, stack height | best hit strict << 6 | (best hit's canonical index + 1) << 7)
+    uint32_t* bstack;           // BVH: traversal stacks (BvhStack: stride P, POOL_BVH_K levels)
+    uint2* bover;               // BVH: the stack levels beyond, BVH_STACK - POOL_BVH_K per slot (arena)
     uint8_t *st, *list, *stack, *ring;
     unsigned long long* tiles;  // the warp's window of tile indices: tile k of its stream is tiles[k % POOL_TILES]
 };
@@ -59,12 +64,14 @@ BT_DEV uint32_t pack_misc(uint32_t ring, bool latched, int vol_obj, uint32_t bou
 // and the queues.  The path state Q (48 B per slot, + 32 B of AOV latches) is read and written once per EVENT (1.5 .. 5
 // per path) by SHADE / REGEN only and lives in global memory (an L2-resident scratch arena of the engine,
 // pool_q_bytes per warp of the persistent grid): the shared memory it would take is worth two more CTAs per SM.
-__host__ __device__ inline size_t pool_warp_bytes(uint32_t w, bool lens) {
+__host__ __device__ inline size_t pool_warp_bytes(uint32_t w, bool lens, bool bvh = false) {
     const size_t P = 32u * w;
-    return P * (lens ? 64 : 32) + POOL_TILES * 8 + 3 * P + POOL_RING * 32;
+    return P * (lens ? 64 : 32) + (bvh ? P * (8 + POOL_BVH_K * 8) : 0) + POOL_TILES * 8 + 3 * P + POOL_RING * 32;
 }
-__host__ __device__ inline size_t pool_q_bytes(uint32_t w) { return (size_t)32u * w * 80; }
-template <bool LENS, bool AOV>
+__host__ __device__ inline size_t pool_q_bytes(uint32_t w, bool bvh = false) {
+    return (size_t)32u * w * (80 + (bvh ? (BVH_STACK - POOL_BVH_K) * 8 : 0));
+}
+template <bool LENS, bool AOV, bool BVH>
 BT_DEV Pool pool_carve(char* base, char* qbase, uint32_t P) {
     Pool pl;
     float4* f = reinterpret_cast<float4*>(base);
@@ -72,6 +79,9 @@ BT_DEV Pool pool_carve(char* base, char* qbase, uint32_t P) {
     pl.fb = f; f += P;
     pl.fc = pl.fd = f;
     if (LENS) { pl.fc = f; f += P; pl.fd = f; f += P; }
+    pl.tv = reinterpret_cast<uint2*>(f);
+    pl.bstack = reinterpret_cast<uint32_t*>(pl.tv + P);
+    if (BVH) f = reinterpret_cast<float4*>(pl.bstack + 2 * POOL_BVH_K * P);
     pl.tiles = reinterpret_cast<unsigned long long*>(f);
     uint8_t* b = reinterpret_cast<uint8_t*>(pl.tiles + POOL_TILES);
     pl.st = b; b += P;
@@ -84,6 +94,7 @@ BT_DEV Pool pool_carve(char* base, char* qbase, uint32_t P) {
     pl.qc = q + 2 * P;
     pl.qe = q + 3 * P;
     pl.qf = q + 4 * P;
+    pl.bover = reinterpret_cast<uint2*>(q + 5 * P);
     return pl;
 }
 // The slots whose state lies in [lo, hi], compacted into pl.list (ballot + popc); stops once 32 are found.
@@ -113,10 +124,11 @@ BT_DEV void unpack_hit(uint32_t w, Hit& h) {
 // PSTATS: scheduling counters (bt_render_pool_stats; never timed): p.stats[0..11] = STEP iterations, flying lanes summed
 // over them, refill rounds, STEP entries, SCAN passes, slots scanned, SHADE passes, slots shaded, REGEN passes,
 // paths issued, paths retired, turns; [12..16] = SM clocks the warps spent in STEP, SCAN, SHADE, REGEN and in the kernel
-template <bool LENS, bool EXACT, int NL, int C, bool PSTATS = false>
+template <bool LENS, bool EXACT, int NL, int C, bool PSTATS = false, bool BVH = false>
 BT_DEV void render_pool_body(const RenderParams& p) {
+    static_assert(!(BVH && LENS), "the pooled traversal serves flat fields (a lensed BVH scene renders through render_body)");
     extern __shared__ float4 smem[];
-    const SceneView sc = stage_scene<false>(p, smem);
+    const SceneView sc = stage_scene<BVH>(p, smem);
     const typename LensSel<NL>::type lens = LensSel<NL>::make(sc.lens, (int)p.scene.n_lens);
     Consts k;
     k.tau_scale = p.tau_scale;
@@ -127,8 +139,8 @@ BT_DEV void render_pool_body(const RenderParams& p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t W = p.pool_w, P = 32u * W;
-    const Pool pl = pool_carve<LENS, AOV>(reinterpret_cast<char*>(smem + p.scene.stage_f4) + warp * pool_warp_bytes(W, LENS),
-                                          p.pool_q + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * pool_q_bytes(W), P);
+    const Pool pl = pool_carve<LENS, AOV, BVH>(reinterpret_cast<char*>(smem + p.scene.stage_f4) + warp * pool_warp_bytes(W, LENS, BVH),
+                                               p.pool_q + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * pool_q_bytes(W, BVH), P);
     for (uint32_t w = 0; w < W; ++w) pl.st[w * 32 + lane] = ST_IDLE;
     __syncwarp();
 
@@ -149,6 +161,7 @@ BT_DEV void render_pool_body(const RenderParams& p) {
 
     // warp-uniform queue sizes
     uint32_t n_fly = 0 /* parked on pl.stack */, n_pend = 0, n_res = 0, n_done = 0, n_free = P;
+    uint32_t n_node = 0, n_leaf = 0;  // BVH: traversals at an inner node / holding a leaf (n_pend stays 0)
     bool regen_futile = false;
     uint32_t turn = 0, w0 = 0;  // w0: the pool row the slot lists start at (rotates)
     uint32_t ps[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // PSTATS only (warp-uniform)
@@ -161,7 +174,8 @@ BT_DEV void render_pool_body(const RenderParams& p) {
         // ---- the phase with the most slots waiting ----------------------------------------------
         const uint32_t c_step = LENS ? min(n_fly, 32u) : 0u, c_scan = min(n_pend, 32u), c_shade = min(n_res, 32u);
         const uint32_t c_regen = regen_futile ? 0u : min(n_free + n_done, 32u);
-        const uint32_t best = max(max(c_step, c_scan), max(c_shade, c_regen));
+        const uint32_t c_node = BVH ? min(n_node, 32u) : 0u, c_leaf = BVH ? min(n_leaf, 32u) : 0u;
+        const uint32_t best = max(max(max(c_step, c_scan), max(c_shade, c_regen)), max(c_node, c_leaf));
         if (best == 0) break;
         if (++w0 >= W) w0 = 0;
 
@@ -245,6 +259,94 @@ BT_DEV void render_pool_body(const RenderParams& p) {
                 n_fly += __popc(m);
             }
             __syncwarp();
+        } else if (BVH && c_node == best) {
+            if (PSTATS) pc_phase = 1;
+            // ================================ NODE ================================
+            // BVH scenes: the SCAN phase is a traversal, run as two kinds of unit on the slots that want them -- here
+            // visits of 4-wide inner nodes (up to steps_per_turn in a row while a slot stays at an inner node), below
+            // leaf tests.  Each runs with a full warp of rays that need exactly that, whatever their origin.
+            const uint32_t n = min(pool_collect(pl, W, w0, ST_NODE, ST_NODE, lane), 32u);
+            bool to_leaf = false, resolved = false;
+            if ((uint32_t)lane < n) {
+                const int slot = pl.list[lane];
+                const float4 a = pl.fa[slot], b = pl.fb[slot];
+                const uint2 tv = pl.tv[slot];
+                const V3 o = v3(a), d = v3(b);
+                BvhTrav t;
+                t.cur = tv.x;
+                t.sp = tv.y & 63u;
+                t.h.t = a.w;
+                BvhStack bs;
+                bs.base = pl.bstack;
+                bs.stride = P;
+                bs.idx = (uint32_t)slot;
+                bs.k = POOL_BVH_K;
+                bs.over = pl.bover + (size_t)slot * (BVH_STACK - POOL_BVH_K);
+                const V3 inv = v3(m_rcp(d.x), m_rcp(d.y), m_rcp(d.z));
+#pragma unroll 1
+                for (uint32_t r = 0; r < p.steps_per_turn && !(t.cur & BVH_LEAF); ++r) bvh_node(t, sc.nodes, bs, o, inv, p.clip_min);
+                pl.tv[slot] = make_uint2(t.cur, (tv.y & ~63u) | t.sp);
+                if (t.cur == BVH_DONE) {
+                    pl.st[slot] = ST_HIT_STRAIGHT;
+                    resolved = true;
+                } else if (t.cur & BVH_LEAF) {
+                    pl.st[slot] = ST_LEAF;
+                    to_leaf = true;
+                }
+            }
+            const uint32_t n_tl = __popc(__ballot_sync(0xffffffffu, to_leaf)), n_rs = __popc(__ballot_sync(0xffffffffu, resolved));
+            n_node -= n_tl + n_rs;
+            n_leaf += n_tl;
+            n_res += n_rs;
+            if (PSTATS) {
+                ++ps[4];
+                ps[5] += n;
+            }
+            __syncwarp();
+        } else if (BVH && c_leaf == best) {
+            if (PSTATS) pc_phase = 1;
+            // ================================ LEAF ================================
+            const uint32_t n = min(pool_collect(pl, W, w0, ST_LEAF, ST_LEAF, lane), 32u);
+            bool to_node = false, resolved = false;
+            if ((uint32_t)lane < n) {
+                const int slot = pl.list[lane];
+                const float4 a = pl.fa[slot], b = pl.fb[slot];
+                const uint2 tv = pl.tv[slot];
+                const V3 o = v3(a), d = v3(b);
+                BvhTrav t;
+                t.cur = tv.x;
+                t.sp = tv.y & 63u;
+                t.h.t = a.w;
+                unpack_hit(__float_as_uint(b.w), t.h);
+                t.best_strict = ((tv.y >> 6) & 1u) != 0;
+                t.best_canon = (int)(tv.y >> 7) - 1;
+                BvhStack bs;
+                bs.base = pl.bstack;
+                bs.stride = P;
+                bs.idx = (uint32_t)slot;
+                bs.k = POOL_BVH_K;
+                bs.over = pl.bover + (size_t)slot * (BVH_STACK - POOL_BVH_K);
+                bvh_leaf(t, sc.prims, bs, o, d, p.clip_min);
+                pl.fa[slot].w = t.h.t;
+                pl.fb[slot].w = __uint_as_float(pack_hit(t.h));
+                pl.tv[slot] = make_uint2(t.cur, t.sp | (t.best_strict ? 64u : 0u) | ((uint32_t)(t.best_canon + 1) << 7));
+                if (t.cur == BVH_DONE) {
+                    pl.st[slot] = ST_HIT_STRAIGHT;
+                    resolved = true;
+                } else if (!(t.cur & BVH_LEAF)) {
+                    pl.st[slot] = ST_NODE;
+                    to_node = true;
+                }
+            }
+            const uint32_t n_tn = __popc(__ballot_sync(0xffffffffu, to_node)), n_rs = __popc(__ballot_sync(0xffffffffu, resolved));
+            n_leaf -= n_tn + n_rs;
+            n_node += n_tn;
+            n_res += n_rs;
+            if (PSTATS) {
+                ++ps[4];
+                ps[5] += n;
+            }
+            __syncwarp();
         } else if (c_scan == best) {
             if (PSTATS) pc_phase = 1;
             // ================================ SCAN ================================
@@ -309,7 +411,7 @@ BT_DEV void render_pool_body(const RenderParams& p) {
             if (PSTATS) pc_phase = 2;
             // ================================ SHADE ===============================
             const uint32_t n = min(pool_collect(pl, W, w0, ST_HIT, ST_HIT_STRAIGHT, lane), 32u);
-            bool to_fly = false, to_pend = false, finished = false;
+            bool to_fly = false, to_pend = false, to_node = false, finished = false;
             int slot = -1;
             if ((uint32_t)lane < n) {
                 slot = pl.list[lane];
@@ -377,9 +479,13 @@ BT_DEV void render_pool_body(const RenderParams& p) {
                         pl.qf[slot] = make_float4(q.aov_normal.x, q.aov_normal.y, q.aov_normal.z, 0.0f);
                     }
                     // the scattered ray: a new flight, or a straight segment (flat field / volume march)
-                    pl.fa[slot] = make_float4(o.x, o.y, o.z, 0.0f);
+                    pl.fa[slot] = make_float4(o.x, o.y, o.z, BVH ? p.clip_max : 0.0f);
                     pl.fb[slot] = make_float4(d.x, d.y, d.z, 0.0f);
-                    if (LENS && !(VOL && q.vol_obj >= 0)) {
+                    if (BVH) {  // a new traversal: at the root, no hit (pack_hit of prim -1 = 0)
+                        pl.tv[slot] = make_uint2(0u, 0u);
+                        pl.st[slot] = ST_NODE;
+                        to_node = true;
+                    } else if (LENS && !(VOL && q.vol_obj >= 0)) {
                         pl.fc[slot] = make_float4(0.0f, __int_as_float(-1), __uint_as_float(0u), 0.0f);
                         pl.st[slot] = ST_FLY;
                         to_fly = true;
@@ -393,6 +499,7 @@ BT_DEV void render_pool_body(const RenderParams& p) {
             if (LENS && to_fly) pl.stack[n_fly + __popc(m_fly & lt)] = (uint8_t)slot;
             n_fly += __popc(m_fly);
             n_pend += __popc(__ballot_sync(0xffffffffu, to_pend));
+            if (BVH) n_node += __popc(__ballot_sync(0xffffffffu, to_node));
             const uint32_t fin = __popc(__ballot_sync(0xffffffffu, finished));
             n_done += fin;
             n_res -= n;
@@ -511,18 +618,19 @@ BT_DEV void render_pool_body(const RenderParams& p) {
                         pl.qe[slot] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0x7f800000));
                         pl.qf[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                     }
-                    pl.fa[slot] = make_float4(o.x, o.y, o.z, 0.0f);
+                    pl.fa[slot] = make_float4(o.x, o.y, o.z, BVH ? p.clip_max : 0.0f);
                     pl.fb[slot] = make_float4(d.x, d.y, d.z, 0.0f);
                     if (LENS) {
                         pl.fc[slot] = make_float4(0.0f, __int_as_float(-1), __uint_as_float(0u), 0.0f);
                         pl.stack[n_fly + rank] = (uint8_t)slot;
                     }
-                    pl.st[slot] = LENS ? ST_FLY : ST_PEND_STRAIGHT;
+                    if (BVH) pl.tv[slot] = make_uint2(0u, 0u);
+                    pl.st[slot] = LENS ? ST_FLY : (BVH ? ST_NODE : ST_PEND_STRAIGHT);
                     pl.ring[ri * 32 + lane] = (uint8_t)slot;
                     ++tot_issued;
                     if (on_b) ++b_issued; else ++a_issued;
                 }
-                if (LENS) n_fly += take; else n_pend += take;
+                if (LENS) n_fly += take; else if (BVH) n_node += take; else n_pend += take;
                 n_free -= take;
             }
             if (PSTATS) {

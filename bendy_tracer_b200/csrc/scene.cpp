@@ -915,11 +915,13 @@ bool make_box(const Object& o, const Affine& tf, float4 out[BOX_STRIDE]) {
     return true;
 }
 
-// ---- BVH2: binned-SAH build, <= 4 primitives per leaf; a node stores BOTH child boxes -----
+// ---- binned-SAH build of a binary tree (<= 4 primitives per leaf), collapsed to the 4-wide nodes the device reads -----
 struct BvhBuild {
     const std::vector<Bounds>& b;
     std::vector<uint32_t> order;   // record position -> canonical primitive index
-    std::vector<float4> nodes;     // BVH_STRIDE float4 per inner node
+    enum { STRIDE2 = 4 };          // binary node: (L box, R box, left, right), the builder's own format
+    std::vector<float4> nodes;     // STRIDE2 float4 per binary inner node
+    std::vector<float4> wide;      // BVH_STRIDE float4 per 4-wide node (collapse())
     explicit BvhBuild(const std::vector<Bounds>& bounds) : b(bounds) {
         for (uint32_t i = 0; i < b.size(); ++i) order.push_back(i);
     }
@@ -948,13 +950,72 @@ struct BvhBuild {
         return box;
     }
     static uint32_t leaf_ref(uint32_t first, uint32_t count) { return BVH_LEAF | (count << 24) | first; }
+    void set_inner(uint32_t self, uint32_t left, const Bounds& l, uint32_t right, const Bounds& r) {  // (unpadded boxes)
+        nodes[self * STRIDE2] = f4(l.lo[0], l.lo[1], l.lo[2], l.hi[0]);
+        nodes[self * STRIDE2 + 1] = f4(l.hi[1], l.hi[2], r.lo[0], r.lo[1]);
+        nodes[self * STRIDE2 + 2] = f4(r.lo[2], r.hi[0], r.hi[1], r.hi[2]);
+        nodes[self * STRIDE2 + 3] = f4(as_f(left), as_f(right), 0.0f, 0.0f);
+    }
     uint32_t make_inner(uint32_t left, const Bounds& lb, uint32_t right, const Bounds& rb) {
-        uint32_t self = (uint32_t)(nodes.size() / BVH_STRIDE);
-        Bounds l = padded(lb), r = padded(rb);
-        nodes.push_back(f4(l.lo[0], l.lo[1], l.lo[2], l.hi[0]));
-        nodes.push_back(f4(l.hi[1], l.hi[2], r.lo[0], r.lo[1]));
-        nodes.push_back(f4(r.lo[2], r.hi[0], r.hi[1], r.hi[2]));
-        nodes.push_back(f4(as_f(left), as_f(right), 0.0f, 0.0f));
+        uint32_t self = (uint32_t)(nodes.size() / STRIDE2);
+        nodes.resize(nodes.size() + STRIDE2);
+        set_inner(self, left, lb, right, rb);
+        return self;
+    }
+    struct Child { uint32_t ref; Bounds box; };
+    void children_of(uint32_t node, Child* l, Child* r) const {
+        const float4* q = &nodes[(size_t)node * STRIDE2];
+        l->ref = as_u(q[3].x);
+        r->ref = as_u(q[3].y);
+        l->box.lo[0] = q[0].x; l->box.lo[1] = q[0].y; l->box.lo[2] = q[0].z; l->box.hi[0] = q[0].w; l->box.hi[1] = q[1].x; l->box.hi[2] = q[1].y;
+        r->box.lo[0] = q[1].z; r->box.lo[1] = q[1].w; r->box.lo[2] = q[2].x; r->box.hi[0] = q[2].y; r->box.hi[1] = q[2].z; r->box.hi[2] = q[2].w;
+    }
+    static bool is_inner(uint32_t ref) { return !(ref & BVH_LEAF); }
+    static bool is_empty_leaf(uint32_t ref) { return (ref & BVH_LEAF) && ((ref >> 24) & 0x7fu) == 0; }
+    static void write_wide(float4* q, const Child* c, int n) {  // (pads the boxes)
+        float v[6][4];
+        uint32_t ref[4];
+        for (int i = 0; i < (int)BVH_WIDTH; ++i) {
+            Bounds b = i < n ? padded(c[i].box) : empty();
+            for (int k = 0; k < 3; ++k) { v[2 * k][i] = b.lo[k]; v[2 * k + 1][i] = b.hi[k]; }
+            ref[i] = i < n ? c[i].ref : (uint32_t)BVH_EMPTY;
+        }
+        for (int k = 0; k < 6; ++k) q[k] = f4(v[k][0], v[k][1], v[k][2], v[k][3]);
+        q[6] = f4(as_f(ref[0]), as_f(ref[1]), as_f(ref[2]), as_f(ref[3]));
+        q[7] = f4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    // Binary node -> 4-wide node: both children are opened when they are inner nodes (so a wide level spans two
+    // binary levels and the wide tree is at most half as deep), then the largest remaining inner child while a slot
+    // is free.  A wide node is stored before its children (refit_bvh sweeps backwards).
+    uint32_t collapse(uint32_t node) {
+        Child c[BVH_WIDTH + 1];
+        int n = 2;
+        children_of(node, &c[0], &c[1]);
+        auto open = [&](int i) {
+            Child l, r;
+            children_of(c[i].ref, &l, &r);
+            c[i] = l;
+            c[n++] = r;
+        };
+        const bool open0 = is_inner(c[0].ref), open1 = is_inner(c[1].ref);
+        if (open0) open(0);
+        if (open1) open(1);
+        while (n < (int)BVH_WIDTH) {
+            int best = -1;
+            for (int i = 0; i < n; ++i)
+                if (is_inner(c[i].ref) && (best < 0 || area(c[i].box) > area(c[best].box))) best = i;
+            if (best < 0) break;
+            open(best);
+        }
+        int m = 0;
+        for (int i = 0; i < n; ++i)
+            if (!is_empty_leaf(c[i].ref)) c[m++] = c[i];
+        n = m;
+        const uint32_t self = (uint32_t)(wide.size() / BVH_STRIDE);
+        wide.resize(wide.size() + BVH_STRIDE);
+        for (int i = 0; i < n; ++i)
+            if (is_inner(c[i].ref)) c[i].ref = collapse(c[i].ref);
+        write_wide(&wide[(size_t)self * BVH_STRIDE], c, n);
         return self;
     }
     // returns a child reference (inner node index, or BVH_LEAF | count << 24 | first) and its box
@@ -971,10 +1032,10 @@ struct BvhBuild {
         int axis = 0;
         for (int k = 1; k < 3; ++k)
             if (cb.hi[k] - cb.lo[k] > cb.hi[axis] - cb.lo[axis]) axis = k;
-        // The traversal stack bounds the depth.  A skewed SAH split is only taken while median splits could
+        // The traversal stack bounds the depth (layout.h: 3 pushes per wide level = per two levels here).  A skewed SAH split is only taken while median splits could
         // still bring what remains down to leaf size; coincident centroids (no axis to split on) are halved by
         // index -- a leaf holds at most 127 records.
-        const int remaining = (int)BVH_STACK - 2 - depth;
+        const int remaining = (int)BVH_MAX_DEPTH2 - 2 - depth;
         const bool degenerate = !(cb.hi[axis] > cb.lo[axis]);
         if (count <= 4 || remaining <= 0 || (degenerate && count <= 127)) {
             if (count > 127) throw SceneError("BVH: the scene is too large for the traversal stack");
@@ -1026,11 +1087,7 @@ struct BvhBuild {
         uint32_t self = make_inner(0, box, 0, box);  // reserve the slot before the children (root = node 0)
         uint32_t left = build(first, mid - first, depth + 1, &lb);
         uint32_t right = build(mid, first + count - mid, depth + 1, &rb);
-        Bounds l = padded(lb), r = padded(rb);
-        nodes[self * BVH_STRIDE] = f4(l.lo[0], l.lo[1], l.lo[2], l.hi[0]);
-        nodes[self * BVH_STRIDE + 1] = f4(l.hi[1], l.hi[2], r.lo[0], r.lo[1]);
-        nodes[self * BVH_STRIDE + 2] = f4(r.lo[2], r.hi[0], r.hi[1], r.hi[2]);
-        nodes[self * BVH_STRIDE + 3] = f4(as_f(left), as_f(right), 0.0f, 0.0f);
+        set_inner(self, left, lb, right, rb);
         return self;
     }
 };
@@ -1406,12 +1463,9 @@ FlatScene flatten(const Scene& scene, int accel) {
         uint32_t rest = bvh.build(n_big, h.n_prims - n_big, 1, &rest_box);
         uint32_t big = BvhBuild::leaf_ref(0, n_big);
         if (n_big > 127) throw SceneError("BVH: more than 127 scene-spanning primitives");
-        Bounds lb = n_big ? all : BvhBuild::empty(), rb = BvhBuild::padded(rest_box);
-        if (n_big) lb = BvhBuild::padded(lb);
-        bvh.nodes[0] = f4(lb.lo[0], lb.lo[1], lb.lo[2], lb.hi[0]);
-        bvh.nodes[1] = f4(lb.hi[1], lb.hi[2], rb.lo[0], rb.lo[1]);
-        bvh.nodes[2] = f4(rb.lo[2], rb.hi[0], rb.hi[1], rb.hi[2]);
-        bvh.nodes[3] = f4(as_f(big), as_f(rest), 0.0f, 0.0f);
+        if (h.n_prims >= 0x00fffff0u) throw SceneError("BVH: too many primitives for a leaf reference");
+        bvh.set_inner(0, big, n_big ? all : BvhBuild::empty(), rest, rest_box);
+        bvh.collapse(0);  // wide node 0 = the root
         std::vector<float4> sorted(prims.size());
         std::vector<uint32_t> where(h.n_prims);
         for (uint32_t pos = 0; pos < h.n_prims; ++pos) {
@@ -1420,7 +1474,7 @@ FlatScene flatten(const Scene& scene, int accel) {
         }
         prims.swap(sorted);
         fs.prim_order = bvh.order;
-        nodes.swap(bvh.nodes);
+        nodes.swap(bvh.wide);
         for (size_t l = 0; l < lights.size(); l += LIGHT_STRIDE) {  // lights point at their primitive record
             uint32_t first;
             std::memcpy(&first, &lights[l].y, 4);
@@ -1458,6 +1512,8 @@ FlatScene flatten(const Scene& scene, int accel) {
         }
         if (!std::getenv("BT_NO_DIST_GRID") && build_dist_grid(prims, bounds, h, &fs.dist, std::getenv("BT_DIST_GRID_HOST") != 0)) h.lens_skip = 3;
     }
+    if (!nodes.empty())
+        while (fs.blob.size() % BVH_STRIDE) fs.blob.push_back(f4(0, 0, 0, 0));  // a node = one 128-byte line
     h.bvh_off = (uint32_t)fs.blob.size();
     h.n_bvh = (uint32_t)(nodes.size() / BVH_STRIDE);
     fs.blob.insert(fs.blob.end(), nodes.begin(), nodes.end());
@@ -1483,7 +1539,7 @@ FlatScene flatten(const Scene& scene, int accel) {
 
 namespace {
 // Recompute every node box of the BVH from the primitives' current bounds: same topology, same leaves.  Children are
-// stored behind their parent (BvhBuild::build reserves the parent's slot first), so one backward sweep sees every
+// stored behind their parent (BvhBuild::collapse reserves the parent's slot first), so one backward sweep sees every
 // child before its parent.
 void refit_bvh(FlatScene& fs) {
     const SceneHeader& h = fs.header;
@@ -1498,14 +1554,15 @@ void refit_bvh(FlatScene& fs) {
     };
     for (uint32_t n = h.n_bvh; n-- > 0;) {
         float4* q = nodes + (size_t)n * BVH_STRIDE;
-        const uint32_t left = as_u(q[3].x), right = as_u(q[3].y);
-        const Bounds lb = child_box(left), rb = child_box(right);
-        own[n] = lb;
-        BvhBuild::grow(own[n], rb);
-        const Bounds l = BvhBuild::padded(lb), r = BvhBuild::padded(rb);
-        q[0] = f4(l.lo[0], l.lo[1], l.lo[2], l.hi[0]);
-        q[1] = f4(l.hi[1], l.hi[2], r.lo[0], r.lo[1]);
-        q[2] = f4(r.lo[2], r.hi[0], r.hi[1], r.hi[2]);
+        const uint32_t ref[BVH_WIDTH] = {as_u(q[6].x), as_u(q[6].y), as_u(q[6].z), as_u(q[6].w)};
+        BvhBuild::Child c[BVH_WIDTH];
+        int m = 0;
+        for (; m < (int)BVH_WIDTH && ref[m] != (uint32_t)BVH_EMPTY; ++m) {
+            c[m].ref = ref[m];
+            c[m].box = child_box(ref[m]);
+            BvhBuild::grow(own[n], c[m].box);
+        }
+        BvhBuild::write_wide(q, c, m);
     }
 }
 }  // namespace

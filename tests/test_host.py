@@ -428,4 +428,4 @@ def test_bvh_build_survives_skewed_and_coincident_primitives():
     sc = bt.Scene.from_json(json.dumps(doc))
     sc.set_accel("bvh")
     info = sc.info()
-    assert info["n_primitives"] == 402 and info["n_bvh_nodes"] > 10
+    assert info["n_primitives"] == 402 and info["n_bvh_nodes"] > 3
