@@ -315,8 +315,7 @@ BT_DEV float sqrt_approx(float x) {
     return r;
 }
 // Rect::hit (rect.rs:110-155) on a pre-transformed record.  strict: Cuboid::hit's `t < best`.
-BT_DEV bool rect_test(const float4* q, V3 o, V3 d, float tmin, float tmax, bool strict, float& t_out, bool& front) {
-    const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+BT_DEV bool rect_test_q(float4 q0, float4 q1, float4 q2, float4 q3, V3 o, V3 d, float tmin, float tmax, bool strict, float& t_out, bool& front) {
     const V3 n = v3(q0);
     const float qq = sdot(d, n);
     const float p = sdot(v3(q1) - o, n);
@@ -334,6 +333,9 @@ BT_DEV bool rect_test(const float4* q, V3 o, V3 d, float tmin, float tmax, bool 
     t_out = t;
     front = p < 0.0f;
     return ok;
+}
+BT_DEV bool rect_test(const float4* q, V3 o, V3 d, float tmin, float tmax, bool strict, float& t_out, bool& front) {
+    return rect_test_q(q[0], q[1], q[2], q[3], o, d, tmin, tmax, strict, t_out, front);
 }
 
 // Rect::hit for a PRIM_RECT_AA record (layout.h): normal on axis K, q2 on axis (K+1)%3, q3 on (K+2)%3,
@@ -638,11 +640,10 @@ BT_DEV uint32_t bvh_pop(BvhTrav& t, const BvhStack& st) {
         ta = tlo;                               \
         ra = rlo;                               \
     }
-BT_DEV void bvh_node(BvhTrav& t, const float4* __restrict__ nodes, const BvhStack& st, V3 o, V3 inv, float tmin) {
+// the visit proper, on a fetched node (the seven float4 of layout.h)
+BT_DEV void bvh_node_visit(BvhTrav& t, float4 lx, float4 hx, float4 ly, float4 hy, float4 lz, float4 hz, float4 rf, const BvhStack& st, V3 o,
+                           V3 inv, float tmin) {
     const float inf = __int_as_float(0x7f800000);
-    const float4* n = nodes + t.cur * BVH_STRIDE;
-    const float4 lx = __ldg(n), hx = __ldg(n + 1), ly = __ldg(n + 2), hy = __ldg(n + 3), lz = __ldg(n + 4), hz = __ldg(n + 5);
-    const float4 rf = __ldg(n + 6);
     uint32_t r0 = __float_as_uint(rf.x), r1 = __float_as_uint(rf.y), r2 = __float_as_uint(rf.z), r3 = __float_as_uint(rf.w);
     float t0 = slab(lx.x, hx.x, ly.x, hy.x, lz.x, hz.x, o, inv, tmin, t.h.t);
     float t1 = slab(lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, o, inv, tmin, t.h.t);
@@ -664,28 +665,56 @@ BT_DEV void bvh_node(BvhTrav& t, const float4* __restrict__ nodes, const BvhStac
         t.cur = bvh_pop(t, st);
     }
 }
+BT_DEV void bvh_node(BvhTrav& t, const float4* __restrict__ nodes, const BvhStack& st, V3 o, V3 inv, float tmin) {
+    const float4* n = nodes + t.cur * BVH_STRIDE;
+    const float4 lx = __ldg(n), hx = __ldg(n + 1), ly = __ldg(n + 2), hy = __ldg(n + 3), lz = __ldg(n + 4), hz = __ldg(n + 5);
+    bvh_node_visit(t, lx, hx, ly, hy, lz, hz, __ldg(n + 6), st, o, inv, tmin);
+}
 #undef BT_BVH_CSWAP
-template <bool FLIGHT = false>
+// PIPE: software pipeline -- the next record's type word and first quarter are in flight while this one is tested (read on
+// demand, every record costs two dependent L2 round trips, type then geometry, in a loop that h.t serialises).  The lane
+// kernel gains 4 % from it; the pooled kernel, whose warps are short of registers rather than of loads in flight, loses 7 %.
+template <bool FLIGHT = false, bool PIPE = true>
 BT_DEV void bvh_leaf(BvhTrav& t, const float4* __restrict__ prims, const BvhStack& st, V3 o, V3 d, float tmin) {
     const uint32_t first = t.cur & 0x00ffffffu, count = (t.cur >> 24) & 0x7fu;
-    for (uint32_t i = first; i < first + count; ++i) {
-        const float4* q = prims + i * PRIM_STRIDE;
-        const int meta = __float_as_int(__ldg(q + 4).x);
+    const float4* q = prims + first * PRIM_STRIDE;
+    int meta_n = 0;
+    float4 q0_n = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (PIPE && count != 0) {
+        meta_n = __float_as_int(__ldg(&q[4].x));
+        q0_n = __ldg(q);
+    }
+    for (uint32_t i = 0; i < count; ++i, q += PRIM_STRIDE) {
+        int meta;
+        float4 q0 = q0_n;
+        if (PIPE) {
+            meta = meta_n;
+            if (i + 1 < count) {
+                meta_n = __float_as_int(__ldg(&q[PRIM_STRIDE + 4].x));
+                q0_n = __ldg(q + PRIM_STRIDE);
+            }
+        } else {
+            meta = __float_as_int(__ldg(q + 4).x);
+        }
         const int type = meta & 3, canon = meta >> PRIM_CANON_SHIFT;
         const bool strict = type == PRIM_CUBOID_FACE;
         float tt;
         bool front = true, ok;
-        if (type == PRIM_SPHERE)
-            ok = sphere_roots<FLIGHT>(__ldg(q), __ldg(q + 1).x, o, d, tmin, t.h.t, tt);
-        else
+        if (type == PRIM_SPHERE) {  // r^2 = q1.x, formed here as the flattener forms it (one float product): q0 is the whole sphere
+            if (!PIPE) q0 = __ldg(q);
+            ok = sphere_roots<FLIGHT>(q0, __fmul_rn(q0.w, q0.w), o, d, tmin, t.h.t, tt);
+        } else if (PIPE) {
+            ok = rect_test_q(q0, __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), o, d, tmin, t.h.t, false, tt, front);
+        } else {
             ok = rect_test(q, o, d, tmin, t.h.t, false, tt, front);
+        }
         if (ok) {
             // tt <= h.t here.  Equal distance: the later canonical index wins unless strict.
             bool take = tt < t.h.t;
             if (!take) take = canon > t.best_canon ? !strict : t.best_strict;
             if (take) {
                 t.h.t = tt;
-                t.h.prim = (int)i;
+                t.h.prim = (int)(first + i);
                 t.h.face = type == PRIM_SPHERE ? 8 : (front ? 0 : 1);
                 t.best_canon = canon;
                 t.best_strict = strict;

@@ -355,12 +355,12 @@ int build_params(const bt_engine* en, bt_scene* s, const SceneDev* dev, uint64_t
     // every ~50 turns per lane: small batches keep lanes flying; a marching volume wants larger ones.
     const bool long_flights = p.scene.n_lens != 0 && !p.scene.has_volume_prims;
     p.compact_lanes = knob(tn.compact_lanes, long_flights ? 12 : 16);
-    const bool bvh_rays = p.scene.n_bvh != 0 && p.scene.n_lens == 0;  // (patience counts node / leaf units there, ~7 per old unit)
-    p.compact_patience = knob(tn.compact_patience, long_flights ? 8 : (bvh_rays ? 96 : 16));
+    const bool bvh_rays = p.scene.n_bvh != 0 && p.scene.n_lens == 0;  // (patience counts node / leaf units there; gpurun_out/r2_sweep_bvh4.log)
+    p.compact_patience = knob(tn.compact_patience, long_flights ? 8 : (bvh_rays ? 32 : 16));
     // A scan over a handful of surface primitives costs less than half a ray generation: such a warp
     // is better off collecting more idle lanes first (scene.json.gz: +4.6 %, profiles/r1_sweep_regen2.log).
     const bool cheap_scans = p.scene.n_lens == 0 && !p.scene.has_volume_prims && p.scene.n_bvh == 0 && p.scene.n_prims <= 8;
-    p.regen_lanes = knob(tn.regen_lanes, long_flights ? 4 : (cheap_scans ? 24 : 12));
+    p.regen_lanes = knob(tn.regen_lanes, long_flights || bvh_rays ? 4 : (cheap_scans ? 24 : 12));
     p.regen_patience = knob(tn.regen_patience, long_flights ? 8 : (cheap_scans ? 32 : 16));
     p.scan_lanes = knob(tn.scan_lanes, 8);      // (profiles/r1_sweep_nearest_sphere_bound.log: flat within 1 % from 6/2 to 8/4)
     p.scan_patience = knob(tn.scan_patience, 3);
@@ -370,11 +370,12 @@ int build_params(const bt_engine* en, bt_scene* s, const SceneDev* dev, uint64_t
     if (use_exact(en, s) && p.scene.n_lens != 0) p.scene.lens_exact = 1;
     if (tn.lens_no_skip > 0) p.scene.lens_skip = 0;
     if (tn.lens_dist_grid == 0 && p.scene.lens_skip == 3) p.scene.lens_skip = 1;  // (A/B: the per-flight bookkeeping)
-    p.steps_per_turn = std::max(1u, knob(tn.steps_per_turn, long_flights ? 3 : 2));
+    p.steps_per_turn = std::max(1u, knob(tn.steps_per_turn, long_flights || bvh_rays ? 3 : 2));  // (pooled traversal: node visits in a row)
     // the pooled kernel (render_pool.cuh): 32 W path slots per warp; 0 = one path per lane (render_body)
     // default: on for lens fields (long flights: C3 +22 %, cornell2 + lens +60 %, cloud + lens +16 % over the lane kernel), off for
     // flat ones, whose scan -> shade ping-pong gains nothing from compaction and pays for the state traffic (C2 -12 %)
-    p.pool_w = std::min(knob(tn.pool_w, p.scene.n_lens != 0 ? 4 : 0), 8u);
+    // -- except BVH scenes, whose traversal runs as pooled NODE / LEAF phases (32 k primitives: 230 against 199 Msamples/s; W = 2 of {1, 2, 3, 4})
+    p.pool_w = std::min(knob(tn.pool_w, p.scene.n_lens != 0 ? 4 : (bvh_rays ? 2 : 0)), 8u);
     p.pool_refill = std::max(1u, knob(tn.pool_refill, 3));   // (gpurun_out/r2_sweep_pool_C3c.log: 3 / 32 best of {3, 6, 9} x {24, 28, 32})
     p.pool_step_min = knob(tn.pool_step_min, 32);
     p.pool_threads = knob(tn.pool_threads, 0) & ~31u;  // 0: the kernel's own CTA size (launch_pool)

@@ -37,7 +37,10 @@ enum {
     ST_HIT_STRAIGHT = 10,
     ST_NODE = 11, ST_LEAF = 12  // BVH scenes: a traversal waiting at an inner node / holding a leaf
 };
-enum { POOL_BVH_K = 8 };  // traversal stack levels of a slot kept in shared memory (the rest: the arena)
+#ifndef BT_POOL_BVH_K
+#define BT_POOL_BVH_K 8
+#endif
+enum { POOL_BVH_K = BT_POOL_BVH_K };  // traversal stack levels of a slot kept in shared memory (the rest: the arena)
 enum { POOL_RING = 16 };  // paths of one pixel in flight at most (in-order retirement window)
 enum { POOL_TILES = 8 };  // window of tiles a warp's lanes may be spread over
 
@@ -326,7 +329,7 @@ BT_DEV void render_pool_body(const RenderParams& p) {
                 bs.idx = (uint32_t)slot;
                 bs.k = POOL_BVH_K;
                 bs.over = pl.bover + (size_t)slot * (BVH_STACK - POOL_BVH_K);
-                bvh_leaf(t, sc.prims, bs, o, d, p.clip_min);
+                bvh_leaf<false, false>(t, sc.prims, bs, o, d, p.clip_min);
                 pl.fa[slot].w = t.h.t;
                 pl.fb[slot].w = __uint_as_float(pack_hit(t.h));
                 pl.tv[slot] = make_uint2(t.cur, t.sp | (t.best_strict ? 64u : 0u) | ((uint32_t)(t.best_canon + 1) << 7));

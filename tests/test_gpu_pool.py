@@ -162,3 +162,35 @@ def test_pool_full_size_c3_slice():
     ref = _render(sc, cam, w, h, 1, 2, pool_w=0)
     got = _render(sc, cam, w, h, 1, 2, pool_w=3)
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+def test_pool_bvh_traversal_equals_lane_kernel(precision):
+    """BVH scenes under a flat field: the pooled kernel runs the traversal as NODE / LEAF phases over its slots
+    (stack: 8 levels in shared memory, the rest in the arena).  Same rays, same tests, same tie rule as the lane
+    kernel's traversal: bit-identical in the exact flavour, to contraction rounding in the fast one (generic kernels)."""
+    import json
+
+    import bendy_tracer_b200 as bt
+    from common import synthetic_scene
+    w, h = 136, 76
+    docs = [json.dumps(synthetic_scene(300, 100, 20, seed=4)), json.dumps(synthetic_scene(3000, 500, 100, seed=5, extent=6.0))]
+    scenes = [bt.Scene.from_json(d) for d in docs]
+    sc2, _ = _scene("cornell2", w, h)
+    sc2.set_accel("bvh")
+    for sc in scenes + [sc2]:
+        sc.set_precision(precision)
+        cam = sc.find_by_tag("camera")
+        sc.set_camera_aspect(cam, float(np.float32(w) / np.float32(h)))
+        assert sc.info()["n_bvh_nodes"] > 0
+        ref = _render(sc, cam, w, h, 2, 2, pool_w=0)
+        for pool_w, turn in ((1, 1), (2, 2), (3, 4)):
+            got = _render(sc, cam, w, h, 2, 2, pool_w=pool_w, steps_per_turn=turn)
+            if precision == "exact":
+                assert np.array_equal(got, ref), (pool_w, f"{(got != ref).any(-1).sum()} pixels differ")
+            else:
+                assert (np.abs(got - ref).mean(axis=(0, 1)) / 8 <= 1e-6).all(), pool_w
+        for output in (1, 2, 3):
+            ref = _render(sc, cam, w, h, 1, 2, output=output, pool_w=0)
+            got = _render(sc, cam, w, h, 1, 2, output=output, pool_w=2)
+            assert np.array_equal(got, ref) if precision == "exact" else np.abs(got - ref).mean() <= 1e-5, output

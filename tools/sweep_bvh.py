@@ -47,3 +47,9 @@ if "sweep" in grid:
 if "quick" in grid:
     for cl, cp, rl, rp in ((16, 32, 8, 16), (16, 32, 4, 16), (16, 32, 6, 8), (12, 32, 4, 8), (16, 48, 2, 4)):
         print(f"compact {cl}/{cp} regen {rl}/{rp}: {run(compact_lanes=cl, compact_patience=cp, regen_lanes=rl, regen_patience=rp):.1f}", flush=True)
+if "pool" in grid:
+    for pw, turn in itertools.product((1, 2, 3), (1, 2, 3, 4)):
+        try:
+            print(f"pool_w {pw} steps_per_turn {turn}: {run(pool_w=pw, steps_per_turn=turn):.1f}", flush=True)
+        except Exception as e:
+            print(f"pool_w {pw}: {e}", flush=True)
