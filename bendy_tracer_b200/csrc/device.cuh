@@ -545,13 +545,12 @@ BT_DEV Hit scan_prims(const float4* prims, const float4* boxes, int n_prims, V3 
 // memory).  Same per-primitive tests as the scan; an exact-distance tie is decided by the canonical
 // primitive index exactly as the reference's scan order would: the later record wins unless it is a
 // cuboid face (strict '<', cuboid.rs:97).
-// entry distance of the ray into one child box of a 4-wide node, +inf when it misses
-BT_DEV float slab(float lx, float hx, float ly, float hy, float lz, float hz, V3 o, V3 inv, float tmin, float tmax) {
-    const float tx0 = (lx - o.x) * inv.x, tx1 = (hx - o.x) * inv.x;
-    const float ty0 = (ly - o.y) * inv.y, ty1 = (hy - o.y) * inv.y;
-    const float tz0 = (lz - o.z) * inv.z, tz1 = (hz - o.z) * inv.z;
-    const float tnear = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
-    const float tfar = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tmax));
+// entry distance of the ray into one child box of a 4-wide node, +inf when it misses.  (nx, fx): the box's plane the
+// ray meets first / last along x -- min.x and max.x, swapped for a ray that runs towards -x (bvh_node picks them by the
+// sign of 1 / d while it fetches, which saves the six min / max that would sort the plane distances here).
+BT_DEV float slab(float nx, float fx, float ny, float fy, float nz, float fz, V3 o, V3 inv, float tmin, float tmax) {
+    const float tnear = fmaxf(fmaxf((nx - o.x) * inv.x, (ny - o.y) * inv.y), fmaxf((nz - o.z) * inv.z, tmin));
+    const float tfar = fminf(fminf((fx - o.x) * inv.x, (fy - o.y) * inv.y), fminf((fz - o.z) * inv.z, tmax));
     // inclusive and slightly generous: never cull a scan hit
     return tnear <= tfar * 1.00001f + 1e-6f ? tnear : __int_as_float(0x7f800000);
 }
@@ -606,18 +605,18 @@ BT_DEV void bvh_push(BvhTrav& t, const BvhStack& st, uint32_t ref, float tn) {
 // pop, skipping subtrees that start beyond the hit found since they were pushed
 BT_DEV uint32_t bvh_pop(BvhTrav& t, const BvhStack& st) {
     uint32_t sp = t.sp, cur = BVH_DONE;
+    while (sp > st.k) {  // (the tail beyond the shared-memory levels: rarely entered)
+        --sp;
+        const uint2 e = st.over[sp - st.k];
+        if (__uint_as_float(e.y) <= t.h.t) {
+            t.sp = sp;
+            return e.x;
+        }
+    }
     while (sp != 0) {
         --sp;
-        uint32_t ref, tn;
-        if (sp < st.k) {
-            ref = st.base[sp * st.stride + st.idx];
-            tn = st.base[(st.k + sp) * st.stride + st.idx];
-        } else {
-            const uint2 e = st.over[sp - st.k];
-            ref = e.x;
-            tn = e.y;
-        }
-        if (__uint_as_float(tn) <= t.h.t) {
+        const uint32_t ref = st.base[sp * st.stride + st.idx];
+        if (__uint_as_float(st.base[(st.k + sp) * st.stride + st.idx]) <= t.h.t) {
             cur = ref;
             break;
         }
@@ -640,15 +639,15 @@ BT_DEV uint32_t bvh_pop(BvhTrav& t, const BvhStack& st) {
         ta = tlo;                               \
         ra = rlo;                               \
     }
-// the visit proper, on a fetched node (the seven float4 of layout.h)
-BT_DEV void bvh_node_visit(BvhTrav& t, float4 lx, float4 hx, float4 ly, float4 hy, float4 lz, float4 hz, float4 rf, const BvhStack& st, V3 o,
+// the visit proper, on a fetched node: the near and far planes of the four child boxes per axis (slab), the references
+BT_DEV void bvh_node_visit(BvhTrav& t, float4 nx, float4 fx, float4 ny, float4 fy, float4 nz, float4 fz, float4 rf, const BvhStack& st, V3 o,
                            V3 inv, float tmin) {
     const float inf = __int_as_float(0x7f800000);
     uint32_t r0 = __float_as_uint(rf.x), r1 = __float_as_uint(rf.y), r2 = __float_as_uint(rf.z), r3 = __float_as_uint(rf.w);
-    float t0 = slab(lx.x, hx.x, ly.x, hy.x, lz.x, hz.x, o, inv, tmin, t.h.t);
-    float t1 = slab(lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, o, inv, tmin, t.h.t);
-    float t2 = r2 != BVH_EMPTY ? slab(lx.z, hx.z, ly.z, hy.z, lz.z, hz.z, o, inv, tmin, t.h.t) : inf;
-    float t3 = r3 != BVH_EMPTY ? slab(lx.w, hx.w, ly.w, hy.w, lz.w, hz.w, o, inv, tmin, t.h.t) : inf;
+    float t0 = slab(nx.x, fx.x, ny.x, fy.x, nz.x, fz.x, o, inv, tmin, t.h.t);
+    float t1 = slab(nx.y, fx.y, ny.y, fy.y, nz.y, fz.y, o, inv, tmin, t.h.t);
+    float t2 = r2 != BVH_EMPTY ? slab(nx.z, fx.z, ny.z, fy.z, nz.z, fz.z, o, inv, tmin, t.h.t) : inf;
+    float t3 = r3 != BVH_EMPTY ? slab(nx.w, fx.w, ny.w, fy.w, nz.w, fz.w, o, inv, tmin, t.h.t) : inf;
     if (r1 == BVH_EMPTY) t1 = inf;  // (a node has at least one child; empty slots come last)
     // nearest first (misses, at +inf, sort last)
     BT_BVH_CSWAP(t0, r0, t1, r1)
@@ -657,57 +656,72 @@ BT_DEV void bvh_node_visit(BvhTrav& t, float4 lx, float4 hx, float4 ly, float4 h
     BT_BVH_CSWAP(t1, r1, t3, r3)
     BT_BVH_CSWAP(t1, r1, t2, r2)
     if (t0 < inf) {
-        if (t3 < inf) bvh_push(t, st, r3, t3);
-        if (t2 < inf) bvh_push(t, st, r2, t2);
-        if (t1 < inf) bvh_push(t, st, r1, t1);
+        if (t.sp + 3 <= st.k) {  // the usual case: straight-line, predicated stores
+            uint32_t* e = st.base + t.sp * st.stride + st.idx;
+            const uint32_t up = st.k * st.stride;
+            if (t3 < inf) {
+                e[0] = r3;
+                e[up] = __float_as_uint(t3);
+                e += st.stride;
+            }
+            if (t2 < inf) {
+                e[0] = r2;
+                e[up] = __float_as_uint(t2);
+                e += st.stride;
+            }
+            if (t1 < inf) {
+                e[0] = r1;
+                e[up] = __float_as_uint(t1);
+            }
+            t.sp += (t1 < inf ? 1u : 0u) + (t2 < inf ? 1u : 0u) + (t3 < inf ? 1u : 0u);
+        } else {
+            if (t3 < inf) bvh_push(t, st, r3, t3);
+            if (t2 < inf) bvh_push(t, st, r2, t2);
+            if (t1 < inf) bvh_push(t, st, r1, t1);
+        }
         t.cur = r0;
     } else {
         t.cur = bvh_pop(t, st);
     }
 }
-BT_DEV void bvh_node(BvhTrav& t, const float4* __restrict__ nodes, const BvhStack& st, V3 o, V3 inv, float tmin) {
+// sgn: bit k set when the ray runs towards -k (bvh_signs)
+BT_DEV uint32_t bvh_signs(V3 inv) { return (inv.x < 0.0f ? 1u : 0u) | (inv.y < 0.0f ? 2u : 0u) | (inv.z < 0.0f ? 4u : 0u); }
+BT_DEV void bvh_node(BvhTrav& t, const float4* __restrict__ nodes, const BvhStack& st, V3 o, V3 inv, uint32_t sgn, float tmin) {
     const float4* n = nodes + t.cur * BVH_STRIDE;
-    const float4 lx = __ldg(n), hx = __ldg(n + 1), ly = __ldg(n + 2), hy = __ldg(n + 3), lz = __ldg(n + 4), hz = __ldg(n + 5);
-    bvh_node_visit(t, lx, hx, ly, hy, lz, hz, __ldg(n + 6), st, o, inv, tmin);
+    const uint32_t sx = sgn & 1u, sy = (sgn >> 1) & 1u, sz = sgn >> 2;
+    const float4 nx = __ldg(n + sx), fx = __ldg(n + (sx ^ 1u)), ny = __ldg(n + 2 + sy), fy = __ldg(n + 2 + (sy ^ 1u));
+    const float4 nz = __ldg(n + 4 + sz), fz = __ldg(n + 4 + (sz ^ 1u));
+    bvh_node_visit(t, nx, fx, ny, fy, nz, fz, __ldg(n + 6), st, o, inv, tmin);
 }
 #undef BT_BVH_CSWAP
-// PIPE: software pipeline -- the next record's type word and first quarter are in flight while this one is tested (read on
-// demand, every record costs two dependent L2 round trips, type then geometry, in a loop that h.t serialises).  The lane
-// kernel gains 4 % from it; the pooled kernel, whose warps are short of registers rather than of loads in flight, loses 7 %.
-template <bool FLIGHT = false, bool PIPE = true>
+// The loop is software-pipelined: the next record's type word and first quarter are in flight while this one is tested (read
+// on demand, every record costs two dependent L2 round trips, type then geometry, in a loop that h.t serialises): +4 % in
+// the lane kernel, +1 % in the pooled one.
+template <bool FLIGHT = false>
 BT_DEV void bvh_leaf(BvhTrav& t, const float4* __restrict__ prims, const BvhStack& st, V3 o, V3 d, float tmin) {
     const uint32_t first = t.cur & 0x00ffffffu, count = (t.cur >> 24) & 0x7fu;
     const float4* q = prims + first * PRIM_STRIDE;
     int meta_n = 0;
     float4 q0_n = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    if (PIPE && count != 0) {
+    if (count != 0) {
         meta_n = __float_as_int(__ldg(&q[4].x));
         q0_n = __ldg(q);
     }
     for (uint32_t i = 0; i < count; ++i, q += PRIM_STRIDE) {
-        int meta;
-        float4 q0 = q0_n;
-        if (PIPE) {
-            meta = meta_n;
-            if (i + 1 < count) {
-                meta_n = __float_as_int(__ldg(&q[PRIM_STRIDE + 4].x));
-                q0_n = __ldg(q + PRIM_STRIDE);
-            }
-        } else {
-            meta = __float_as_int(__ldg(q + 4).x);
+        const int meta = meta_n;
+        const float4 q0 = q0_n;
+        if (i + 1 < count) {
+            meta_n = __float_as_int(__ldg(&q[PRIM_STRIDE + 4].x));
+            q0_n = __ldg(q + PRIM_STRIDE);
         }
         const int type = meta & 3, canon = meta >> PRIM_CANON_SHIFT;
         const bool strict = type == PRIM_CUBOID_FACE;
         float tt;
         bool front = true, ok;
-        if (type == PRIM_SPHERE) {  // r^2 = q1.x, formed here as the flattener forms it (one float product): q0 is the whole sphere
-            if (!PIPE) q0 = __ldg(q);
+        if (type == PRIM_SPHERE)  // r^2 = q1.x, formed here as the flattener forms it (one float product): q0 is the whole sphere
             ok = sphere_roots<FLIGHT>(q0, __fmul_rn(q0.w, q0.w), o, d, tmin, t.h.t, tt);
-        } else if (PIPE) {
+        else
             ok = rect_test_q(q0, __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), o, d, tmin, t.h.t, false, tt, front);
-        } else {
-            ok = rect_test(q, o, d, tmin, t.h.t, false, tt, front);
-        }
         if (ok) {
             // tt <= h.t here.  Equal distance: the later canonical index wins unless strict.
             bool take = tt < t.h.t;
@@ -731,8 +745,9 @@ BT_DEV Hit bvh_closest(const float4* __restrict__ prims, const float4* __restric
     const BvhStack st = bvh_lane_stack(stack, spill);
     bvh_begin(t, tmax);
     const V3 inv = v3(m_rcp(d.x), m_rcp(d.y), m_rcp(d.z));
+    const uint32_t sgn = bvh_signs(inv);
     while (t.cur != BVH_DONE) {  // "while-while": inside a warp the two phases never interleave
-        while (!(t.cur & BVH_LEAF)) bvh_node(t, nodes, st, o, inv, tmin);
+        while (!(t.cur & BVH_LEAF)) bvh_node(t, nodes, st, o, inv, sgn, tmin);
         if (t.cur != BVH_DONE) bvh_leaf<FLIGHT>(t, prims, st, o, d, tmin);
     }
     return t.h;

@@ -374,8 +374,8 @@ int build_params(const bt_engine* en, bt_scene* s, const SceneDev* dev, uint64_t
     // the pooled kernel (render_pool.cuh): 32 W path slots per warp; 0 = one path per lane (render_body)
     // default: on for lens fields (long flights: C3 +22 %, cornell2 + lens +60 %, cloud + lens +16 % over the lane kernel), off for
     // flat ones, whose scan -> shade ping-pong gains nothing from compaction and pays for the state traffic (C2 -12 %)
-    // -- except BVH scenes, whose traversal runs as pooled NODE / LEAF phases (32 k primitives: 230 against 199 Msamples/s; W = 2 of {1, 2, 3, 4})
-    p.pool_w = std::min(knob(tn.pool_w, p.scene.n_lens != 0 ? 4 : (bvh_rays ? 2 : 0)), 8u);
+    // -- except BVH scenes, whose traversal runs as pooled NODE / LEAF phases (32 k primitives: 238 against 221 Msamples/s; W = 3 of {1, 2, 3, 4})
+    p.pool_w = std::min(knob(tn.pool_w, p.scene.n_lens != 0 ? 4 : (bvh_rays ? 3 : 0)), 8u);
     p.pool_refill = std::max(1u, knob(tn.pool_refill, 3));   // (gpurun_out/r2_sweep_pool_C3c.log: 3 / 32 best of {3, 6, 9} x {24, 28, 32})
     p.pool_step_min = knob(tn.pool_step_min, 32);
     p.pool_threads = knob(tn.pool_threads, 0) & ~31u;  // 0: the kernel's own CTA size (launch_pool)

@@ -611,6 +611,7 @@ BT_DEV void render_body(const RenderParams& p) {
                 bstate = 1;
             }
             const V3 inv = v3(m_rcp(d.x), m_rcp(d.y), m_rcp(d.z));
+            const uint32_t sgn = bvh_signs(inv);
             uint32_t waited = 0;
 #pragma unroll 1
             for (;;) {
@@ -619,7 +620,7 @@ BT_DEV void render_body(const RenderParams& p) {
                 const unsigned m_leaf = __ballot_sync(0xffffffffu, bstate == 1 && at_leaf);
                 if ((m_node | m_leaf) == 0) break;
                 if (__popc(m_node) >= __popc(m_leaf)) {
-                    if (bstate == 1 && !at_leaf) bvh_node(btrav, sc.nodes, bstack, o, inv, p.clip_min);
+                    if (bstate == 1 && !at_leaf) bvh_node(btrav, sc.nodes, bstack, o, inv, sgn, p.clip_min);
                 } else {
                     if (bstate == 1 && at_leaf) bvh_leaf(btrav, sc.prims, bstack, o, d, p.clip_min);
                 }
@@ -735,7 +736,7 @@ __global__ void BT_POOL_BOUNDS(LENS) render_pool_kernel(const __grid_constant__ 
 }
 // BVH scenes under a flat field: the scan is a pooled traversal (NODE / LEAF phases)
 #ifndef BT_BVH_POOL_CTAS
-#define BT_BVH_POOL_CTAS 6
+#define BT_BVH_POOL_CTAS 5  // (96 registers, no spills; W = 3: 238 Msamples/s on the 32 k-primitive scene against 223 .. 232 at 6 CTAs x 80 registers, W = 2)
 #endif
 template <int C>
 __global__ void __launch_bounds__(128, BT_BVH_POOL_CTAS) render_pool_bvh_kernel(const __grid_constant__ RenderParams p) {

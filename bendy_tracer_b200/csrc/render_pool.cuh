@@ -286,8 +286,9 @@ BT_DEV void render_pool_body(const RenderParams& p) {
                 bs.k = POOL_BVH_K;
                 bs.over = pl.bover + (size_t)slot * (BVH_STACK - POOL_BVH_K);
                 const V3 inv = v3(m_rcp(d.x), m_rcp(d.y), m_rcp(d.z));
+                const uint32_t sgn = bvh_signs(inv);
 #pragma unroll 1
-                for (uint32_t r = 0; r < p.steps_per_turn && !(t.cur & BVH_LEAF); ++r) bvh_node(t, sc.nodes, bs, o, inv, p.clip_min);
+                for (uint32_t r = 0; r < p.steps_per_turn && !(t.cur & BVH_LEAF); ++r) bvh_node(t, sc.nodes, bs, o, inv, sgn, p.clip_min);
                 pl.tv[slot] = make_uint2(t.cur, (tv.y & ~63u) | t.sp);
                 if (t.cur == BVH_DONE) {
                     pl.st[slot] = ST_HIT_STRAIGHT;
@@ -329,7 +330,7 @@ BT_DEV void render_pool_body(const RenderParams& p) {
                 bs.idx = (uint32_t)slot;
                 bs.k = POOL_BVH_K;
                 bs.over = pl.bover + (size_t)slot * (BVH_STACK - POOL_BVH_K);
-                bvh_leaf<false, false>(t, sc.prims, bs, o, d, p.clip_min);
+                bvh_leaf(t, sc.prims, bs, o, d, p.clip_min);
                 pl.fa[slot].w = t.h.t;
                 pl.fb[slot].w = __uint_as_float(pack_hit(t.h));
                 pl.tv[slot] = make_uint2(t.cur, t.sp | (t.best_strict ? 64u : 0u) | ((uint32_t)(t.best_canon + 1) << 7));

@@ -23,7 +23,7 @@ GROUPS = [  # (region label, function-name regex) for device.cuh
     ("rng (xoshiro256++, seeding, Uniform / Bernoulli)", r"^(rotl64|splitmix_mix|next_u64|next_u32|seed_from_u64|path_seed|uniform_f32|standard_f32|gen_bool|uniform_index|Rng)$"),
     ("sincos", r"^bt_sincos$"),
     ("sphere test", r"^(sphere_roots\w*|sqrt_approx|sphere_free_bound|free_update|FreeInfo)$"),
-    ("rect test (general)", r"^(rect_test|sdot|sat|sdiv)$"),
+    ("rect test (general)", r"^(rect_test|rect_test_q|sdot|sat|sdiv)$"),
     ("rect test (axis-aligned)", r"^(rect_test_aa|comp|sat1)$"),
     ("box slab test", r"^(box_test|rcp_approx)$"),
     ("scan loop", r"^(scan_prims\w*|Hit)$"),
@@ -53,6 +53,8 @@ POOL_MARKS = [  # render_pool.cuh
     (r"^enum \{", "pool: layout / collect"),
     (r"BT_DEV void render_pool_body", "pool: prologue + phase selection"),
     (r"=+ STEP =+", "pool: STEP loop control + refill rounds"),
+    (r"=+ NODE =+", "pool: NODE pass (BVH scenes: state load / store, queues)"),
+    (r"=+ LEAF =+", "pool: LEAF pass (BVH scenes: state load / store, queues)"),
     (r"=+ SCAN =+", "pool: SCAN pass (state load / store, queues)"),
     (r"=+ SHADE =+", "pool: SHADE pass (state load / store, queues)"),
     (r"=+ REGEN =+", "pool: REGEN pass (retire, pixel stream, issue)"),
