@@ -571,15 +571,15 @@ struct BvhStack {
     uint32_t stride, idx, k;
     uint2* over;
 };
-struct BvhSpill {  // stack levels BVH_STACK_SMEM .. BVH_STACK - 1 of one lane
-    uint2 e[BVH_STACK - BVH_STACK_SMEM];
+struct BvhSpill {  // the stack levels of one lane beyond those in shared memory (k >= 1: room for all of them)
+    uint2 e[BVH_STACK];
 };
-BT_DEV BvhStack bvh_lane_stack(uint32_t* stack, BvhSpill& spill) {
+BT_DEV BvhStack bvh_lane_stack(uint32_t* stack, BvhSpill& spill, uint32_t k = BVH_STACK_SMEM) {
     BvhStack s;
     s.base = stack;
     s.stride = blockDim.x;
     s.idx = threadIdx.x;
-    s.k = BVH_STACK_SMEM;
+    s.k = min(k, (uint32_t)BVH_STACK_SMEM);
     s.over = spill.e;
     return s;
 }

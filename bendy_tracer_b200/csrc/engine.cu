@@ -40,7 +40,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 struct Tuning {
     int64_t compact_lanes = -1, compact_patience = -1, regen_lanes = -1, regen_patience = -1, scan_lanes = -1, scan_patience = -1;
     int64_t steps_per_turn = -1, lens_no_skip = -1, lens_dist_grid = -1, host_bands = -1;
-    int64_t pool_w = -1, pool_refill = -1, pool_step_min = -1, pool_threads = -1;
+    int64_t pool_w = -1, pool_refill = -1, pool_step_min = -1, pool_threads = -1, bvh_stack_k = -1;
 };
 struct TuningName {
     const char* name;
@@ -54,6 +54,7 @@ static const TuningName kTuning[] = {
     {"host_bands", &Tuning::host_bands},
     {"pool_w", &Tuning::pool_w},               {"pool_refill", &Tuning::pool_refill},
     {"pool_step_min", &Tuning::pool_step_min}, {"pool_threads", &Tuning::pool_threads},
+    {"bvh_stack_k", &Tuning::bvh_stack_k},
 };
 
 struct bt_engine {
@@ -379,6 +380,7 @@ int build_params(const bt_engine* en, bt_scene* s, const SceneDev* dev, uint64_t
     p.pool_refill = std::max(1u, knob(tn.pool_refill, 3));   // (gpurun_out/r2_sweep_pool_C3c.log: 3 / 32 best of {3, 6, 9} x {24, 28, 32})
     p.pool_step_min = knob(tn.pool_step_min, 32);
     p.pool_threads = knob(tn.pool_threads, 0) & ~31u;  // 0: the kernel's own CTA size (launch_pool)
+    p.bvh_stack_k = std::max(1u, knob(tn.bvh_stack_k, 0xffffu));  // (tests: force the traversal stack's tail)
     p.tau_scale = uniform_scale_inclusive(0.0f, 6.28318530717958647692f);
     p.one_scale = uniform_scale_inclusive(0.0f, 1.0f);
     *out = p;

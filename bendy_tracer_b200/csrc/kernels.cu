@@ -553,7 +553,7 @@ BT_DEV void render_body(const RenderParams& p) {
     int fstate = FL_FLY;
     BvhTrav btrav;  // BVH && !LENS: the traversal this lane is in
     BvhSpill bspill;
-    const BvhStack bstack = bvh_lane_stack(sc.stack, bspill);
+    const BvhStack bstack = bvh_lane_stack(sc.stack, bspill, p.bvh_stack_k);
     bvh_begin(btrav, 0.0f);
     int bstate = 0;  // 0 none, 1 traversing, 2 done
 

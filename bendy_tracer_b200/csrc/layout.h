@@ -144,6 +144,7 @@ struct RenderParams {
     uint32_t pool_refill;            // STEP: lanes that wait for a flight before the warp pays for a refill round
     uint32_t pool_step_min;          // STEP: with the stack empty, keep stepping while at least this many lanes fly
     uint32_t pool_threads;           // CTA size of the pooled kernel
+    uint32_t bvh_stack_k;            // BVH traversal: stack levels kept in shared memory (clamped to what the kernel allocates)
     unsigned long long* pool_counter;  // ... and its tile counter (zeroed before every launch)
     char* pool_q;                    // the pooled kernel's path-state arena: pool_q_bytes per warp of its grid (device memory)
     uint64_t pool_q_cap;             // bytes available at pool_q (bounds the grid)

@@ -283,7 +283,7 @@ BT_DEV void render_pool_body(const RenderParams& p) {
                 bs.base = pl.bstack;
                 bs.stride = P;
                 bs.idx = (uint32_t)slot;
-                bs.k = POOL_BVH_K;
+                bs.k = min(p.bvh_stack_k, (uint32_t)POOL_BVH_K);
                 bs.over = pl.bover + (size_t)slot * (BVH_STACK - POOL_BVH_K);
                 const V3 inv = v3(m_rcp(d.x), m_rcp(d.y), m_rcp(d.z));
                 const uint32_t sgn = bvh_signs(inv);
@@ -328,7 +328,7 @@ BT_DEV void render_pool_body(const RenderParams& p) {
                 bs.base = pl.bstack;
                 bs.stride = P;
                 bs.idx = (uint32_t)slot;
-                bs.k = POOL_BVH_K;
+                bs.k = min(p.bvh_stack_k, (uint32_t)POOL_BVH_K);
                 bs.over = pl.bover + (size_t)slot * (BVH_STACK - POOL_BVH_K);
                 bvh_leaf(t, sc.prims, bs, o, d, p.clip_min);
                 pl.fa[slot].w = t.h.t;

@@ -132,6 +132,7 @@ uint64_t bt_engine_launch_count(const bt_engine* engine);
  *   host_bands      row bands a BT_MEM_HOST frame is pipelined in (bt_render)
  *   compact_lanes, compact_patience, regen_lanes, regen_patience, scan_lanes, scan_patience,
  *   steps_per_turn                               thresholds of the one-path-per-lane kernel
+ *   bvh_stack_k     BVH traversal: stack levels kept in shared memory (fewer = more of the stack in its slow tail; tests)
  *   lens_no_skip    1: as BT_LENS_NO_SKIP for every scene */
 int bt_engine_set_tuning(bt_engine* engine, const char* name, int64_t value);
 

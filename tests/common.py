@@ -143,3 +143,27 @@ def cornell_with_cuboid_light(extra_rect_light=True):
     if not extra_rect_light:
         objs["6"]["flags"]["bits"] = 0
     return doc
+
+
+def skewed_scene(n_coincident=200, n_chain=200, chain_radius=0.0):
+    """synthetic_scene's fixtures plus n_coincident spheres on one spot and a geometric chain x = 8 * 2^-i that makes
+    every SAH split lopsided (the BVH builder's depth budget / median fallback; deep, narrow trees for the traversal).
+    chain_radius > 0: the chain spheres get radius chain_radius * x (disjoint, visible), else 0.01."""
+    import json
+    doc = synthetic_scene(0, 0, 0, seed=3)
+    objs = doc["objects"]["collection"]
+    key = doc["objects"]["next_key"]
+    proto = objs["2"]
+    for i in range(n_coincident + n_chain):
+        o = json.loads(json.dumps(proto))
+        o["object_ref"] = key
+        o["flags"] = {"bits": 0}
+        x = 0.0 if i < n_coincident else float(np.float32(2.0 ** -(i - n_coincident) * 8.0))
+        o["inner"]["Sphere"]["radius"] = float(np.float32(chain_radius * x)) if chain_radius > 0 and i >= n_coincident else 0.01
+        t = o["transform"]["transform_world"]
+        t[9:12] = [x, 0.5, 0.0]
+        o["transform"]["transform_local"] = list(t)
+        objs[str(key)] = o
+        key += 1
+    doc["objects"]["next_key"] = key
+    return doc

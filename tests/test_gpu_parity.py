@@ -581,6 +581,34 @@ def test_bvh_equals_linear_scan_on_shipped_scenes(name, lens):
             assert (d > 1e-3).mean() < 5e-3 and np.median(d) <= 1e-6, ((d > 1e-3).mean(), np.median(d))
 
 
+def test_bvh_deep_narrow_tree_equals_linear_scan():
+    """Coincident spheres (leaves of up to 127 records) and a geometric chain of disjoint spheres (every SAH split
+    lopsided: a deep, narrow tree): BVH == linear scan bit for bit in the exact flavour -- through the lane kernel and
+    the pooled traversal, with the stack in shared memory and with all but one level of it in its slow tail."""
+    import json
+    import bendy_tracer_b200 as bt
+    from common import skewed_scene
+    w, h = 128, 72
+    for chain_radius in (0.0, 0.3):
+        esc = bt.Scene.from_json(json.dumps(skewed_scene(120, 60, chain_radius)))
+        cam = esc.find_by_tag("camera")
+        esc.set_camera_aspect(cam, float(np.float32(w) / np.float32(h)))
+        esc.set_precision("exact")
+        esc.set_accel("linear_faces")
+        ref = engine_render(esc, cam, w, h, 2, 2, 0, seed=6)[0].copy()
+        assert np.isfinite(ref).all() and ref[..., :3].sum() > 0
+        esc.set_accel("bvh")
+        assert esc.info()["n_bvh_nodes"] > 3
+        eng = bt.Engine.default(0)
+        for knobs in ({}, {"pool_w": 0}, {"bvh_stack_k": 1}, {"pool_w": 0, "bvh_stack_k": 1}):
+            eng.set_tuning(**knobs)
+            try:
+                got = engine_render(esc, cam, w, h, 2, 2, 0, seed=6)[0].copy()
+            finally:
+                eng.set_tuning(**{k: None for k in knobs})
+            assert np.array_equal(got, ref), (chain_radius, knobs, int((got != ref).any(-1).sum()))
+
+
 def test_bvh_synthetic_scene_vs_oracle(oracle):
     """a 500-primitive scene: BVH render == linear-scan render bit for bit, and both match the oracle"""
     import json

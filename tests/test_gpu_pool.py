@@ -194,3 +194,12 @@ def test_pool_bvh_traversal_equals_lane_kernel(precision):
             ref = _render(sc, cam, w, h, 1, 2, output=output, pool_w=0)
             got = _render(sc, cam, w, h, 1, 2, output=output, pool_w=2)
             assert np.array_equal(got, ref) if precision == "exact" else np.abs(got - ref).mean() <= 1e-5, output
+        # the traversal stack's slow tail (local memory in the lane kernel, the arena in the pooled one) holds everything
+        # beyond ONE shared-memory level here: same images
+        ref = _render(sc, cam, w, h, 2, 2, pool_w=0)
+        for pool_w in (0, 3):
+            got = _render(sc, cam, w, h, 2, 2, pool_w=pool_w, bvh_stack_k=1)
+            if precision == "exact" or pool_w == 0:
+                assert np.array_equal(got, ref), (pool_w, "bvh_stack_k=1")
+            else:
+                assert (np.abs(got - ref).mean(axis=(0, 1)) / 8 <= 1e-6).all(), pool_w

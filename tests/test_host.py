@@ -408,23 +408,8 @@ def test_json_nesting_limit_is_an_error_not_a_crash():
 def test_bvh_build_survives_skewed_and_coincident_primitives():
     """200 spheres on one spot and a geometric cluster that makes every SAH split lopsided: the builder falls back to
     median splits near its depth budget instead of rejecting the scene (flattening happens at load: no GPU needed)"""
-    from common import synthetic_scene
-    doc = synthetic_scene(0, 0, 0, seed=3)
-    objs = doc["objects"]["collection"]
-    key = doc["objects"]["next_key"]
-    proto = objs["2"]
-    for i in range(400):
-        o = json.loads(json.dumps(proto))
-        o["object_ref"] = key
-        o["flags"] = {"bits": 0}
-        o["inner"]["Sphere"]["radius"] = 0.01
-        t = o["transform"]["transform_world"]
-        x = 0.0 if i < 200 else float(np.float32(2.0 ** -(i - 200) * 8.0))      # coincident, then geometrically spaced
-        t[9:12] = [x, 0.5, 0.0]
-        o["transform"]["transform_local"] = list(t)
-        objs[str(key)] = o
-        key += 1
-    doc["objects"]["next_key"] = key
+    from common import skewed_scene
+    doc = skewed_scene()
     sc = bt.Scene.from_json(json.dumps(doc))
     sc.set_accel("bvh")
     info = sc.info()
