@@ -66,6 +66,7 @@ SIGNATURES = {
     "bt_scene_set_accel": (C.c_int, [_P, C.c_int]),
     "bt_scene_set_precision": (C.c_int, [_P, C.c_int]),
     "bt_scene_get_info": (C.c_int, [_P, C.POINTER(BtSceneInfo)]),
+    "bt_scene_copy_bvh": (C.c_int, [_P, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64]),
     "bt_config_default": (None, [C.POINTER(BtConfig)]),
     "bt_render_config_default": (None, [C.POINTER(BtRenderConfig)]),
     "bt_render": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(BtConfig), C.POINTER(BtRenderConfig), C.c_uint64,

@@ -281,6 +281,18 @@ class Scene:
         check(lib.bt_scene_get_info(self.handle, C.byref(i)))
         return {k: getattr(i, k) for k, _ in i._fields_}
 
+    def bvh(self):
+        """the acceleration structure as of the last flatten / commit (bt_scene_copy_bvh): `nodes` float32 [n, 8, 4]
+        (min.x max.x min.y max.y min.z max.z of the four children, then the child references -- see `refs`),
+        `refs` uint32 [n, 4], `order` uint32 [n_primitives] (tree position -> canonical index), `bounds` float32
+        [n_primitives, 6] (canonical order)"""
+        i = self.info()
+        nodes = np.zeros((i["n_bvh_nodes"], 8, 4), np.float32)
+        order = np.zeros(i["n_primitives"], np.uint32)
+        bounds = np.zeros((i["n_primitives"], 6), np.float32)
+        check(lib.bt_scene_copy_bvh(self.handle, nodes.ctypes.data, nodes.shape[0], order.ctypes.data, bounds.ctypes.data, order.shape[0]))
+        return {"nodes": nodes, "refs": nodes[:, 6, :].copy().view(np.uint32), "order": order, "bounds": bounds}
+
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None
         if h:

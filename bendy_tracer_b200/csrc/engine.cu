@@ -723,6 +723,30 @@ int bt_scene_get_info(const bt_scene* scene, bt_scene_info* info) {
     GUARD_END
 }
 
+int bt_scene_copy_bvh(const bt_scene* scene, float* nodes, uint64_t nodes_cap, uint32_t* order, float* bounds, uint64_t prims_cap) {
+    if (!scene) return fail(BT_ERR_INVALID_ARG, "NULL argument");
+    GUARD_BEGIN
+    FlatScene tmp;
+    const FlatScene* f = &scene->flat;
+    if (scene->flat_dirty) {
+        tmp = flatten(scene->scene, scene->accel);
+        f = &tmp;
+    }
+    const SceneHeader& h = f->header;
+    if ((nodes && nodes_cap < h.n_bvh) || ((order || bounds) && prims_cap < h.n_prims)) return fail(BT_ERR_INVALID_ARG, "buffer too small");
+    if (nodes && h.n_bvh) std::memcpy(nodes, &f->blob[h.bvh_off], (size_t)h.n_bvh * BVH_STRIDE * sizeof(float4));
+    if (order)
+        for (uint32_t i = 0; i < h.n_prims; ++i) order[i] = f->prim_order[i];
+    if (bounds)
+        for (uint32_t i = 0; i < h.n_prims; ++i)
+            for (int k = 0; k < 3; ++k) {
+                bounds[i * 6 + k] = f->prim_bounds[i].lo[k];
+                bounds[i * 6 + 3 + k] = f->prim_bounds[i].hi[k];
+            }
+    return BT_OK;
+    GUARD_END
+}
+
 void bt_config_default(bt_config* c) {
     if (!c) return;
     c->max_bounces = 8;

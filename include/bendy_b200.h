@@ -183,6 +183,13 @@ int bt_scene_set_accel(bt_scene* scene, int accel);
 enum { BT_PRECISION_AUTO = 0, BT_PRECISION_FAST = 1, BT_PRECISION_EXACT = 2 };
 int bt_scene_set_precision(bt_scene* scene, int precision);
 int bt_scene_get_info(const bt_scene* scene, bt_scene_info* info);
+/* Introspection of the acceleration structure (tests, tools; an extension like the BVH itself): copies the 4-wide nodes
+ * (32 floats per node: min.x[4] max.x[4] min.y[4] max.y[4] min.z[4] max.z[4], four child references as raw 32-bit
+ * patterns, four unused -- child: inner node index, 0x80000000 | count << 24 | first record, or 0xfffffffe = empty), the
+ * record order (tree position -> canonical primitive index) and the primitives' bounds (6 floats each: min xyz, max
+ * xyz, canonical order) as of the last flatten / commit.  Any pointer may be NULL; capacities in nodes / primitives;
+ * BT_ERR_INVALID_ARG when one is too small (bt_scene_get_info gives the counts). */
+int bt_scene_copy_bvh(const bt_scene* scene, float* nodes, uint64_t nodes_cap, uint32_t* order, float* bounds, uint64_t prims_cap);
 
 /* ---- the hot path ---------------------------------------------------------------------- */
 void bt_config_default(bt_config* cfg);                /* Config::DEFAULT, mod.rs:29-38 */

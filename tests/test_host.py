@@ -414,3 +414,84 @@ def test_bvh_build_survives_skewed_and_coincident_primitives():
     sc.set_accel("bvh")
     info = sc.info()
     assert info["n_primitives"] == 402 and info["n_bvh_nodes"] > 3
+
+
+def _check_bvh(sc, max_depth=11):
+    """structural invariants of the 4-wide BVH (bt_scene_copy_bvh): every primitive in exactly one leaf, every child box
+    holds what is below it (conservatively padded), empty slots last, children stored behind their parent, depth and
+    stack demand within what the traversal kernels allocate"""
+    b = sc.bvh()
+    nodes, refs, order, bounds = b["nodes"], b["refs"], b["order"], b["bounds"]
+    n, n_prims = len(nodes), len(order)
+    assert n > 0 and sorted(order.tolist()) == list(range(n_prims))
+    LEAF, EMPTY = 0x80000000, 0xFFFFFFFE
+    seen = np.zeros(n_prims, np.int32)
+    visited = np.zeros(n, np.int32)
+    deepest = 0
+
+    def walk(node, depth):
+        nonlocal deepest
+        deepest = max(deepest, depth)
+        visited[node] += 1
+        lo = np.full(3, np.inf, np.float32)
+        hi = np.full(3, -np.inf, np.float32)
+        empty_seen = False
+        for c in range(4):
+            r = int(refs[node, c])
+            if r == EMPTY:
+                empty_seen = True
+                continue
+            assert not empty_seen, "an empty slot before a child"
+            box_lo, box_hi = nodes[node, 0:6:2, c], nodes[node, 1:6:2, c]
+            if r & LEAF:
+                first, count = r & 0xFFFFFF, (r >> 24) & 0x7F
+                assert 1 <= count <= 127 and first + count <= n_prims
+                prims = order[first:first + count]
+                seen[first:first + count] += 1
+                c_lo, c_hi = bounds[prims, :3].min(0), bounds[prims, 3:].max(0)
+            else:
+                assert node < r < n, "children are stored behind their parent (refit sweeps backwards)"
+                c_lo, c_hi = walk(r, depth + 1)
+            assert (box_lo <= c_lo).all() and (box_hi >= c_hi).all(), (node, c)
+            pad = 2e-4 * np.maximum(1, np.maximum(np.abs(box_lo), np.abs(box_hi))) + 1e-6     # (the builder pads by 1e-4 of that)
+            if not (node == 0 and r & LEAF):      # (the leaf of scene-spanning primitives carries the whole scene's box)
+                assert (c_lo - box_lo <= pad).all() and (box_hi - c_hi <= pad).all(), "the box is the padded union, no looser"
+            lo, hi = np.minimum(lo, c_lo), np.maximum(hi, c_hi)
+        assert refs[node, 0] != EMPTY
+        return lo, hi
+
+    sys.setrecursionlimit(10000)
+    walk(0, 1)
+    assert (seen == 1).all() and (visited == 1).all()
+    assert deepest <= max_depth and 3 * deepest <= 40       # BVH_STACK (layout.h): 3 pushes per level
+    return deepest
+
+
+def test_bvh4_structure_and_refit():
+    from common import skewed_scene, synthetic_scene
+    for doc in (synthetic_scene(300, 100, 20, seed=4), synthetic_scene(3000, 500, 100, seed=5, extent=6.0), skewed_scene(), skewed_scene(120, 60, 0.3)):
+        sc = bt.Scene.from_json(json.dumps(doc))
+        sc.set_accel("bvh")
+        _check_bvh(sc)
+    # a shipped scene forced onto the BVH (a scene-spanning ground sphere goes to its own leaf beside the tree)
+    sc = bt.Scene.load(O.scene_path("scene"))
+    sc.set_accel("bvh")
+    _check_bvh(sc)
+    # refit after transform edits: same topology, boxes follow the primitives
+    doc = synthetic_scene(3000, 500, 100, seed=5, extent=6.0)
+    sc = bt.Scene.from_json(json.dumps(doc))
+    before = sc.bvh()
+    objs = json.loads(sc.to_json())["objects"]["collection"]
+    moved = [int(k) for k in list(objs)[10:400:7]]
+    for ref in moved:
+        t = list(objs[str(ref)]["transform"]["transform_world"])
+        t[9] += 0.37
+        t[11] -= 0.21
+        sc.apply_transform(ref, t)
+    sc.commit()
+    after = sc.bvh()
+    assert np.array_equal(before["refs"], after["refs"]) and np.array_equal(before["order"], after["order"])
+    assert not np.array_equal(before["bounds"], after["bounds"]) and not np.array_equal(before["nodes"], after["nodes"])
+    _check_bvh(sc)
+    fresh = bt.Scene.from_json(sc.to_json())
+    assert np.array_equal(np.sort(fresh.bvh()["bounds"], axis=0), np.sort(after["bounds"], axis=0))
