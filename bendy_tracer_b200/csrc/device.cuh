@@ -560,8 +560,6 @@ BT_DEV float slab(float nx, float fx, float ny, float fy, float nz, float fz, V3
 struct BvhTrav {
     uint32_t cur, sp;
     Hit h;
-    int best_canon;
-    bool best_strict;
 };
 // Where one traversal keeps its stack: levels < k in shared memory (entry `level * stride + idx`, the entry
 // distances k * stride words further), the rarely reached rest in `over` (local memory in the lane kernel, a
@@ -590,8 +588,6 @@ BT_DEV void bvh_begin(BvhTrav& t, float tmax) {
     t.h.t = tmax;
     t.h.prim = -1;
     t.h.face = 0;
-    t.best_canon = -1;
-    t.best_strict = false;
 }
 BT_DEV void bvh_push(BvhTrav& t, const BvhStack& st, uint32_t ref, float tn) {
     if (t.sp < st.k) {
@@ -694,44 +690,57 @@ BT_DEV void bvh_node(BvhTrav& t, const float4* __restrict__ nodes, const BvhStac
     bvh_node_visit(t, nx, fx, ny, fy, nz, fz, __ldg(n + 6), st, o, inv, tmin);
 }
 #undef BT_BVH_CSWAP
-// The loop is software-pipelined: the next record's type word and first quarter are in flight while this one is tested (read
-// on demand, every record costs two dependent L2 round trips, type then geometry, in a loop that h.t serialises): +4 % in
-// the lane kernel, +1 % in the pooled one.
+// An exact-distance tie (tt == h.t, h.t possibly still the far clip with no hit behind it) is decided as the reference's scan
+// order would decide it: the record that comes later in canonical order wins unless it is a cuboid face (strict '<',
+// cuboid.rs:97).  Ties are rare (shared cuboid edges, coincident primitives), so the canonical index and the type of the
+// two records are read only then -- the common path of a leaf test never touches q4.
+BT_DEV bool bvh_tie_take(const float4* __restrict__ prims, int held, int cand) {
+    int held_canon = -1;
+    bool held_strict = false;
+    if (held >= 0) {
+        const int m = __float_as_int(__ldg(&prims[held * PRIM_STRIDE + 4].x));
+        held_canon = m >> PRIM_CANON_SHIFT;
+        held_strict = (m & 3) == PRIM_CUBOID_FACE;
+    }
+    const int m = __float_as_int(__ldg(&prims[cand * PRIM_STRIDE + 4].x));
+    return (m >> PRIM_CANON_SHIFT) > held_canon ? (m & 3) != PRIM_CUBOID_FACE : held_strict;
+}
+// The records of the leaf held in t.cur, then pop.  The reference tells what the leaf holds (layout.h): all spheres (one
+// float4 per test: r^2 is formed as the flattener forms it, one float product), no sphere (four float4), or a mix (the type
+// word of every record is read first).  The builder makes leaves of ONE record, so the loops run once except for
+// coincident primitives; the sphere loop keeps the next record in flight.
 template <bool FLIGHT = false>
 BT_DEV void bvh_leaf(BvhTrav& t, const float4* __restrict__ prims, const BvhStack& st, V3 o, V3 d, float tmin) {
-    const uint32_t first = t.cur & 0x00ffffffu, count = (t.cur >> 24) & 0x7fu;
+    const uint32_t first = t.cur & 0x00ffffffu, count = (t.cur >> 24) & 0x1fu, kind = (t.cur >> 29) & 3u;
     const float4* q = prims + first * PRIM_STRIDE;
-    int meta_n = 0;
-    float4 q0_n = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    if (count != 0) {
-        meta_n = __float_as_int(__ldg(&q[4].x));
-        q0_n = __ldg(q);
-    }
-    for (uint32_t i = 0; i < count; ++i, q += PRIM_STRIDE) {
-        const int meta = meta_n;
-        const float4 q0 = q0_n;
-        if (i + 1 < count) {
-            meta_n = __float_as_int(__ldg(&q[PRIM_STRIDE + 4].x));
-            q0_n = __ldg(q + PRIM_STRIDE);
+    if (kind == BVH_KIND_SPHERES) {
+        float4 q0_n = __ldg(q);
+        for (uint32_t i = 0; i < count; ++i, q += PRIM_STRIDE) {
+            const float4 q0 = q0_n;
+            if (i + 1 < count) q0_n = __ldg(q + PRIM_STRIDE);
+            float tt;
+            if (sphere_roots<FLIGHT>(q0, __fmul_rn(q0.w, q0.w), o, d, tmin, t.h.t, tt)) {
+                if (tt < t.h.t || bvh_tie_take(prims, t.h.prim, (int)(first + i))) {  // (tt <= h.t here)
+                    t.h.t = tt;
+                    t.h.prim = (int)(first + i);
+                    t.h.face = 8;
+                }
+            }
         }
-        const int type = meta & 3, canon = meta >> PRIM_CANON_SHIFT;
-        const bool strict = type == PRIM_CUBOID_FACE;
-        float tt;
-        bool front = true, ok;
-        if (type == PRIM_SPHERE)  // r^2 = q1.x, formed here as the flattener forms it (one float product): q0 is the whole sphere
-            ok = sphere_roots<FLIGHT>(q0, __fmul_rn(q0.w, q0.w), o, d, tmin, t.h.t, tt);
-        else
-            ok = rect_test_q(q0, __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), o, d, tmin, t.h.t, false, tt, front);
-        if (ok) {
-            // tt <= h.t here.  Equal distance: the later canonical index wins unless strict.
-            bool take = tt < t.h.t;
-            if (!take) take = canon > t.best_canon ? !strict : t.best_strict;
-            if (take) {
+    } else {
+        for (uint32_t i = 0; i < count; ++i, q += PRIM_STRIDE) {
+            const bool sphere = kind != BVH_KIND_RECTS && (__float_as_int(__ldg(&q[4].x)) & 3) == PRIM_SPHERE;
+            const float4 q0 = __ldg(q);
+            float tt;
+            bool front = true, ok;
+            if (sphere)
+                ok = sphere_roots<FLIGHT>(q0, __fmul_rn(q0.w, q0.w), o, d, tmin, t.h.t, tt);
+            else
+                ok = rect_test_q(q0, __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), o, d, tmin, t.h.t, false, tt, front);
+            if (ok && (tt < t.h.t || bvh_tie_take(prims, t.h.prim, (int)(first + i)))) {
                 t.h.t = tt;
                 t.h.prim = (int)(first + i);
-                t.h.face = type == PRIM_SPHERE ? 8 : (front ? 0 : 1);
-                t.best_canon = canon;
-                t.best_strict = strict;
+                t.h.face = sphere ? 8 : (front ? 0 : 1);
             }
         }
     }

@@ -30,10 +30,12 @@ enum { PRIM_CANON_SHIFT = 4 };
 //   a 4-wide inner node holds the boxes of its (up to) four children, one float4 per bound and axis, so a child is
 //   only visited when its box is hit and one fetch decides four subtrees:
 //   n0 = min.x[0..3]  n1 = max.x[0..3]  n2 = min.y  n3 = max.y  n4 = min.z  n5 = max.z  n6 = child references  n7 = -
-//   child reference: inner node index, BVH_LEAF | count << 24 | first record (count <= 127), or BVH_EMPTY
+//   child reference: inner node index, BVH_LEAF | kind << 29 | count << 24 | first record (count <= BVH_LEAF_MAX;
+//   kind: BVH_KIND_SPHERES / BVH_KIND_RECTS when every record of the leaf is a sphere / none is, else 0), or BVH_EMPTY
 //   Traversal stack: BVH_STACK_SMEM entries per lane in shared memory, the (rarely reached) rest up to BVH_STACK in
 //   local memory; the builder keeps the tree shallow enough that 3 pushes per level never exceed BVH_STACK.
-enum { BVH_STRIDE = 8, BVH_WIDTH = 4, BVH_LEAF = 0x80000000u, BVH_EMPTY = 0xfffffffeu, BVH_STACK_SMEM = 16, BVH_STACK = 40, BVH_MAX_DEPTH2 = 24 };
+enum { BVH_STRIDE = 8, BVH_WIDTH = 4, BVH_LEAF = 0x80000000u, BVH_EMPTY = 0xfffffffeu, BVH_STACK_SMEM = 16, BVH_STACK = 40, BVH_MAX_DEPTH2 = 24,
+       BVH_LEAF_MAX = 31, BVH_KIND_SPHERES = 1, BVH_KIND_RECTS = 2 };
 
 // ---- material record: MAT_STRIDE float4 (reference src/scene/data/material.rs:22-44) -------
 //   m0 = (albedo.rgb, kind)   m1 = (roughness, ior, intensity, -)

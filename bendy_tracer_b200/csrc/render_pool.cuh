@@ -51,7 +51,7 @@ struct Pool {
     uint4 *qa, *qb;             // Q: xoshiro256++ state
     float4* qc;                 //    (T, misc)   misc = ring index | latched << 4 | (vol_obj + 1) << 5 | bounce << 12 | volume bounce << 20
     float4 *qe, *qf;            //    AOV latches (albedo, depth) (normal, -)   [CT_AOV kernels]
-    uint2* tv;                  // BVH: (node reference, stack height | best hit strict << 6 | (best hit's canonical index + 1) << 7)
+    uint2* tv;                  // BVH: (node reference, stack height)
     uint32_t* bstack;           // BVH: traversal stacks (BvhStack: stride P, POOL_BVH_K levels)
     uint2* bover;               // BVH: the stack levels beyond, BVH_STACK - POOL_BVH_K per slot (arena)
     uint8_t *st, *list, *stack, *ring;
@@ -277,7 +277,7 @@ BT_DEV void render_pool_body(const RenderParams& p) {
                 const V3 o = v3(a), d = v3(b);
                 BvhTrav t;
                 t.cur = tv.x;
-                t.sp = tv.y & 63u;
+                t.sp = tv.y;
                 t.h.t = a.w;
                 BvhStack bs;
                 bs.base = pl.bstack;
@@ -289,7 +289,7 @@ BT_DEV void render_pool_body(const RenderParams& p) {
                 const uint32_t sgn = bvh_signs(inv);
 #pragma unroll 1
                 for (uint32_t r = 0; r < p.steps_per_turn && !(t.cur & BVH_LEAF); ++r) bvh_node(t, sc.nodes, bs, o, inv, sgn, p.clip_min);
-                pl.tv[slot] = make_uint2(t.cur, (tv.y & ~63u) | t.sp);
+                pl.tv[slot] = make_uint2(t.cur, t.sp);
                 if (t.cur == BVH_DONE) {
                     pl.st[slot] = ST_HIT_STRAIGHT;
                     resolved = true;
@@ -319,11 +319,9 @@ BT_DEV void render_pool_body(const RenderParams& p) {
                 const V3 o = v3(a), d = v3(b);
                 BvhTrav t;
                 t.cur = tv.x;
-                t.sp = tv.y & 63u;
+                t.sp = tv.y;
                 t.h.t = a.w;
                 unpack_hit(__float_as_uint(b.w), t.h);
-                t.best_strict = ((tv.y >> 6) & 1u) != 0;
-                t.best_canon = (int)(tv.y >> 7) - 1;
                 BvhStack bs;
                 bs.base = pl.bstack;
                 bs.stride = P;
@@ -333,7 +331,7 @@ BT_DEV void render_pool_body(const RenderParams& p) {
                 bvh_leaf(t, sc.prims, bs, o, d, p.clip_min);
                 pl.fa[slot].w = t.h.t;
                 pl.fb[slot].w = __uint_as_float(pack_hit(t.h));
-                pl.tv[slot] = make_uint2(t.cur, t.sp | (t.best_strict ? 64u : 0u) | ((uint32_t)(t.best_canon + 1) << 7));
+                pl.tv[slot] = make_uint2(t.cur, t.sp);
                 if (t.cur == BVH_DONE) {
                     pl.st[slot] = ST_HIT_STRAIGHT;
                     resolved = true;

@@ -915,7 +915,7 @@ bool make_box(const Object& o, const Affine& tf, float4 out[BOX_STRIDE]) {
     return true;
 }
 
-// ---- binned-SAH build of a binary tree (<= 4 primitives per leaf), collapsed to the 4-wide nodes the device reads -----
+// ---- binned-SAH build of a binary tree (one primitive per leaf), collapsed to the 4-wide nodes the device reads -----
 struct BvhBuild {
     const std::vector<Bounds>& b;
     std::vector<uint32_t> order;   // record position -> canonical primitive index
@@ -949,7 +949,13 @@ struct BvhBuild {
         }
         return box;
     }
-    static uint32_t leaf_ref(uint32_t first, uint32_t count) { return BVH_LEAF | (count << 24) | first; }
+    std::vector<uint8_t> sphere;   // per canonical primitive: is it a sphere record (leaf kinds)
+    uint32_t leaf_ref(uint32_t first, uint32_t count) const {
+        uint32_t n_sph = 0;
+        for (uint32_t i = first; i < first + count; ++i) n_sph += order[i] < sphere.size() && sphere[order[i]];
+        const uint32_t kind = count == 0 ? 0u : (n_sph == count ? (uint32_t)BVH_KIND_SPHERES : (n_sph == 0 ? (uint32_t)BVH_KIND_RECTS : 0u));
+        return BVH_LEAF | (kind << 29) | (count << 24) | first;
+    }
     void set_inner(uint32_t self, uint32_t left, const Bounds& l, uint32_t right, const Bounds& r) {  // (unpadded boxes)
         nodes[self * STRIDE2] = f4(l.lo[0], l.lo[1], l.lo[2], l.hi[0]);
         nodes[self * STRIDE2 + 1] = f4(l.hi[1], l.hi[2], r.lo[0], r.lo[1]);
@@ -971,7 +977,7 @@ struct BvhBuild {
         r->box.lo[0] = q[1].z; r->box.lo[1] = q[1].w; r->box.lo[2] = q[2].x; r->box.hi[0] = q[2].y; r->box.hi[1] = q[2].z; r->box.hi[2] = q[2].w;
     }
     static bool is_inner(uint32_t ref) { return !(ref & BVH_LEAF); }
-    static bool is_empty_leaf(uint32_t ref) { return (ref & BVH_LEAF) && ((ref >> 24) & 0x7fu) == 0; }
+    static bool is_empty_leaf(uint32_t ref) { return (ref & BVH_LEAF) && ((ref >> 24) & 0x1fu) == 0; }
     static void write_wide(float4* q, const Child* c, int n) {  // (pads the boxes)
         float v[6][4];
         uint32_t ref[4];
@@ -1034,11 +1040,14 @@ struct BvhBuild {
             if (cb.hi[k] - cb.lo[k] > cb.hi[axis] - cb.lo[axis]) axis = k;
         // The traversal stack bounds the depth (layout.h: 3 pushes per wide level = per two levels here).  A skewed SAH split is only taken while median splits could
         // still bring what remains down to leaf size; coincident centroids (no axis to split on) are halved by
-        // index -- a leaf holds at most 127 records.
+        // index -- a leaf holds at most BVH_LEAF_MAX records.
         const int remaining = (int)BVH_MAX_DEPTH2 - 2 - depth;
         const bool degenerate = !(cb.hi[axis] > cb.lo[axis]);
-        if (count <= 4 || remaining <= 0 || (degenerate && count <= 127)) {
-            if (count > 127) throw SceneError("BVH: the scene is too large for the traversal stack");
+        // one primitive per leaf: measured 1 / 2 / 3 / 4 / 6 / 8 -> 270 / 252 / 255 / 244 / 232 / 222 Msamples/s on the 32 k-primitive scene (a
+        // leaf test is a divergent loop over records of mixed type; a node visit is four uniform slab tests).  BT_BVH_LEAF: experiments.
+        static const uint32_t leaf_max = std::getenv("BT_BVH_LEAF") ? (uint32_t)std::max(1, std::atoi(std::getenv("BT_BVH_LEAF"))) : 1u;
+        if (count <= leaf_max || remaining <= 0 || (degenerate && count <= (uint32_t)BVH_LEAF_MAX)) {
+            if (count > (uint32_t)BVH_LEAF_MAX) throw SceneError("BVH: the scene is too large for the traversal stack");
             return leaf_ref(first, count);
         }
         const bool force_median = degenerate || (uint64_t)count > ((uint64_t)64 << std::max(0, remaining - 2));
@@ -1441,6 +1450,7 @@ FlatScene flatten(const Scene& scene, int accel) {
     for (uint32_t i = 0; i < h.n_prims; ++i) fs.prim_order.push_back(i);
     if (use_bvh && h.n_prims > 0) {
         BvhBuild bvh(bounds);
+        for (uint32_t i = 0; i < h.n_prims; ++i) bvh.sphere.push_back((as_u(prims[(size_t)i * PRIM_STRIDE + 4].x) & 3u) == (uint32_t)PRIM_SPHERE);
         // primitives that span a large part of the scene (a ground sphere of radius 100 ...) would
         // bloat every node they fall into: they go to one leaf beside the tree of the rest
         std::vector<float> diag(h.n_prims);
@@ -1456,13 +1466,12 @@ FlatScene flatten(const Scene& scene, int accel) {
                                                           [&](uint32_t i) { return diag[i] > big_cut; }) - bvh.order.begin());
         Bounds all = BvhBuild::empty();
         for (uint32_t i = 0; i < h.n_prims; ++i) BvhBuild::grow(all, bounds[i]);
-        if (n_big == 0 || n_big == h.n_prims) n_big = 0;
+        if (n_big == h.n_prims || n_big > (uint32_t)BVH_LEAF_MAX) n_big = 0;  // (too many to sit in one leaf: no special case)
         // node 0 is always an inner node: (left = big-primitive leaf or empty leaf, right = the tree)
         bvh.make_inner(0, all, 0, all);
         Bounds rest_box;
         uint32_t rest = bvh.build(n_big, h.n_prims - n_big, 1, &rest_box);
-        uint32_t big = BvhBuild::leaf_ref(0, n_big);
-        if (n_big > 127) throw SceneError("BVH: more than 127 scene-spanning primitives");
+        uint32_t big = bvh.leaf_ref(0, n_big);
         if (h.n_prims >= 0x00fffff0u) throw SceneError("BVH: too many primitives for a leaf reference");
         bvh.set_inner(0, big, n_big ? all : BvhBuild::empty(), rest, rest_box);
         bvh.collapse(0);  // wide node 0 = the root
@@ -1548,7 +1557,7 @@ void refit_bvh(FlatScene& fs) {
     auto child_box = [&](uint32_t ref) {
         if (!(ref & BVH_LEAF)) return own[ref];
         Bounds b = BvhBuild::empty();
-        const uint32_t first = ref & 0x00ffffffu, count = (ref >> 24) & 0x7fu;
+        const uint32_t first = ref & 0x00ffffffu, count = (ref >> 24) & 0x1fu;
         for (uint32_t pos = first; pos < first + count; ++pos) BvhBuild::grow(b, fs.prim_bounds[fs.prim_order[pos]]);
         return b;
     };

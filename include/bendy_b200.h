@@ -185,7 +185,8 @@ int bt_scene_set_precision(bt_scene* scene, int precision);
 int bt_scene_get_info(const bt_scene* scene, bt_scene_info* info);
 /* Introspection of the acceleration structure (tests, tools; an extension like the BVH itself): copies the 4-wide nodes
  * (32 floats per node: min.x[4] max.x[4] min.y[4] max.y[4] min.z[4] max.z[4], four child references as raw 32-bit
- * patterns, four unused -- child: inner node index, 0x80000000 | count << 24 | first record, or 0xfffffffe = empty), the
+ * patterns, four unused -- child: inner node index, 0x80000000 | kind << 29 | count << 24 | first record (kind 1: all
+ * spheres, 2: no sphere, 0: mixed; count <= 31), or 0xfffffffe = empty), the
  * record order (tree position -> canonical primitive index) and the primitives' bounds (6 floats each: min xyz, max
  * xyz, canonical order) as of the last flatten / commit.  Any pointer may be NULL; capacities in nodes / primitives;
  * BT_ERR_INVALID_ARG when one is too small (bt_scene_get_info gives the counts). */

@@ -582,7 +582,7 @@ def test_bvh_equals_linear_scan_on_shipped_scenes(name, lens):
 
 
 def test_bvh_deep_narrow_tree_equals_linear_scan():
-    """Coincident spheres (leaves of up to 127 records) and a geometric chain of disjoint spheres (every SAH split
+    """Coincident spheres (leaves of up to 31 records, exact-distance ties on every ray that meets them) and a geometric chain of disjoint spheres (every SAH split
     lopsided: a deep, narrow tree): BVH == linear scan bit for bit in the exact flavour -- through the lane kernel and
     the pooled traversal, with the stack in shared memory and with all but one level of it in its slow tail."""
     import json

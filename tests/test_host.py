@@ -416,7 +416,7 @@ def test_bvh_build_survives_skewed_and_coincident_primitives():
     assert info["n_primitives"] == 402 and info["n_bvh_nodes"] > 3
 
 
-def _check_bvh(sc, max_depth=11):
+def _check_bvh(sc, max_depth=11, types=None):
     """structural invariants of the 4-wide BVH (bt_scene_copy_bvh): every primitive in exactly one leaf, every child box
     holds what is below it (conservatively padded), empty slots last, children stored behind their parent, depth and
     stack demand within what the traversal kernels allocate"""
@@ -444,9 +444,12 @@ def _check_bvh(sc, max_depth=11):
             assert not empty_seen, "an empty slot before a child"
             box_lo, box_hi = nodes[node, 0:6:2, c], nodes[node, 1:6:2, c]
             if r & LEAF:
-                first, count = r & 0xFFFFFF, (r >> 24) & 0x7F
-                assert 1 <= count <= 127 and first + count <= n_prims
+                first, count, kind = r & 0xFFFFFF, (r >> 24) & 0x1F, (r >> 29) & 3
+                assert 1 <= count <= 31 and first + count <= n_prims
                 prims = order[first:first + count]
+                if types is not None:         # the leaf's kind: 1 = all spheres, 2 = no sphere, 0 = mixed
+                    sph = int(types[prims].sum())
+                    assert kind == (1 if sph == count else 2 if sph == 0 else 0), (kind, sph, count)
                 seen[first:first + count] += 1
                 c_lo, c_hi = bounds[prims, :3].min(0), bounds[prims, 3:].max(0)
             else:
@@ -469,10 +472,20 @@ def _check_bvh(sc, max_depth=11):
 
 def test_bvh4_structure_and_refit():
     from common import skewed_scene, synthetic_scene
+    def record_types(doc):          # 1 per sphere record, 0 per rect / cuboid-face record, in canonical (ascending ObjectRef) order
+        out = []
+        for key in sorted(doc["objects"]["collection"], key=int):
+            inner = doc["objects"]["collection"][key]["inner"]
+            kind = inner if isinstance(inner, str) else next(iter(inner))
+            out += {"Sphere": [1], "Rect": [0], "Cuboid": [0] * 6}.get(kind, [])
+        return np.array(out, np.int32)
+
     for doc in (synthetic_scene(300, 100, 20, seed=4), synthetic_scene(3000, 500, 100, seed=5, extent=6.0), skewed_scene(), skewed_scene(120, 60, 0.3)):
         sc = bt.Scene.from_json(json.dumps(doc))
         sc.set_accel("bvh")
-        _check_bvh(sc)
+        types = record_types(doc)
+        assert len(types) == sc.info()["n_primitives"]
+        _check_bvh(sc, types=types)
     # a shipped scene forced onto the BVH (a scene-spanning ground sphere goes to its own leaf beside the tree)
     sc = bt.Scene.load(O.scene_path("scene"))
     sc.set_accel("bvh")
