@@ -1051,38 +1051,45 @@ struct BvhBuild {
             return leaf_ref(first, count);
         }
         const bool force_median = degenerate || (uint64_t)count > ((uint64_t)64 << std::max(0, remaining - 2));
-        // binned SAH on the widest centroid axis
+        // binned SAH: the cheapest of the candidate planes of all three axes (env BT_BVH_SAH_AXES=1: the widest centroid axis only)
         const int NB = 16;
-        Bounds bin_box[NB];
-        uint32_t bin_n[NB];
-        for (int i = 0; i < NB; ++i) { bin_box[i] = empty(); bin_n[i] = 0; }
-        const float scale = degenerate ? 0.0f : (float)NB / (cb.hi[axis] - cb.lo[axis]);
-        auto bin_of = [&](uint32_t prim) {
-            int k = (int)((0.5f * (b[prim].lo[axis] + b[prim].hi[axis]) - cb.lo[axis]) * scale);
+        static const bool all_axes = !(std::getenv("BT_BVH_SAH_AXES") && std::atoi(std::getenv("BT_BVH_SAH_AXES")) == 1);
+        const int widest = axis;
+        int best = -1, best_axis = widest;
+        float best_cost = 3.0e38f;
+        auto bin_on = [&](uint32_t prim, int ax) {
+            const float ext = cb.hi[ax] - cb.lo[ax];
+            int k = (int)((0.5f * (b[prim].lo[ax] + b[prim].hi[ax]) - cb.lo[ax]) * (ext > 0.0f ? (float)NB / ext : 0.0f));
             return std::min(std::max(k, 0), NB - 1);
         };
-        for (uint32_t i = first; i < first + count; ++i) {
-            int k = bin_of(order[i]);
-            grow(bin_box[k], b[order[i]]);
-            bin_n[k]++;
+        for (int ax = 0; ax < 3 && !degenerate; ++ax) {
+            if (!(all_axes || ax == widest) || !(cb.hi[ax] > cb.lo[ax])) continue;
+            Bounds bin_box[NB];
+            uint32_t bin_n[NB];
+            for (int i = 0; i < NB; ++i) { bin_box[i] = empty(); bin_n[i] = 0; }
+            for (uint32_t i = first; i < first + count; ++i) {
+                int k = bin_on(order[i], ax);
+                grow(bin_box[k], b[order[i]]);
+                bin_n[k]++;
+            }
+            float right_area[NB];
+            Bounds acc = empty();
+            for (int i = NB - 1; i > 0; --i) {
+                grow(acc, bin_box[i]);
+                right_area[i] = area(acc);
+            }
+            acc = empty();
+            uint32_t nl = 0;
+            for (int i = 0; i < NB - 1; ++i) {
+                grow(acc, bin_box[i]);
+                nl += bin_n[i];
+                if (nl == 0 || nl == count) continue;
+                float cost = area(acc) * (float)nl + right_area[i + 1] * (float)(count - nl);
+                if (cost < best_cost) { best_cost = cost; best = i; best_axis = ax; }
+            }
         }
-        float right_area[NB];
-        Bounds acc = empty();
-        for (int i = NB - 1; i > 0; --i) {
-            grow(acc, bin_box[i]);
-            right_area[i] = area(acc);
-        }
-        acc = empty();
-        uint32_t nl = 0;
-        int best = -1;
-        float best_cost = 3.0e38f;
-        for (int i = 0; i < NB - 1; ++i) {
-            grow(acc, bin_box[i]);
-            nl += bin_n[i];
-            if (nl == 0 || nl == count) continue;
-            float cost = area(acc) * (float)nl + right_area[i + 1] * (float)(count - nl);
-            if (cost < best_cost) { best_cost = cost; best = i; }
-        }
+        if (best >= 0 && !force_median) axis = best_axis;
+        auto bin_of = [&](uint32_t prim) { return bin_on(prim, axis); };
         uint32_t mid;
         if (best >= 0 && !force_median) {
             mid = (uint32_t)(std::partition(order.begin() + first, order.begin() + first + count,
