@@ -356,7 +356,7 @@ int build_params(const bt_engine* en, bt_scene* s, const SceneDev* dev, uint64_t
     // every ~50 turns per lane: small batches keep lanes flying; a marching volume wants larger ones.
     const bool long_flights = p.scene.n_lens != 0 && !p.scene.has_volume_prims;
     p.compact_lanes = knob(tn.compact_lanes, long_flights ? 12 : 16);
-    const bool bvh_rays = p.scene.n_bvh != 0 && p.scene.n_lens == 0;  // (patience counts node / leaf units there; gpurun_out/r2_sweep_bvh4.log)
+    const bool bvh_rays = p.scene.n_bvh != 0 && p.scene.n_lens == 0;  // (patience counts node / leaf units there; profiles/r2_sweep_bvh.md)
     p.compact_patience = knob(tn.compact_patience, long_flights ? 8 : (bvh_rays ? 32 : 16));
     // A scan over a handful of surface primitives costs less than half a ray generation: such a warp
     // is better off collecting more idle lanes first (scene.json.gz: +4.6 %, profiles/r1_sweep_regen2.log).
@@ -377,7 +377,7 @@ int build_params(const bt_engine* en, bt_scene* s, const SceneDev* dev, uint64_t
     // flat ones, whose scan -> shade ping-pong gains nothing from compaction and pays for the state traffic (C2 -12 %)
     // -- except BVH scenes, whose traversal runs as pooled NODE / LEAF phases (32 k primitives: 238 against 221 Msamples/s; W = 3 of {1, 2, 3, 4})
     p.pool_w = std::min(knob(tn.pool_w, p.scene.n_lens != 0 ? 4 : (bvh_rays ? 3 : 0)), 8u);
-    p.pool_refill = std::max(1u, knob(tn.pool_refill, 3));   // (gpurun_out/r2_sweep_pool_C3c.log: 3 / 32 best of {3, 6, 9} x {24, 28, 32})
+    p.pool_refill = std::max(1u, knob(tn.pool_refill, 3));   // (profiles/r2_sweep_pool_C3.log: 3 / 32 best of {3, 6, 9} x {24, 28, 32})
     p.pool_step_min = knob(tn.pool_step_min, 32);
     p.pool_threads = knob(tn.pool_threads, 0) & ~31u;  // 0: the kernel's own CTA size (launch_pool)
     p.bvh_stack_k = std::max(1u, knob(tn.bvh_stack_k, 0xffffu));  // (tests: force the traversal stack's tail)
